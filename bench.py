@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — LLaMA-7B FP32 decode tokens/sec on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): LLaMA-7B FP32, context 512, predict 128 — a 384-token
+synthetic prompt is prefilled (untimed setup), then single-token decode steps are timed.
+A "step" = one decoded token per in-flight sequence (N sequences at N GPUs).
+  value : whole-job decode tokens/s, tokens/KV/weights resident in HBM, K CUDA-graph replays timed
+          with CUDA events on the engine's stream (lb_decode_resident).
+  e2e   : the same K steps through the public API lb_eval() with HOST buffers: token id H2D and
+          128 KB logits D2H inside the timed region, one synchronous call per token.
+  roofline    : dominant kernel (w1/w3 SwiGLU GEMV) algorithmic bytes / CUDA-event time vs measured HBM peak.
+  cpu_baseline: the reference's own binary (--avx, all host threads) on a bounded sample.
+--impl reference times the reference's own CPU implementation (oracle/_ref/llama-go-linux).
+Weights (26.4 GB/token) are far larger than L2 (126 MB): no flush needed between iterations.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LLaMA-7B FP32 decode tokens/sec"
+UNIT = "tokens/s"
+PROMPT_LEN = 384
+CTX = 512
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def _scratch_dir(need_bytes):
+    for d in ("/dev/shm", tempfile.gettempdir(), ROOT):
+        try:
+            if shutil.disk_usage(d).free > need_bytes * 1.2:
+                return tempfile.mkdtemp(prefix="lb_ref_", dir=d)
+        except Exception:
+            continue
+    return tempfile.mkdtemp(prefix="lb_ref_")
+
+
+def reference_cpu_decode(steps, warmup, threads=None):
+    """Time the reference's own CPU path on this box's host cores.
+
+    Bounded sample: the reference binary (--avx, all host threads) decodes `warmup+steps` tokens on
+    LLaMA-7B-SHAPED models with 2 and with 4 layers (same dims/heads/ff/vocab, same synthetic
+    weights as the GPU arm's seed 0); per-token time is linear in the layer count
+    (t = t_head + L * t_layer), so the full 32-layer figure is extrapolated from the
+    two measurements.  Falls back to the C oracle (kind "port") if the binary is not in oracle/_ref.
+    """
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import synth
+    from oracle import refbin
+    threads = threads or os.cpu_count() or 1
+    dims = (32000, 4096, 256, 32)
+    prompt = "abcde"                       # BOS + 2 spaces + 5 bytes = 8 tokens (>= 8 for --avx)
+    n_prompt = 8
+    predict = warmup + steps + 1           # 1 prompt eval + (predict-1) single-token evals
+    context = n_prompt + predict + 8
+    per_token_ms = {}
+    if refbin.available():
+        kind = "reference"
+        td = _scratch_dir(4.4e9 + 2.8e9)
+        try:
+            hp4 = synth.HParams(*dims, 4)
+            tensors4 = list(synth.synth_model_fast(0, hp4))
+            for L in (2, 4):
+                hp = synth.HParams(*dims, L)
+                names = {n for n, *_ in synth.tensor_table(hp)}
+                path = os.path.join(td, f"m{L}.bin")
+                synth.write_ggjt(path, hp, [(n, a) for n, a in tensors4 if n in names])
+                r = refbin.run(path, prompt, predict, context, threads, True, port=18090 + L, timeout=3000)
+                dec = r["eval_ms"][1:][warmup:warmup + steps]
+                if len(dec) < max(1, steps // 2):
+                    raise RuntimeError("reference binary produced no timing report:\n" + r["raw"][-2000:].decode("utf-8", "replace"))
+                per_token_ms[L] = float(np.mean(dec))
+                os.unlink(path)
+        finally:
+            shutil.rmtree(td, ignore_errors=True)
+    else:
+        kind = "port"
+        from oracle import oracle as O
+        O.build(); O.set_dot_mode(True); O.set_threads(threads)
+        for L in (2, 4):
+            hp = synth.HParams(*dims, L)
+            om = O.OracleModel(hp).load(synth.synth_model_fast(0, hp))
+            oc = O.OracleContext(om, context)
+            oc.eval(synth.prompt_token_ids(prompt.encode()), 0)
+            ts = []
+            for i in range(min(warmup + steps, 12)):
+                t0 = time.perf_counter(); oc.eval([5 + i], n_prompt + i); ts.append((time.perf_counter() - t0) * 1e3)
+            per_token_ms[L] = float(np.mean(ts[min(warmup, len(ts) - 1):]))
+        O.set_dot_mode(False)
+    t_layer = (per_token_ms[4] - per_token_ms[2]) / 2.0
+    t_head = per_token_ms[2] - 2.0 * t_layer
+    t_full = t_head + 32.0 * t_layer
+    return {
+        "tok_s": 1000.0 / t_full, "ms_per_token": t_full, "kind": kind, "cores": threads,
+        "sample": (f"reference binary --avx --threads {threads}: {steps} single-token decodes (after {warmup} warm-up) on "
+                   f"7B-shaped 2-layer ({per_token_ms[2]:.1f} ms/token) and 4-layer ({per_token_ms[4]:.1f} ms/token) "
+                   f"models, extrapolated to 32 layers as t_head + 32*t_layer ({t_head:.1f} + 32*{t_layer:.2f} ms)"),
+    }
+
+
+def run_reference(args):
+    rank, world, _ = rank_world()
+    if rank != 0:
+        return
+    r = reference_cpu_decode(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["tok_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_token"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LLaMA-7B FP32 single-sequence decode (reference CPU path, --avx)", "l2": "inputs>L2"},
+        "cpu_baseline": {"value": r["tok_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["tok_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
+
+
+def run_single_gpu(args):
+    import ctypes as C
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import _capi, llama, synth
+    _capi.require_gpu()
+    lib = _capi.lib()
+    hp = synth.LLAMA_7B
+    K, W = args.steps, args.warmup
+    ctx_size = max(CTX, PROMPT_LEN + 2 * W + K + 1)
+    t_setup = time.time()
+    model = llama.Model(hp).init_random(0)
+    lctx = llama.NewContext(model, ctx_size)
+    rs = np.random.RandomState(0)
+    prompt = rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32)
+    gen = rs.randint(3, hp.vocab, size=W + K).astype(np.uint32)
+    llama.Eval(lctx, prompt, 0)                         # prefill (setup, untimed)
+    t_setup = time.time() - t_setup
+
+    # ---- value: device-resident decode, CUDA events on the engine's stream
+    llama.DecodeResident(lctx, gen[:max(W, 1)], PROMPT_LEN)           # warm-up (also captures the CUDA graph)
+    check = lib.lb_context_synchronize
+    check(lctx._h)
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = lib.lb_kernel_launches()
+    ms = llama.DecodeResident(lctx, gen[W:W + K], PROMPT_LEN + W)
+    check(lctx._h)
+    launches = lib.lb_kernel_launches() - l0
+    value = K / (ms / 1e3)
+
+    # ---- e2e: public API, host buffers, one synchronous lb_eval per token
+    for i in range(W):
+        llama.Eval(lctx, gen[i:i + 1], PROMPT_LEN + i)
+    check(lctx._h)
+    t0 = time.perf_counter()
+    for i in range(K):
+        llama.Eval(lctx, gen[W + i:W + i + 1], PROMPT_LEN + W + i)
+    check(lctx._h)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    e2e = K / e2e_s
+
+    # ---- roofline of the dominant kernel + per-kernel table (live CUDA-event timing)
+    peak, peak_src = measured_peak()
+    names = {0: "gemv qkv [12288x4096]", 1: "gemv wo+res [4096x4096]", 2: "gemv_swiglu w1,w3 [2x11008x4096]",
+             3: "gemv w2+res [4096x11008]", 4: "gemv lm_head [32000x4096]", 5: "attention T=%d" % (PROMPT_LEN + W + K // 2),
+             6: "rmsnorm [4096]"}
+    kern = {}
+    for which in range(7):
+        msk, by = C.c_float(0), C.c_uint64(0)
+        _capi.check(lib.lb_bench_kernel(lctx._h, which, 64, PROMPT_LEN + W + K // 2, C.byref(msk), C.byref(by)))
+        us = msk.value * 1e3 / 64
+        kern[names[which]] = {"us": round(us, 2), "bytes": by.value, "GB/s": round(by.value / us / 1e3, 1)}
+    dom = kern[names[2]]
+    T_mid = PROMPT_LEN + W + K / 2.0
+    bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+    step_gbs = bytes_per_token * value / 1e9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            r = reference_cpu_decode(steps=12, warmup=2)
+            cpu = {"value": r["tok_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # the baseline is reported, never the target; do not lose the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LLaMA-7B FP32 single-sequence decode, context %d, %d-token prompt prefilled, past %d..%d"
+                               % (ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
+                   "weights": "random-init (device RNG, seed 0) 26.4 GB", "kv_cache": "fp32 in HBM",
+                   "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (26.4 GB weights per step)",
+                   "setup_s": round(t_setup, 1)},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 + 8, "d2h_bytes_per_step": 4 * hp.vocab,
+                "api": "lb_eval (C-ABI, host buffers, synchronous)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "gemv_swiglu_kernel (w1,w3)", "achieved": dom["GB/s"], "peak": peak,
+                     "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4), "traffic": kernel_traffic("gemv_swiglu_kernel"),
+                     "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]},
+        "step_roofline": {"bytes_per_token": int(bytes_per_token), "achieved_GBs": round(step_gbs, 1),
+                          "frac": round(step_gbs / peak, 4), "roofline_tok_s": round(peak * 1e9 / bytes_per_token, 1)},
+        "kernels": kern,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    rank, world, _ = rank_world()
+    if world > 1 or args.gpus > 1:
+        from bench_pipeline import run_pipeline   # layer-sharded multi-GPU arm
+        return run_pipeline(args)
+    return run_single_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/*
+ * llamab200.h — C-ABI of the B200-native LLaMA forward-pass engine.
+ *
+ * Drop-in boundary for the hot path of gotzmann/llama.go: the exported Go API of
+ * pkg/ml (Tensor, op constructors, Graph, GraphCompute) and pkg/llama (NewContext, Eval).
+ * The reference has no FFI of its own (CGO_ENABLED=0, Makefile:25; the only foreign call is
+ * the Go-asm stub vdot, pkg/ml/floats_avx.go:28), so these are the entry points a cgo shim
+ * placed under pkg/ml and pkg/llama binds (INTEGRATION.md shows that shim).  Plain pointers
+ * and sizes only; no torch, no C++ types.
+ *
+ * Conventions
+ *   - Every function that can fail returns int: 0 = OK, non-zero = error; the message is in
+ *     lb_last_error() (thread-local).  Constructors return NULL on error.  The reference's
+ *     behaviour on the same conditions is print "[HALT] ..." + os.Exit(1) (e.g. ml.go:254-257,
+ *     2116-2124); the Go shim maps a non-zero status back to that.
+ *   - Host pointers are only read/written during the call and never retained (cgo rule).
+ *   - lb_model is immutable after load and may be shared; each lb_context owns its KV cache
+ *     and CUDA stream and is single-threaded, many may run concurrently ("pods",
+ *     pkg/server/server.go:84-106).
+ *   - There is NO CPU fallback: every entry point fails if no sm_100 device is usable.
+ */
+#ifndef LLAMAB200_H
+#define LLAMAB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_API __attribute__((visibility("default")))
+
+/* dtype codes = ml.DType (pkg/ml/ml.go:85-94) */
+enum { LB_TYPE_F32 = 0, LB_TYPE_F16 = 1, LB_TYPE_Q4_0 = 2, LB_TYPE_Q4_1 = 3, LB_TYPE_I8 = 4,
+       LB_TYPE_I16 = 5, LB_TYPE_I32 = 6,
+       LB_TYPE_Q8_0 = 16 /* this repo's block format: 32 int8 + fp32 scale, see DESIGN.md */ };
+
+typedef struct lb_model   lb_model;    /* = llama.Model   (pkg/llama/llama.go:181-193) */
+typedef struct lb_context lb_context;  /* = llama.Context (pkg/llama/llama.go:83-88)   */
+typedef struct lb_mlctx   lb_mlctx;    /* = ml.Context    (pkg/ml/ml.go:50-57)         */
+typedef struct lb_tensor  lb_tensor;   /* = ml.Tensor     (pkg/ml/ml.go:180-203)       */
+typedef struct lb_graph   lb_graph;    /* = ml.Graph      (pkg/ml/ml.go:31-45)         */
+
+/* HParams (pkg/llama/llama.go:149-158); ff is derived as in llama.go:761 */
+typedef struct {
+    uint32_t vocab, dim, mult, heads, layers;
+} lb_hparams;
+
+/* ---- library -------------------------------------------------------------------------- */
+LB_API const char *lb_last_error(void);
+LB_API int         lb_device_count(void);          /* usable sm_100 devices; <=0 => nothing works */
+LB_API const char *lb_version(void);
+LB_API uint64_t    lb_kernel_launches(void);       /* kernels launched by this library so far (process-wide) */
+
+/* ---- model = llama.Model + LoadModel's tensor map (llama.go:712-976) ------------------ */
+/* Layers [layer_begin, layer_end) live on `device`; the stage with layer_begin == 0 also owns
+ * tok_embeddings, the stage with layer_end == layers also owns norm + output.
+ * weight_type: LB_TYPE_F32, or LB_TYPE_Q8_0 to hold the 2-D matrices block-quantised. */
+LB_API lb_model *lb_model_create(const lb_hparams *hp, int device, uint32_t layer_begin,
+                                 uint32_t layer_end, int weight_type);
+LB_API void      lb_model_free(lb_model *m);
+/* name = ggjt tensor name (llama.go:826-861); dtype LB_TYPE_F32 or LB_TYPE_F16 (widened to FP32
+ * like llama.go:938-941); tensors of layers this stage does not own are accepted and ignored. */
+LB_API int       lb_model_set_tensor(lb_model *m, const char *name, int dtype, const void *host, size_t nbytes);
+LB_API int       lb_model_get_tensor(lb_model *m, const char *name, float *host, size_t nelem); /* dequantised */
+/* Synthetic weights generated on the device; bit-identical to llama.go_b200/synth.py. */
+LB_API int       lb_model_init_random(lb_model *m, uint64_t seed);
+LB_API uint64_t  lb_model_weight_bytes(const lb_model *m);   /* bytes one decoded token streams */
+/* Host-side generator of the same synthetic weights (elements [start, start+count) of tensor
+ * `tensor_id`), multi-threaded; used to write ggjt files for the reference binary quickly.
+ * Pure host code: works without a GPU. */
+LB_API int       lb_synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tensor_id,
+                                    uint64_t start, float mean, double sigma);
+/* Micro-benchmark of one hot-path kernel for the roofline report: launches kernel `which`
+ * (0 qkv gemv, 1 wo gemv+residual, 2 w1/w3 swiglu gemv, 3 w2 gemv+residual, 4 lm_head gemv,
+ * 5 attention at `past`, 6 rmsnorm) `iters` times back to back on the context's stream, cycling
+ * through the layers so the weights never sit in L2; ms_out = CUDA-event time of all launches,
+ * bytes_out = algorithmic bytes of ONE launch. */
+LB_API int       lb_bench_kernel(lb_context *c, int which, uint32_t iters, uint32_t past, float *ms_out,
+                                 uint64_t *bytes_out);
+
+/* ---- context = llama.NewContext / ReleaseContext / Eval (llama.go:91-113, 211-426) ---- */
+LB_API lb_context *lb_context_create(lb_model *m, uint32_t ctx_size);
+LB_API void        lb_context_free(lb_context *c);
+/* llama.Eval: evaluate `n` new tokens at position `past`; logits_out receives row n-1 ([vocab]).
+ * Host buffers; H2D of the ids and D2H of the logits happen inside the call. */
+LB_API int lb_eval(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
+/* Same, but every row of logits ([n][vocab]) as the reference computes them (llama.go:384). */
+LB_API int lb_eval_all_logits(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
+/* The same forward pass built node for node with the op API below, exactly as llama.go:211-426
+ * builds it, and run by lb_graph_compute (slow path; exists to prove the op API is a drop-in). */
+LB_API int lb_eval_graph(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
+/* Device-resident decode: enqueue `steps` single-token evals starting at `past` with the given
+ * tokens (teacher forcing), no host copies; used by bench.py for the kernel-only number.
+ * ms_out (optional) = CUDA-event time of the whole batch of steps on the context's stream. */
+LB_API int lb_decode_resident(lb_context *c, const uint32_t *tokens, uint32_t steps, uint32_t past, float *ms_out);
+LB_API int lb_context_read_logits(lb_context *c, float *logits_out);              /* last eval's row */
+LB_API int lb_context_read_kv(lb_context *c, uint32_t layer, uint32_t t0, uint32_t nt, float *k_out, float *v_out);
+LB_API int lb_context_read_hidden(lb_context *c, uint32_t n, float *hidden_out);  /* residual stream before final norm */
+LB_API int lb_context_synchronize(lb_context *c);
+/* pipeline stages (multi-GPU layer sharding): run only this stage's layers.
+ * hidden_in/out are DEVICE pointers to [n][dim] FP32 (NULL on the first/last stage). */
+LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past,
+                         const float *hidden_in_dev, float *hidden_out_dev, float *logits_out);
+LB_API float *lb_context_hidden_buffer(lb_context *c);   /* device [max_batch][dim] scratch for hand-offs */
+LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
+
+/* ---- op-level mirror of pkg/ml -------------------------------------------------------- */
+LB_API lb_mlctx  *lb_ml_new_context(int device);                   /* ml.NewContext (ml.go:59-74) */
+LB_API void       lb_ml_release_context(lb_mlctx *ctx);            /* ReleaseContext (ml.go:77-80) */
+LB_API lb_tensor *lb_new_tensor(lb_mlctx *ctx, int dtype, uint32_t dims, uint32_t ne0, uint32_t ne1,
+                                uint32_t ne2, uint32_t ne3, const float *host_or_null); /* NewTensor ml.go:760 */
+LB_API int        lb_tensor_write(lb_tensor *t, const float *host, size_t nelem);  /* = fill t.Data */
+LB_API int        lb_tensor_read(lb_tensor *t, float *host, size_t nelem);         /* = read t.Data (backing store) */
+LB_API int        lb_tensor_shape(const lb_tensor *t, uint32_t ne[4], uint32_t nb[4]); /* NB in bytes, ml.go:188 */
+/* lazy op constructors, same arguments as the Go ctors (file:line in pkg/ml/ml.go) */
+LB_API lb_tensor *lb_get_rows(lb_mlctx *, lb_tensor *a, lb_tensor *b);                 /* :528 */
+LB_API lb_tensor *lb_rms_norm(lb_mlctx *, lb_tensor *a);                               /* :559 */
+LB_API lb_tensor *lb_repeat(lb_mlctx *, lb_tensor *a, lb_tensor *b);                   /* :487 */
+LB_API lb_tensor *lb_mul(lb_mlctx *, lb_tensor *a, lb_tensor *b);                      /* :241 */
+LB_API lb_tensor *lb_add(lb_mlctx *, lb_tensor *a, lb_tensor *b);                      /* :347 */
+LB_API lb_tensor *lb_mul_mat(lb_mlctx *, lb_tensor *a, lb_tensor *b);                  /* :295 */
+LB_API lb_tensor *lb_view_1d(lb_mlctx *, lb_tensor *a, uint32_t ne0, uint32_t offset_floats); /* :601 */
+LB_API lb_tensor *lb_cpy(lb_mlctx *, lb_tensor *a, lb_tensor *b);                      /* :733 */
+LB_API lb_tensor *lb_rope(lb_mlctx *, lb_tensor *a, uint32_t past, uint32_t dims, uint32_t mode); /* :848 */
+LB_API lb_tensor *lb_permute(lb_mlctx *, lb_tensor *a, uint32_t ax0, uint32_t ax1, uint32_t ax2, uint32_t ax3); /* :786 */
+LB_API lb_tensor *lb_transpose(lb_mlctx *, lb_tensor *a);                              /* :1087 */
+LB_API lb_tensor *lb_reshape_3d(lb_mlctx *, lb_tensor *a, uint32_t ne0, uint32_t ne1, uint32_t ne2); /* :882 */
+LB_API lb_tensor *lb_new_f32(lb_mlctx *, float value);                                 /* :915 */
+LB_API lb_tensor *lb_scale(lb_mlctx *, lb_tensor *a, lb_tensor *b);                    /* :959 */
+LB_API lb_tensor *lb_diag_mask_inf(lb_mlctx *, lb_tensor *a, uint32_t past);           /* :968 */
+LB_API lb_tensor *lb_soft_max(lb_mlctx *, lb_tensor *a);                               /* :993 */
+LB_API lb_tensor *lb_silu(lb_mlctx *, lb_tensor *a);                                   /* :1041 */
+/* graph */
+LB_API lb_graph *lb_graph_new(void);
+LB_API void      lb_graph_free(lb_graph *g);
+LB_API int       lb_build_forward_expand(lb_graph *g, lb_tensor *t);                   /* :642 */
+LB_API int       lb_graph_compute(lb_mlctx *ctx, lb_graph *g);                         /* :1411, synchronous */
+LB_API uint32_t  lb_graph_nodes(const lb_graph *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAMAB200_H */

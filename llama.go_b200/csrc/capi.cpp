@@ -1,0 +1,243 @@
+// capi.cpp — the extern "C" boundary declared in include/llamab200.h.
+#include "../../include/llamab200.h"
+
+#include <string.h>
+
+#include <string>
+
+#include "llama.hpp"
+#include "ml.hpp"
+
+using namespace lb;
+
+struct lb_model { llama::Model *m; };
+struct lb_context { llama::Context *c; };
+struct lb_mlctx { ml::Context *c; };
+struct lb_graph { ml::Graph g; };
+// lb_tensor* is an ml::Tensor* (owned by its lb_mlctx)
+static inline ml::Tensor *T(lb_tensor *t) { return reinterpret_cast<ml::Tensor *>(t); }
+static inline const ml::Tensor *T(const lb_tensor *t) { return reinterpret_cast<const ml::Tensor *>(t); }
+static inline lb_tensor *W(ml::Tensor *t) { return reinterpret_cast<lb_tensor *>(t); }
+
+static thread_local std::string g_err;
+
+#define LB_TRY_INT(body)                 \
+    try {                                \
+        body;                            \
+        return 0;                        \
+    } catch (const std::exception &e) {  \
+        g_err = e.what();                \
+        return 1;                        \
+    } catch (...) {                      \
+        g_err = "unknown error";         \
+        return 1;                        \
+    }
+#define LB_TRY_PTR(type, expr)           \
+    try {                                \
+        return (type)(expr);             \
+    } catch (const std::exception &e) {  \
+        g_err = e.what();                \
+        return nullptr;                  \
+    } catch (...) {                      \
+        g_err = "unknown error";         \
+        return nullptr;                  \
+    }
+
+static void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        throw Error(std::string("no CUDA device is usable (there is no CPU fallback): ") + cudaGetErrorString(e));
+    LB_CHECK(device >= 0 && device < n, "device index out of range");
+    cudaDeviceProp p;
+    LB_CUDA(cudaGetDeviceProperties(&p, device));
+    LB_CHECK(p.major == 10, "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(p.major) +
+                                std::to_string(p.minor));
+}
+
+extern "C" {
+
+const char *lb_last_error(void) { return g_err.c_str(); }
+const char *lb_version(void) { return "llamab200 0.1 (sm_100a)"; }
+uint64_t lb_kernel_launches(void) { return g_launches.load(); }
+
+int lb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+lb_model *lb_model_create(const lb_hparams *hp, int device, uint32_t layer_begin, uint32_t layer_end, int weight_type) {
+    try {
+        LB_CHECK(hp != nullptr, "lb_model_create: nil hparams");
+        require_device(device);
+        llama::HParams h;
+        h.vocab = hp->vocab; h.dim = hp->dim; h.mult = hp->mult; h.heads = hp->heads; h.layers = hp->layers;
+        auto *m = new lb_model{nullptr};
+        try {
+            m->m = new llama::Model(h, device, layer_begin, layer_end, weight_type);
+        } catch (...) { delete m; throw; }
+        return m;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void lb_model_free(lb_model *m) { if (m) { delete m->m; delete m; } }
+int lb_model_set_tensor(lb_model *m, const char *name, int dtype, const void *host, size_t nbytes) {
+    LB_TRY_INT(LB_CHECK(m && name && host, "lb_model_set_tensor: nil argument"); m->m->set_tensor(name, dtype, host, nbytes));
+}
+int lb_model_get_tensor(lb_model *m, const char *name, float *host, size_t nelem) {
+    LB_TRY_INT(LB_CHECK(m && name && host, "lb_model_get_tensor: nil argument"); m->m->get_tensor(name, host, nelem));
+}
+int lb_model_init_random(lb_model *m, uint64_t seed) { LB_TRY_INT(LB_CHECK(m, "nil model"); m->m->init_random(seed)); }
+uint64_t lb_model_weight_bytes(const lb_model *m) { return m ? m->m->weight_bytes_per_token() : 0; }
+
+int lb_synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma) {
+    LB_TRY_INT(LB_CHECK(dst, "nil dst"); llama::synth_fill_host(dst, count, seed, tid, start, mean, sigma));
+}
+int lb_bench_kernel(lb_context *c, int which, uint32_t iters, uint32_t past, float *ms_out, uint64_t *bytes_out) {
+    LB_TRY_INT(LB_CHECK(c && ms_out && bytes_out, "nil argument"); *ms_out = c->c->bench_kernel(which, iters, past, bytes_out));
+}
+
+lb_context *lb_context_create(lb_model *m, uint32_t ctx_size) {
+    try {
+        LB_CHECK(m != nullptr, "lb_context_create: nil model");
+        auto *c = new lb_context{nullptr};
+        try { c->c = new llama::Context(m->m, ctx_size); } catch (...) { delete c; throw; }
+        return c;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void lb_context_free(lb_context *c) { if (c) { delete c->c; delete c; } }
+
+int lb_eval(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->eval(tokens, n, past, logits_out, false));
+}
+int lb_eval_all_logits(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->eval(tokens, n, past, logits_out, true));
+}
+int lb_eval_graph(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out) {
+    LB_TRY_INT(LB_CHECK(c && tokens, "nil argument"); c->c->eval_graph(tokens, n, past, logits_out));
+}
+int lb_decode_resident(lb_context *c, const uint32_t *tokens, uint32_t steps, uint32_t past, float *ms_out) {
+    LB_TRY_INT(LB_CHECK(c && tokens, "nil argument"); float ms = c->c->decode_resident(tokens, steps, past); if (ms_out) *ms_out = ms);
+}
+int lb_context_read_logits(lb_context *c, float *out) {
+    LB_TRY_INT(LB_CHECK(c && out, "nil argument"); LB_CHECK(c->c->model->has_head(), "this stage has no lm_head");
+               LB_CUDA(cudaSetDevice(c->c->model->device));
+               LB_CUDA(cudaMemcpyAsync(out, c->c->logits, c->c->model->hp.vocab * sizeof(float), cudaMemcpyDeviceToHost, c->c->stream));
+               LB_CUDA(cudaStreamSynchronize(c->c->stream)));
+}
+int lb_context_read_kv(lb_context *c, uint32_t layer, uint32_t t0, uint32_t nt, float *k_out, float *v_out) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); llama::Context *x = c->c;
+               LB_CHECK(layer >= x->model->layer_begin && layer < x->model->layer_end, "layer not held by this stage");
+               LB_CHECK((uint64_t)t0 + nt <= x->ctx_size, "kv range out of bounds");
+               size_t d = x->model->hp.dim; size_t off = ((size_t)(layer - x->model->layer_begin) * x->ctx_size + t0) * d;
+               LB_CUDA(cudaSetDevice(x->model->device)); LB_CUDA(cudaStreamSynchronize(x->stream));
+               if (k_out) LB_CUDA(cudaMemcpy(k_out, x->kv_k + off, (size_t)nt * d * 4, cudaMemcpyDeviceToHost));
+               if (v_out) LB_CUDA(cudaMemcpy(v_out, x->kv_v + off, (size_t)nt * d * 4, cudaMemcpyDeviceToHost)));
+}
+int lb_context_read_hidden(lb_context *c, uint32_t n, float *out) {
+    LB_TRY_INT(LB_CHECK(c && out, "nil argument"); llama::Context *x = c->c; LB_CHECK(n <= x->max_batch, "n too large");
+               LB_CUDA(cudaSetDevice(x->model->device)); LB_CUDA(cudaStreamSynchronize(x->stream));
+               LB_CUDA(cudaMemcpy(out, x->x, (size_t)n * x->model->hp.dim * 4, cudaMemcpyDeviceToHost)));
+}
+int lb_context_synchronize(lb_context *c) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); LB_CUDA(cudaSetDevice(c->c->model->device)); LB_CUDA(cudaStreamSynchronize(c->c->stream)));
+}
+int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, const float *hidden_in_dev,
+                  float *hidden_out_dev, float *logits_out) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->use_graph = false; c->c->eval(tokens, n, past, logits_out, false, hidden_in_dev, hidden_out_dev));
+}
+float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
+void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }
+
+// ---- pkg/ml mirror ----
+lb_mlctx *lb_ml_new_context(int device) {
+    try {
+        require_device(device);
+        auto *x = new lb_mlctx{nullptr};
+        try { x->c = new ml::Context(device); } catch (...) { delete x; throw; }
+        return x;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void lb_ml_release_context(lb_mlctx *ctx) { if (ctx) { delete ctx->c; delete ctx; } }
+
+lb_tensor *lb_new_tensor(lb_mlctx *ctx, int dtype, uint32_t dims, uint32_t ne0, uint32_t ne1, uint32_t ne2, uint32_t ne3,
+                         const float *host) {
+    try {
+        LB_CHECK(ctx, "nil context");
+        LB_CHECK(dims >= 1 && dims <= 4, "NewTensor : dims must be 1..4");
+        ml::Tensor *t = ml::NewTensor(ctx->c, (ml::DType)dtype, dims, ne0, ne1, ne2, ne3, nullptr, 0);
+        if (host) {
+            LB_CUDA(cudaMemcpyAsync(t->data, host, (size_t)t->nelements() * 4, cudaMemcpyHostToDevice, ctx->c->stream));
+            LB_CUDA(cudaStreamSynchronize(ctx->c->stream));
+        }
+        return W(t);
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+int lb_tensor_write(lb_tensor *t, const float *host, size_t nelem) {
+    LB_TRY_INT(LB_CHECK(t && host, "nil argument"); LB_CHECK(nelem <= T(t)->avail, "tensor write out of bounds");
+               LB_CUDA(cudaMemcpy(T(t)->data, host, nelem * 4, cudaMemcpyHostToDevice)));
+}
+int lb_tensor_read(lb_tensor *t, float *host, size_t nelem) {
+    LB_TRY_INT(LB_CHECK(t && host, "nil argument"); LB_CHECK(nelem <= T(t)->avail, "tensor read out of bounds");
+               LB_CUDA(cudaDeviceSynchronize()); LB_CUDA(cudaMemcpy(host, T(t)->data, nelem * 4, cudaMemcpyDeviceToHost)));
+}
+int lb_tensor_shape(const lb_tensor *t, uint32_t ne[4], uint32_t nb[4]) {
+    LB_TRY_INT(LB_CHECK(t, "nil tensor"); for (int i = 0; i < 4; i++) { if (ne) ne[i] = T(t)->ne[i]; if (nb) nb[i] = T(t)->nb[i]; });
+}
+
+#define LB_OP1(name, fn) \
+    lb_tensor *name(lb_mlctx *c, lb_tensor *a) { LB_TRY_PTR(lb_tensor *, (LB_CHECK(c && a, "nil argument"), W(fn(c->c, T(a))))); }
+#define LB_OP2(name, fn) \
+    lb_tensor *name(lb_mlctx *c, lb_tensor *a, lb_tensor *b) { LB_TRY_PTR(lb_tensor *, (LB_CHECK(c && a && b, "nil argument"), W(fn(c->c, T(a), T(b))))); }
+
+static inline void chk(bool ok, const char *msg) { if (!ok) throw Error(std::string("[HALT] ") + msg); }
+#undef LB_OP1
+#undef LB_OP2
+#define LB_OP1(name, fn) \
+    lb_tensor *name(lb_mlctx *c, lb_tensor *a) { try { chk(c && a, "nil argument"); return W(fn(c->c, T(a))); } catch (const std::exception &e) { g_err = e.what(); return nullptr; } }
+#define LB_OP2(name, fn) \
+    lb_tensor *name(lb_mlctx *c, lb_tensor *a, lb_tensor *b) { try { chk(c && a && b, "nil argument"); return W(fn(c->c, T(a), T(b))); } catch (const std::exception &e) { g_err = e.what(); return nullptr; } }
+
+LB_OP2(lb_get_rows, ml::GetRows)
+LB_OP1(lb_rms_norm, ml::RMSNorm)
+LB_OP2(lb_repeat, ml::Repeat)
+LB_OP2(lb_mul, ml::Mul)
+LB_OP2(lb_add, ml::Add)
+LB_OP2(lb_mul_mat, ml::MulMat)
+LB_OP2(lb_cpy, ml::Copy)
+LB_OP1(lb_transpose, ml::Transpose)
+LB_OP2(lb_scale, ml::Scale)
+LB_OP1(lb_soft_max, ml::SoftMax)
+LB_OP1(lb_silu, ml::Silu)
+
+lb_tensor *lb_view_1d(lb_mlctx *c, lb_tensor *a, uint32_t ne0, uint32_t off) {
+    try { chk(c && a, "nil argument"); return W(ml::View1D(c->c, T(a), ne0, off)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+lb_tensor *lb_rope(lb_mlctx *c, lb_tensor *a, uint32_t past, uint32_t dims, uint32_t mode) {
+    try { chk(c && a, "nil argument"); return W(ml::Rope(c->c, T(a), past, dims, mode)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+lb_tensor *lb_permute(lb_mlctx *c, lb_tensor *a, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+    try { chk(c && a, "nil argument"); return W(ml::Permute(c->c, T(a), a0, a1, a2, a3)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+lb_tensor *lb_reshape_3d(lb_mlctx *c, lb_tensor *a, uint32_t ne0, uint32_t ne1, uint32_t ne2) {
+    try { chk(c && a, "nil argument"); return W(ml::Reshape3D(c->c, T(a), ne0, ne1, ne2)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+lb_tensor *lb_new_f32(lb_mlctx *c, float v) {
+    try { chk(c, "nil argument"); return W(ml::NewFP32(c->c, v)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+lb_tensor *lb_diag_mask_inf(lb_mlctx *c, lb_tensor *a, uint32_t past) {
+    try { chk(c && a, "nil argument"); return W(ml::DiagMaskInf(c->c, T(a), past)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+
+lb_graph *lb_graph_new(void) { return new lb_graph(); }
+void lb_graph_free(lb_graph *g) { delete g; }
+int lb_build_forward_expand(lb_graph *g, lb_tensor *t) { LB_TRY_INT(LB_CHECK(g && t, "nil argument"); ml::BuildForwardExpand(&g->g, T(t))); }
+int lb_graph_compute(lb_mlctx *ctx, lb_graph *g) { LB_TRY_INT(LB_CHECK(ctx && g, "nil argument"); ml::GraphCompute(ctx->c, &g->g, true)); }
+uint32_t lb_graph_nodes(const lb_graph *g) { return g ? (uint32_t)g->g.nodes.size() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// common.cuh — shared host/device helpers for the llamab200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+
+namespace lb {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define LB_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw lb::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                            ":" + std::to_string(__LINE__) + ")");                             \
+    } while (0)
+
+#define LB_CHECK(cond, msg)                                    \
+    do {                                                       \
+        if (!(cond)) throw lb::Error(std::string("[HALT] ") + (msg)); \
+    } while (0)
+
+// process-wide count of kernels this library launched (bench.py's gpu_launches)
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define LB_LAUNCH_CHECK()            \
+    do {                             \
+        lb::count_launch();          \
+        LB_CUDA(cudaGetLastError()); \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// streaming 128-bit load: read-only path, do not allocate in L1 (weights are touched once)
+__device__ __forceinline__ float4 ld_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int4 ld_stream_i4(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// SiluFP32 of the reference: x / float32(1 + exp(float64(-x)))   (pkg/ml/ml.go:2587-2589)
+__device__ __forceinline__ float silu_ref(float x) {
+    return __fdiv_rn(x, (float)(1.0 + exp((double)(-x))));
+}
+#endif
+
+}  // namespace lb

@@ -1,0 +1,68 @@
+// kernels.cuh — launchers of every CUDA kernel in the library (definitions in kernels_*.cu).
+// All pointers are device pointers; every launcher enqueues on `st` and returns immediately.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb {
+
+// strided view of a device tensor: mirrors ml.Tensor's NE/NB (pkg/ml/ml.go:187-188) with the
+// strides already divided down to floats.
+struct TView {
+    float *data;
+    uint32_t ne[4];
+    uint32_t nb[4];
+};
+
+namespace k {
+
+// ---- generic op kernels (one per reference ComputeForward*; used by the pkg/ml mirror) ----
+void get_rows_f32ids(const float *table, uint32_t nc, const float *ids, uint32_t nr, float *dst, cudaStream_t st);
+void get_rows_u32ids(const float *table, uint32_t nc, const uint32_t *ids, uint32_t nr, float *dst, cudaStream_t st);
+// y = x * f32(1/sqrt(mean_f64(x^2) + 1e-5)); if w != nullptr additionally y = y * w (w broadcast over rows)
+void rms_norm(const float *x, const float *w, float *y, uint32_t nc, uint32_t nr, cudaStream_t st);
+void repeat_rows(const float *a, uint32_t nc0, uint32_t nr0, float *dst, uint32_t nc, uint32_t nr, cudaStream_t st);
+void mul(const float *a, const float *b, float *dst, size_t n, cudaStream_t st);
+void add(const float *a, const float *b, float *dst, size_t n, cudaStream_t st);
+void scale_inplace(float *x, float v, size_t n, cudaStream_t st);
+void silu(const float *x, float *y, size_t n, cudaStream_t st);
+void diag_mask_inf(float *x, uint32_t ne0, uint32_t ne1, uint32_t ne2, uint32_t past, cudaStream_t st);
+void soft_max_rows(float *x, uint32_t nc, uint32_t nr, cudaStream_t st);
+void cpy_strided(const TView &src, float *dst, cudaStream_t st);
+// rope on a contiguous [ne0, ne1, ne2] tensor, in place (ComputeForwardRopeFP32, ml.go:2253-2328)
+void rope(float *x, uint32_t ne0, uint32_t ne1, uint32_t ne2, uint32_t past, uint32_t dims, uint32_t mode, cudaStream_t st);
+void mul_mat_generic(const TView &a, const TView &b, const TView &dst, cudaStream_t st);
+void init_random(float *dst, uint64_t count, uint64_t seed, uint64_t tid, float mean, float sigma_scale, cudaStream_t st);
+void f16_to_f32(const uint16_t *src, float *dst, size_t n, cudaStream_t st);
+
+// ---- fused hot-path kernels (llama::Eval) ----
+enum Epilogue { EPI_NONE = 0, EPI_ADD_RESIDUAL = 1 };
+// y[n][m] = sum_k W[m][k] * x[n][k]   (+ residual[n][m]);  W row-major [M][K]; x rows ldx apart,
+// y/residual rows ldy apart.  N = 1..8 columns per weight pass (decode / pod batch).
+void gemv_f32(const float *W, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N,
+              float *y, uint32_t ldy, const float *residual, cudaStream_t st);
+// act[n][m] = silu(W1[m]·x[n]) * (W3[m]·x[n])   (llama.go:354-361)
+void gemv_f32_swiglu(const float *W1, const float *W3, uint32_t M, uint32_t K, const float *x, uint32_t ldx,
+                     uint32_t N, float *act, uint32_t ldy, cudaStream_t st);
+// prefill GEMM, any N: Y[n][m] = sum_k W[m][k] X[n][k] (+ residual)
+void gemm_f32(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+              float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
+void swiglu(const float *gate, const float *up, float *dst, size_t n, cudaStream_t st);
+// q (rows ldq apart, [N][dim]) rotated in place at positions past+n; k rotated and stored to
+// Kc[(past+n)][dim]; v stored to Vc[(past+n)][dim]   (llama.go:274-297 — K is cached rotated)
+// `past_dev` is a DEVICE pointer to the position of the first new token, so that a captured CUDA
+// graph can be replayed for every decode step without re-baking the position.
+void rope_qk_store(float *q, const float *k, const float *v, uint32_t ld, float *Kc, float *Vc,
+                   uint32_t N, const uint32_t *past_dev, uint32_t dim, uint32_t heads, cudaStream_t st);
+// causal attention over the FP32 cache: out[n][h*hd+d] for queries n (position past+n), head dim 128|64|32
+// max_T bounds past+N (sizes the shared-memory score buffer at launch/capture time).
+void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,
+               const uint32_t *past_dev, uint32_t max_T, uint32_t dim, uint32_t heads, cudaStream_t st);
+// single-token embedding gather for graph replay: row = table[tokens[*step_dev + n]]
+void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, const uint32_t *step_dev,
+                       uint32_t nr, float *dst, cudaStream_t st);
+// state[0] (= past) += dp; state[1] (= step) += ds
+void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
+
+}  // namespace k
+}  // namespace lb

@@ -1,0 +1,517 @@
+// llama.cpp — see llama.hpp.
+#include "llama.hpp"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+
+namespace lb {
+namespace llama {
+
+static const double IH_STD = 37837.22539803592;  // llama.go_b200/synth.py
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool Model::known_name(const HParams &hp, const std::string &name) {
+    if (name == "tok_embeddings.weight" || name == "norm.weight" || name == "output.weight") return true;
+    unsigned il;
+    char rest[64];
+    if (sscanf(name.c_str(), "layers.%u.%63s", &il, rest) == 2 && il < hp.layers) {
+        static const char *kinds[] = {"attention_norm.weight", "attention.wq.weight", "attention.wk.weight",
+                                      "attention.wv.weight", "attention.wo.weight", "ffn_norm.weight",
+                                      "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight"};
+        for (const char *kname : kinds)
+            if (!strcmp(rest, kname)) return true;
+    }
+    return false;
+}
+
+Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp(h), device(dev), layer_begin(lb_), layer_end(le_), weight_type(wt) {
+    LB_CHECK(hp.vocab && hp.dim && hp.mult && hp.heads && hp.layers, "model: zero hyper-parameter");
+    LB_CHECK(hp.dim % hp.heads == 0, "model: dim must be divisible by heads");
+    LB_CHECK(hp.dim % 4 == 0, "model: dim must be a multiple of 4");
+    LB_CHECK(layer_begin < layer_end && layer_end <= hp.layers, "model: bad layer range");
+    LB_CHECK(wt == 0, "model: only LB_TYPE_F32 weights are implemented in this build");
+    LB_CUDA(cudaSetDevice(device));
+    const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
+    const size_t A = 64;  // floats: 256-byte alignment of every tensor
+    size_t total = 0;
+    auto reserve = [&](size_t n) { size_t off = total; total += align_up(n, A); return off; };
+    size_t o_emb = 0, o_norm = 0, o_out = 0;
+    if (has_embedding()) o_emb = reserve(V * d);
+    if (has_head()) { o_norm = reserve(d); o_out = reserve(V * d); }
+    struct LOff { size_t an, qkv, wo, fn, w1, w2, w3; };
+    std::vector<LOff> lo(layer_end - layer_begin);
+    for (auto &l : lo) {
+        l.an = reserve(d); l.qkv = reserve(3 * d * d); l.wo = reserve(d * d); l.fn = reserve(d);
+        l.w1 = reserve(ff * d); l.w3 = reserve(ff * d); l.w2 = reserve(d * ff);
+    }
+    slab_floats = total;
+    LB_CUDA(cudaMalloc(&slab, total * sizeof(float)));
+    LB_CUDA(cudaMemset(slab, 0, total * sizeof(float)));
+    const float sd = 1.0f / sqrtf((float)d), sff = 1.0f / sqrtf((float)ff);
+    if (has_embedding()) {
+        tok_embeddings = slab + o_emb;
+        tensors["tok_embeddings.weight"] = {tok_embeddings, V * d, 1, 0.f, 1.f};
+    }
+    if (has_head()) {
+        norm = slab + o_norm; output = slab + o_out;
+        tensors["norm.weight"] = {norm, d, 2, 1.f, 0.1f};
+        tensors["output.weight"] = {output, V * d, 3, 0.f, (float)pow((double)d, -0.5)};
+    }
+    layers.resize(lo.size());
+    for (size_t i = 0; i < lo.size(); i++) {
+        Layer &L = layers[i];
+        L.attention_norm = slab + lo[i].an; L.wqkv = slab + lo[i].qkv; L.wo = slab + lo[i].wo;
+        L.ffn_norm = slab + lo[i].fn; L.w1 = slab + lo[i].w1; L.w3 = slab + lo[i].w3; L.w2 = slab + lo[i].w2;
+        uint32_t il = layer_begin + (uint32_t)i;
+        std::string p = "layers." + std::to_string(il) + ".";
+        uint64_t base = 16ull * (il + 1);
+        const float sdd = (float)pow((double)d, -0.5), sf = (float)pow((double)ff, -0.5);
+        (void)sd; (void)sff;
+        tensors[p + "attention_norm.weight"] = {L.attention_norm, d, base + 0, 1.f, 0.1f};
+        tensors[p + "attention.wq.weight"] = {L.wqkv, d * d, base + 1, 0.f, sdd};
+        tensors[p + "attention.wk.weight"] = {L.wqkv + d * d, d * d, base + 2, 0.f, sdd};
+        tensors[p + "attention.wv.weight"] = {L.wqkv + 2 * d * d, d * d, base + 3, 0.f, sdd};
+        tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd};
+        tensors[p + "ffn_norm.weight"] = {L.ffn_norm, d, base + 5, 1.f, 0.1f};
+        tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd};
+        tensors[p + "feed_forward.w2.weight"] = {L.w2, d * ff, base + 7, 0.f, sf};
+        tensors[p + "feed_forward.w3.weight"] = {L.w3, ff * d, base + 8, 0.f, sdd};
+    }
+}
+
+Model::~Model() {
+    cudaSetDevice(device);
+    if (slab) cudaFree(slab);
+}
+
+void Model::set_tensor(const std::string &name, int dtype, const void *host, size_t nbytes) {
+    // LoadModel's tensor loop, llama.go:889-959: unknown names abort (:906-910); only F32 and F16
+    // are accepted (:937-959), F16 is widened to FP32.
+    LB_CHECK(known_name(hp, name), "Unknown tensor '" + name + "' in model file");
+    auto it = tensors.find(name);
+    if (it == tensors.end()) return;  // belongs to another pipeline stage
+    LB_CHECK(dtype == 0 || dtype == 1, "Tensor data type is not supported yet!");
+    const size_t esz = dtype == 0 ? 4 : 2;
+    LB_CHECK(nbytes == it->second.nelem * esz, "tensor '" + name + "' has the wrong size");
+    LB_CUDA(cudaSetDevice(device));
+    if (dtype == 0) {
+        LB_CUDA(cudaMemcpy(it->second.ptr, host, nbytes, cudaMemcpyHostToDevice));
+    } else {
+        void *tmp = nullptr;
+        LB_CUDA(cudaMalloc(&tmp, nbytes));
+        LB_CUDA(cudaMemcpy(tmp, host, nbytes, cudaMemcpyHostToDevice));
+        k::f16_to_f32(static_cast<const uint16_t *>(tmp), it->second.ptr, it->second.nelem, 0);
+        LB_CUDA(cudaDeviceSynchronize());
+        cudaFree(tmp);
+    }
+}
+
+void Model::get_tensor(const std::string &name, float *host, size_t nelem) {
+    auto it = tensors.find(name);
+    LB_CHECK(it != tensors.end(), "tensor '" + name + "' is not held by this stage");
+    LB_CHECK(nelem == it->second.nelem, "tensor '" + name + "' has the wrong size");
+    LB_CUDA(cudaSetDevice(device));
+    LB_CUDA(cudaMemcpy(host, it->second.ptr, nelem * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+void Model::init_random(uint64_t seed) {
+    LB_CUDA(cudaSetDevice(device));
+    for (auto &kv : tensors) {
+        const Entry &e = kv.second;
+        // float32(sigma / IH_STD): the division is done in double on the host exactly like numpy does
+        float sscale = (float)((double)e.sigma / IH_STD);
+        k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
+    }
+    LB_CUDA(cudaDeviceSynchronize());
+}
+
+uint64_t Model::weight_bytes_per_token() const {
+    // every layer matrix + both norms, lm_head, final norm, one embedding row
+    const uint64_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
+    uint64_t b = (uint64_t)(layer_end - layer_begin) * (4 * d * d + 3 * d * ff + 2 * d);
+    if (has_head()) b += V * d + d;
+    if (has_embedding()) b += d;
+    return b * 4;
+}
+
+// ---------------------------------------------------------------------------------------------
+Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
+    LB_CHECK(cs > 0, "context: ctx_size must be > 0");
+    LB_CUDA(cudaSetDevice(m->device));
+    LB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const HParams &hp = m->hp;
+    const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab, nl = m->layers.size();
+    max_batch = cs;
+    auto dalloc = [&](size_t floats) {
+        void *p = nullptr;
+        LB_CUDA(cudaMalloc(&p, (floats ? floats : 1) * sizeof(float)));
+        LB_CUDA(cudaMemset(p, 0, (floats ? floats : 1) * sizeof(float)));
+        return static_cast<float *>(p);
+    };
+    kv_k = dalloc(nl * cs * d);
+    kv_v = dalloc(nl * cs * d);
+    x = dalloc((size_t)max_batch * d); y = dalloc((size_t)max_batch * d); cur = dalloc((size_t)max_batch * d);
+    qkv = dalloc((size_t)max_batch * 3 * d); attn = dalloc((size_t)max_batch * d);
+    act = dalloc((size_t)max_batch * ff); up = dalloc((size_t)max_batch * ff);
+    logits = dalloc(V);
+    tokens_cap = max_batch + 4096;
+    LB_CUDA(cudaMalloc(&tokens_dev, tokens_cap * sizeof(uint32_t)));
+    LB_CUDA(cudaMemset(tokens_dev, 0, tokens_cap * sizeof(uint32_t)));
+    LB_CUDA(cudaMalloc(&state_dev, 2 * sizeof(uint32_t)));
+    LB_CUDA(cudaMemset(state_dev, 0, 2 * sizeof(uint32_t)));
+    LB_CUDA(cudaMallocHost(&state_host, 2 * sizeof(uint32_t)));
+    LB_CUDA(cudaMallocHost(&tokens_host, tokens_cap * sizeof(uint32_t)));
+    LB_CUDA(cudaMallocHost(&logits_host, V * sizeof(float)));
+    LB_CUDA(cudaEventCreate(&ev0));
+    LB_CUDA(cudaEventCreate(&ev1));
+    use_graph = getenv("LB_NO_GRAPH") == nullptr;  // profiling aid: plain launches instead of graph replay
+}
+
+Context::~Context() {
+    cudaSetDevice(model->device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (decode_graph) cudaGraphExecDestroy(decode_graph);
+    for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits})
+        if (p) cudaFree(p);
+    if (tokens_dev) cudaFree(tokens_dev);
+    if (state_dev) cudaFree(state_dev);
+    if (state_host) cudaFreeHost(state_host);
+    if (tokens_host) cudaFreeHost(tokens_host);
+    if (logits_host) cudaFreeHost(logits_host);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+static void matmul(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,
+                   uint32_t ldy, const float *res, cudaStream_t st) {
+    if (N <= 8) k::gemv_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
+    else k::gemm_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
+}
+
+// The fused forward pass.  Per layer (llama.go:246-370):
+//   cur  = rmsnorm(x) * attention_norm                      (:255-259)      1 kernel
+//   qkv  = [wq;wk;wv] · cur                                 (:263-265)      1 kernel
+//   rope(q), rope(k) -> K cache, v -> V cache               (:274-297)      1 kernel
+//   attn = softmax(mask(K·q / sqrt(hd))) · V                (:300-333)      1 kernel
+//   y    = wo · attn + x                                    (:336-340)      1 kernel
+//   cur  = rmsnorm(y) * ffn_norm                            (:346-351)      1 kernel
+//   act  = silu(w1 · cur) * (w3 · cur)                      (:354-361)      1 kernel (decode)
+//   x    = w2 · act + y                                     (:363-366)      1 kernel
+void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const float *hidden_in, float *hidden_out) {
+    const HParams &hp = model->hp;
+    const uint32_t d = hp.dim, ff = hp.ff(), V = hp.vocab, H = hp.heads;
+    const uint32_t *past_dev = state_dev, *step_dev = state_dev + 1;
+    cudaStream_t st = stream;
+    if (model->has_embedding()) {
+        if (tokens_indirect) k::get_rows_indirect(model->tok_embeddings, d, tokens_dev, step_dev, n, x, st);
+        else k::get_rows_u32ids(model->tok_embeddings, d, tokens_dev, n, x, st);
+    } else {
+        LB_CHECK(hidden_in != nullptr, "eval_stage: this stage needs hidden_in");
+        if (hidden_in != x) LB_CUDA(cudaMemcpyAsync(x, hidden_in, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    for (size_t li = 0; li < model->layers.size(); li++) {
+        const Layer &L = model->layers[li];
+        float *Kc = kv_k + li * (size_t)ctx_size * d, *Vc = kv_v + li * (size_t)ctx_size * d;
+        k::rms_norm(x, L.attention_norm, cur, d, n, st);
+        matmul(L.wqkv, 3 * d, d, cur, d, n, qkv, 3 * d, nullptr, st);
+        k::rope_qk_store(qkv, qkv + d, qkv + 2 * d, 3 * d, Kc, Vc, n, past_dev, d, H, st);
+        k::attention(qkv, 3 * d, Kc, Vc, attn, n, past_dev, ctx_size, d, H, st);
+        matmul(L.wo, d, d, attn, d, n, y, d, x, st);
+        k::rms_norm(y, L.ffn_norm, cur, d, n, st);
+        if (n <= 8) {
+            k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, n, act, ff, st);
+        } else {
+            k::gemm_f32(L.w3, ff, d, cur, d, n, up, ff, nullptr, st);
+            k::gemm_f32(L.w1, ff, d, cur, d, n, act, ff, nullptr, st);
+            k::swiglu(act, up, act, (size_t)n * ff, st);
+        }
+        matmul(L.w2, d, ff, act, ff, n, x, d, y, st);
+    }
+    if (hidden_out && hidden_out != x)
+        LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (model->has_head()) {
+        if (all_rows) {
+            if (!all_logits) {
+                LB_CUDA(cudaMalloc(&all_logits, (size_t)max_batch * V * sizeof(float)));
+            }
+            k::rms_norm(x, model->norm, cur, d, n, st);
+            matmul(model->output, V, d, cur, d, n, all_logits, V, nullptr, st);
+        } else {
+            // only row n-1 is ever read (llama.go:394-401); the reference computes all n (:384)
+            k::rms_norm(x + (size_t)(n - 1) * d, model->norm, cur, d, 1, st);
+            k::gemv_f32(model->output, V, d, cur, d, 1, logits, V, nullptr, st);
+        }
+    }
+}
+
+void Context::build_decode_graph() {
+    cudaGraph_t g = nullptr;
+    LB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        forward(1, /*tokens_indirect=*/true, false, nullptr, nullptr);
+        k::advance_state(state_dev, 1, 1, stream);
+    } catch (...) {
+        cudaStreamEndCapture(stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    LB_CUDA(cudaStreamEndCapture(stream, &g));
+    LB_CUDA(cudaGraphInstantiate(&decode_graph, g, 0));
+    cudaGraphDestroy(g);
+}
+
+void Context::eval(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out, bool all_rows,
+                   const float *hidden_in, float *hidden_out) {
+    const HParams &hp = model->hp;
+    LB_CHECK(n >= 1, "Eval : no tokens");
+    LB_CHECK(n <= max_batch, "Eval : batch larger than the context");
+    LB_CHECK((uint64_t)past + n <= ctx_size, "Eval : pastCount + N exceeds the context size");
+    LB_CUDA(cudaSetDevice(model->device));
+    if (model->has_embedding()) {
+        LB_CHECK(tokens != nullptr, "Eval : nil tokens");
+        for (uint32_t i = 0; i < n; i++) {
+            LB_CHECK(tokens[i] < hp.vocab, "Eval : token id out of range");
+            tokens_host[i] = tokens[i];
+        }
+        LB_CUDA(cudaMemcpyAsync(tokens_dev, tokens_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    }
+    state_host[0] = past; state_host[1] = 0;
+    LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    const bool single_stage = model->has_embedding() && model->has_head();
+    if (n == 1 && !all_rows && single_stage && use_graph) {
+        if (!decode_graph) {
+            // first single-token eval runs eagerly (also sets kernel attributes), then capture
+            forward(1, true, false, nullptr, nullptr);
+            LB_CUDA(cudaStreamSynchronize(stream));
+            build_decode_graph();
+        } else {
+            LB_CUDA(cudaGraphLaunch(decode_graph, stream));
+            count_launch(model->layers.size() * 8 + 4);
+        }
+    } else {
+        forward(n, false, all_rows, hidden_in, hidden_out);
+    }
+    last_n = n;
+    if (logits_out && model->has_head()) {
+        if (all_rows) {
+            LB_CUDA(cudaMemcpyAsync(logits_out, all_logits, (size_t)n * hp.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        } else {
+            LB_CUDA(cudaMemcpyAsync(logits_host, logits, hp.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    LB_CUDA(cudaStreamSynchronize(stream));  // Eval is synchronous (llama.go:389-401)
+    if (logits_out && model->has_head() && !all_rows) memcpy(logits_out, logits_host, hp.vocab * sizeof(float));
+}
+
+float Context::decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t past) {
+    const HParams &hp = model->hp;
+    LB_CHECK(model->has_embedding() && model->has_head(), "decode_resident : needs a single-stage model");
+    LB_CHECK(steps >= 1 && steps <= tokens_cap, "decode_resident : too many steps");
+    LB_CHECK((uint64_t)past + steps <= ctx_size, "decode_resident : past + steps exceeds the context size");
+    LB_CUDA(cudaSetDevice(model->device));
+    for (uint32_t i = 0; i < steps; i++) {
+        LB_CHECK(tokens[i] < hp.vocab, "decode_resident : token id out of range");
+        tokens_host[i] = tokens[i];
+    }
+    LB_CUDA(cudaMemcpyAsync(tokens_dev, tokens_host, steps * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    state_host[0] = past; state_host[1] = 0;
+    LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    uint32_t done = 0;
+    if (!decode_graph) {
+        forward(1, true, false, nullptr, nullptr);
+        k::advance_state(state_dev, 1, 1, stream);
+        LB_CUDA(cudaStreamSynchronize(stream));
+        build_decode_graph();
+        done = 1;
+    }
+    LB_CUDA(cudaStreamSynchronize(stream));
+    LB_CUDA(cudaEventRecord(ev0, stream));
+    for (uint32_t i = done; i < steps; i++) {
+        LB_CUDA(cudaGraphLaunch(decode_graph, stream));
+        count_launch(model->layers.size() * 8 + 4);
+    }
+    LB_CUDA(cudaEventRecord(ev1, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    LB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_n = 1;
+    return ms;
+}
+
+float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch) {
+    const HParams &hp = model->hp;
+    const uint32_t d = hp.dim, ff = hp.ff(), V = hp.vocab, H = hp.heads;
+    const size_t nl = model->layers.size();
+    LB_CHECK(iters >= 1 && nl >= 1, "bench_kernel : nothing to run");
+    LB_CHECK(past < ctx_size, "bench_kernel : past exceeds the context");
+    LB_CUDA(cudaSetDevice(model->device));
+    state_host[0] = past; state_host[1] = 0;
+    LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    auto launch = [&](uint32_t i) {
+        const Layer &L = model->layers[i % nl];
+        float *Kc = kv_k + (i % nl) * (size_t)ctx_size * d, *Vc = kv_v + (i % nl) * (size_t)ctx_size * d;
+        switch (which) {
+            case 0: k::gemv_f32(L.wqkv, 3 * d, d, cur, d, 1, qkv, 3 * d, nullptr, stream); break;
+            case 1: k::gemv_f32(L.wo, d, d, attn, d, 1, y, d, x, stream); break;
+            case 2: k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, 1, act, ff, stream); break;
+            case 3: k::gemv_f32(L.w2, d, ff, act, ff, 1, up, d, y, stream); break;
+            case 4: LB_CHECK(model->has_head(), "no lm_head on this stage");
+                    k::gemv_f32(model->output, V, d, cur, d, 1, logits, V, nullptr, stream); break;
+            case 5: k::attention(qkv, 3 * d, Kc, Vc, attn, 1, state_dev, ctx_size, d, H, stream); break;
+            case 6: k::rms_norm(x, L.attention_norm, cur, d, 1, stream); break;
+            default: LB_CHECK(false, "bench_kernel : unknown kernel id");
+        }
+    };
+    const uint64_t T = (uint64_t)past + 1;
+    switch (which) {  // algorithmic bytes: weights + activations in + out
+        case 0: *bytes_per_launch = 4ull * (3ull * d * d + d + 3ull * d); break;
+        case 1: *bytes_per_launch = 4ull * ((uint64_t)d * d + 3ull * d); break;
+        case 2: *bytes_per_launch = 4ull * (2ull * ff * d + d + ff); break;
+        case 3: *bytes_per_launch = 4ull * ((uint64_t)d * ff + ff + 2ull * d); break;
+        case 4: *bytes_per_launch = 4ull * ((uint64_t)V * d + d + V); break;
+        case 5: *bytes_per_launch = 4ull * (2ull * T * d + 2ull * d); break;
+        default: *bytes_per_launch = 4ull * 3ull * d; break;
+    }
+    for (uint32_t i = 0; i < 3; i++) launch(i);  // warm-up
+    LB_CUDA(cudaStreamSynchronize(stream));
+    LB_CUDA(cudaEventRecord(ev0, stream));
+    for (uint32_t i = 0; i < iters; i++) launch(i + 3);
+    LB_CUDA(cudaEventRecord(ev1, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    LB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    return ms;
+}
+
+// Host-side twin of k::init_random (same integer recipe as llama.go_b200/synth.py).
+static inline uint64_t splitmix64_host(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma) {
+    const uint64_t base = seed * 0x9E3779B97F4A7C15ull + tid * 0xD1B54A32D192ED03ull;
+    const float sscale = (float)(sigma / IH_STD);
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 32) nt = 32;
+    if (count < (1u << 16)) nt = 1;
+    std::vector<std::thread> th;
+    const uint64_t chunk = (count + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        uint64_t b = (uint64_t)t * chunk, e = b + chunk < count ? b + chunk : count;
+        if (b >= e) break;
+        th.emplace_back([=]() {
+            for (uint64_t i = b; i < e; i++) {
+                uint64_t h = splitmix64_host(base + start + i);
+                int s = (int)(h & 0xFFFF) + (int)((h >> 16) & 0xFFFF) + (int)((h >> 32) & 0xFFFF) + (int)(h >> 48);
+                volatile float tt = (float)(s - 131070) * sscale;  // one rounding, no FMA contraction
+                dst[i] = mean + tt;
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+}
+
+// ---------------------------------------------------------------------------------------------
+// llama.Eval transcribed node for node onto the ml:: mirror (llama.go:211-426).  Every ml.* call
+// below is the same call, with the same arguments, that the reference makes at the cited line.
+void Context::eval_graph(const uint32_t *tokens, uint32_t N, uint32_t pastCount, float *logits_out) {
+    using namespace ml;
+    const HParams &hp = model->hp;
+    LB_CHECK(model->has_embedding() && model->has_head(), "eval_graph : needs a single-stage model");
+    LB_CHECK(N >= 1 && (uint64_t)pastCount + N <= ctx_size, "Eval : pastCount + N exceeds the context size");
+    LB_CUDA(cudaSetDevice(model->device));
+    const uint32_t embdSize = hp.dim, layersCount = hp.layers, ctxSize = ctx_size, headsCount = hp.heads;
+    const uint32_t vocabSize = hp.vocab, rotCount = hp.dim / hp.heads, ff = hp.ff();
+
+    ml::Context mctx(model->device, stream);
+    ml::Context *ctx0 = &mctx;
+    Graph graph;
+    auto weight = [&](float *p, uint32_t ne0, uint32_t ne1) {  // leaves created with ctx == nil in Go
+        return NewTensor(ctx0, TYPE_F32, ne1 > 1 ? 2 : 1, ne0, ne1, 1, 1, p, (size_t)ne0 * ne1);
+    };
+    const size_t kvSize = (size_t)embdSize * layersCount * ctxSize;
+    Tensor *kvK = NewTensor(ctx0, TYPE_F32, 1, (uint32_t)kvSize, 1, 1, 1, kv_k, kvSize);
+    Tensor *kvV = NewTensor(ctx0, TYPE_F32, 1, (uint32_t)kvSize, 1, 1, 1, kv_v, kvSize);
+
+    Tensor *embd = NewTensor1D(ctx0, TYPE_F32, N);  // :239-242 — ids as float32
+    std::vector<float> idsf(N);
+    for (uint32_t i = 0; i < N; i++) {
+        LB_CHECK(tokens[i] < vocabSize, "Eval : token id out of range");
+        idsf[i] = (float)tokens[i];
+    }
+    LB_CUDA(cudaMemcpyAsync(embd->data, idsf.data(), N * sizeof(float), cudaMemcpyHostToDevice, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+
+    Tensor *inpL = GetRows(ctx0, weight(model->tok_embeddings, embdSize, vocabSize), embd);  // :244
+    for (uint32_t il = 0; il < layersCount; il++) {
+        const Layer &L = model->layers[il];
+        Tensor *wq = weight(L.wqkv, embdSize, embdSize);
+        Tensor *wk = weight(L.wqkv + (size_t)embdSize * embdSize, embdSize, embdSize);
+        Tensor *wv = weight(L.wqkv + 2 * (size_t)embdSize * embdSize, embdSize, embdSize);
+        Tensor *inpSA = inpL;
+        Tensor *cur = RMSNorm(ctx0, inpL);                                              // :255
+        Tensor *rep = Repeat(ctx0, weight(L.attention_norm, embdSize, 1), cur);         // :258
+        cur = Mul(ctx0, rep, cur);                                                      // :259
+        Tensor *Qcur = MulMat(ctx0, wq, cur);                                           // :263
+        Tensor *Kcur = MulMat(ctx0, wk, cur);                                           // :264
+        Tensor *Vcur = MulMat(ctx0, wv, cur);                                           // :265
+        Tensor *kview = View1D(ctx0, kvK, N * embdSize, embdSize * (il * ctxSize + pastCount));  // :274
+        Tensor *vview = View1D(ctx0, kvV, N * embdSize, embdSize * (il * ctxSize + pastCount));  // :275
+        BuildForwardExpand(&graph, Copy(ctx0, Kcur, kview));                            // :277
+        BuildForwardExpand(&graph, Copy(ctx0, Vcur, vview));                            // :278
+        Tensor *Q = Permute(ctx0,
+                            Rope(ctx0, Copy(ctx0, Qcur, NewTensor3D(ctx0, TYPE_F32, embdSize / headsCount, headsCount, N)),
+                                 pastCount, rotCount, 0),
+                            0, 2, 1, 3);                                                // :281-288
+        Tensor *K = Permute(ctx0,
+                            Rope(ctx0,
+                                 Reshape3D(ctx0, View1D(ctx0, kvK, (pastCount + N) * embdSize, il * ctxSize * embdSize),
+                                           embdSize / headsCount, headsCount, pastCount + N),
+                                 pastCount, rotCount, 1),
+                            0, 2, 1, 3);                                                // :290-297
+        Tensor *KQ = MulMat(ctx0, K, Q);                                                // :300
+        Tensor *KQScaled = Scale(ctx0, KQ, NewFP32(ctx0, (float)(1.0 / sqrt((double)embdSize / (double)headsCount))));  // :303-307
+        Tensor *KQMasked = DiagMaskInf(ctx0, KQScaled, pastCount);                      // :310
+        Tensor *KQSoftMax = SoftMax(ctx0, KQMasked);                                    // :313
+        Tensor *VTrans = Copy(ctx0,
+                              Permute(ctx0,
+                                      Reshape3D(ctx0, View1D(ctx0, kvV, (pastCount + N) * embdSize, il * ctxSize * embdSize),
+                                                embdSize / headsCount, headsCount, pastCount + N),
+                                      1, 2, 0, 3),
+                              NewTensor3D(ctx0, TYPE_F32, pastCount + N, embdSize / headsCount, headsCount));  // :315-322
+        Tensor *KQV = MulMat(ctx0, VTrans, KQSoftMax);                                  // :325
+        Tensor *KQVMerged = Permute(ctx0, KQV, 0, 2, 1, 3);                             // :328
+        cur = Copy(ctx0, KQVMerged, NewTensor2D(ctx0, TYPE_F32, embdSize, N));          // :331-333
+        cur = MulMat(ctx0, weight(L.wo, embdSize, embdSize), cur);                      // :336
+        Tensor *inpFF = Add(ctx0, cur, inpSA);                                          // :340
+        cur = RMSNorm(ctx0, inpFF);                                                     // :346
+        cur = Mul(ctx0, Repeat(ctx0, weight(L.ffn_norm, embdSize, 1), cur), cur);       // :349-351
+        Tensor *tmp = MulMat(ctx0, weight(L.w3, embdSize, ff), cur);                    // :354
+        cur = MulMat(ctx0, weight(L.w1, embdSize, ff), cur);                            // :356
+        cur = Silu(ctx0, cur);                                                          // :359
+        cur = Mul(ctx0, cur, tmp);                                                      // :361
+        cur = MulMat(ctx0, weight(L.w2, ff, embdSize), cur);                            // :363
+        cur = Add(ctx0, cur, inpFF);                                                    // :366
+        inpL = cur;                                                                     // :369
+    }
+    inpL = RMSNorm(ctx0, inpL);                                                         // :374
+    inpL = Mul(ctx0, Repeat(ctx0, weight(model->norm, embdSize, 1), inpL), inpL);       // :377-379
+    inpL = MulMat(ctx0, weight(model->output, embdSize, vocabSize), inpL);              // :384
+    BuildForwardExpand(&graph, inpL);                                                   // :387
+    GraphCompute(ctx0, &graph);                                                         // :389
+    // :394-401 — row N-1 of the logits
+    if (logits_out)
+        LB_CUDA(cudaMemcpy(logits_out, inpL->data + (size_t)vocabSize * (N - 1), vocabSize * sizeof(float), cudaMemcpyDeviceToHost));
+    last_n = N;
+}
+
+}  // namespace llama
+}  // namespace lb

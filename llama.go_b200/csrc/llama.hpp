@@ -1,0 +1,98 @@
+// llama.hpp — device-resident mirror of pkg/llama's Model / Context / Eval
+// (pkg/llama/llama.go:83-113, 127-204, 211-426).
+#pragma once
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ml.hpp"
+
+namespace lb {
+namespace llama {
+
+struct HParams {  // llama.go:149-158
+    uint32_t vocab = 0, dim = 0, mult = 0, heads = 0, layers = 0;
+    uint32_t ff() const { return ((2 * (4 * dim) / 3 + mult - 1) / mult) * mult; }  // llama.go:761
+    uint32_t head_dim() const { return dim / heads; }
+};
+
+struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] matrix
+    float *attention_norm = nullptr;
+    float *wqkv = nullptr;  // rows [0,dim) = wq, [dim,2dim) = wk, [2dim,3dim) = wv
+    float *wo = nullptr;
+    float *ffn_norm = nullptr;
+    float *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+};
+
+// llama.Model (llama.go:181-193) for one pipeline stage: layers [layer_begin, layer_end).
+struct Model {
+    HParams hp;
+    int device = 0;
+    uint32_t layer_begin = 0, layer_end = 0;
+    int weight_type = 0;
+    bool has_embedding() const { return layer_begin == 0; }
+    bool has_head() const { return layer_end == hp.layers; }
+
+    float *slab = nullptr;  // one allocation for every weight of the stage
+    size_t slab_floats = 0;
+    float *tok_embeddings = nullptr, *norm = nullptr, *output = nullptr;
+    std::vector<Layer> layers;  // index = global layer - layer_begin
+
+    struct Entry { float *ptr; size_t nelem; uint64_t tid; float mean, sigma; };
+    std::map<std::string, Entry> tensors;  // ggjt names (llama.go:826-861) owned by this stage
+
+    Model(const HParams &hp, int device, uint32_t lb, uint32_t le, int weight_type);
+    ~Model();
+    bool owns(const std::string &name) const { return tensors.count(name) != 0; }
+    static bool known_name(const HParams &hp, const std::string &name);
+    void set_tensor(const std::string &name, int dtype, const void *host, size_t nbytes);
+    void get_tensor(const std::string &name, float *host, size_t nelem);
+    void init_random(uint64_t seed);
+    uint64_t weight_bytes_per_token() const;
+};
+
+// llama.Context (llama.go:83-113): FP32 KV cache in HBM + activations + stream + decode graph.
+struct Context {
+    Model *model;
+    uint32_t ctx_size;
+    cudaStream_t stream = nullptr;
+    uint32_t max_batch;
+
+    float *kv_k = nullptr, *kv_v = nullptr;  // [local_layers][ctx][dim]  (llama.go:93-97)
+    float *x = nullptr, *y = nullptr, *cur = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *up = nullptr;
+    float *logits = nullptr;       // [vocab] (last row)
+    float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
+    uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
+    uint32_t tokens_cap = 0;
+    uint32_t *state_dev = nullptr;   // {past, step}
+    uint32_t *state_host = nullptr;  // pinned {past, step}
+    uint32_t *tokens_host = nullptr; // pinned staging
+    float *logits_host = nullptr;    // pinned staging [vocab]
+    cudaGraphExec_t decode_graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t last_n = 0;
+    bool use_graph = true;
+
+    Context(Model *m, uint32_t ctx_size);
+    ~Context();
+
+    // llama.Eval (llama.go:211-426), fused path
+    void eval(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out, bool all_rows,
+              const float *hidden_in_dev = nullptr, float *hidden_out_dev = nullptr);
+    // llama.Eval built node for node with the ml:: op API (slow path)
+    void eval_graph(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
+    float decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t past);
+    float bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch);
+
+   private:
+    void forward(uint32_t n, bool tokens_indirect, bool all_rows, const float *hidden_in, float *hidden_out);
+    void build_decode_graph();
+};
+
+void synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma);
+
+}  // namespace llama
+}  // namespace lb

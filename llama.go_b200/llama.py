@@ -1,0 +1,152 @@
+"""Python mirror of the reference's pkg/llama hot-path API (pkg/llama/llama.go:83-113, 211-426).
+
+    model = llama.Model(hp); model.load(tensors) | model.init_random(seed) | llama.LoadModel(path)
+    lctx  = llama.NewContext(model, ctx_size)
+    llama.Eval(lctx, tokens, pastCount)      # fills lctx.Logits (row N-1), like the reference
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi, synth
+from ._capi import HParamsC, LlamaB200Error, check, check_ptr, lib  # noqa: F401
+
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class Model:
+    """llama.Model (llama.go:181-193), device resident.  layer range = pipeline stage."""
+
+    def __init__(self, hp: synth.HParams, device: int = 0, layer_begin: int = 0, layer_end: int | None = None,
+                 weight_type: int = 0):
+        _capi.require_gpu()
+        self.hp = hp
+        self.device = device
+        self.layer_begin = layer_begin
+        self.layer_end = hp.layers if layer_end is None else layer_end
+        c = HParamsC(hp.vocab, hp.dim, hp.mult, hp.heads, hp.layers)
+        self._h = check_ptr(lib().lb_model_create(C.byref(c), device, self.layer_begin, self.layer_end, weight_type))
+
+    def set_tensor(self, name: str, arr: np.ndarray) -> None:
+        if arr.dtype == np.float16:
+            a, dt = np.ascontiguousarray(arr), 1
+        else:
+            a, dt = np.ascontiguousarray(arr, dtype=np.float32), 0
+        check(lib().lb_model_set_tensor(self._h, name.encode(), dt, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def get_tensor(self, name: str, shape) -> np.ndarray:
+        out = np.empty(int(np.prod(shape)), np.float32)
+        check(lib().lb_model_get_tensor(self._h, name.encode(), out.ctypes.data_as(_f32p), out.size))
+        return out.reshape(shape)
+
+    def load(self, tensors) -> "Model":
+        for name, arr in tensors:
+            self.set_tensor(name, arr)
+        return self
+
+    def init_random(self, seed: int) -> "Model":
+        check(lib().lb_model_init_random(self._h, seed))
+        return self
+
+    @property
+    def weight_bytes_per_token(self) -> int:
+        return lib().lb_model_weight_bytes(self._h)
+
+    def free(self):
+        if self._h:
+            lib().lb_model_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def LoadModel(fileName: str, device: int = 0):
+    """LoadModel (llama.go:712-976): ggjt v1 file -> (vocab, Model)."""
+    hp, vocab, tensors = synth.read_ggjt(fileName)
+    m = Model(hp, device)
+    m.load(tensors.items())
+    return vocab, m
+
+
+class Context:
+    """llama.Context (llama.go:83-88): KV cache + Logits."""
+
+    def __init__(self, model: Model, ctx_size: int):
+        self.model = model
+        self.ctx_size = ctx_size
+        self._h = check_ptr(lib().lb_context_create(model._h, ctx_size))
+        self.Logits = np.zeros(model.hp.vocab, np.float32)
+
+    def ReleaseContext(self):
+        if self._h:
+            lib().lb_context_free(self._h)
+            self._h = None
+
+    def kv(self, layer: int, t0: int, nt: int):
+        d = self.model.hp.dim
+        k = np.empty((nt, d), np.float32)
+        v = np.empty((nt, d), np.float32)
+        check(lib().lb_context_read_kv(self._h, layer, t0, nt, k.ctypes.data_as(_f32p), v.ctypes.data_as(_f32p)))
+        return k, v
+
+    def hidden(self, n: int) -> np.ndarray:
+        out = np.empty((n, self.model.hp.dim), np.float32)
+        check(lib().lb_context_read_hidden(self._h, n, out.ctypes.data_as(_f32p)))
+        return out
+
+    def __del__(self):
+        try:
+            self.ReleaseContext()
+        except Exception:
+            pass
+
+
+def NewContext(model: Model, ctx_size: int) -> Context:
+    return Context(model, ctx_size)
+
+
+def _toks(tokens):
+    t = np.ascontiguousarray(tokens, dtype=np.uint32).reshape(-1)
+    return t, t.ctypes.data_as(_u32p)
+
+
+def Eval(lctx: Context, tokens, pastCount: int) -> np.ndarray:
+    """llama.Eval (llama.go:211-426).  Fills and returns lctx.Logits."""
+    t, p = _toks(tokens)
+    check(lib().lb_eval(lctx._h, p, t.size, pastCount, lctx.Logits.ctypes.data_as(_f32p)))
+    return lctx.Logits
+
+
+def EvalAllLogits(lctx: Context, tokens, pastCount: int) -> np.ndarray:
+    t, p = _toks(tokens)
+    out = np.empty((t.size, lctx.model.hp.vocab), np.float32)
+    check(lib().lb_eval_all_logits(lctx._h, p, t.size, pastCount, out.ctypes.data_as(_f32p)))
+    lctx.Logits[:] = out[-1]
+    return out
+
+
+def EvalGraph(lctx: Context, tokens, pastCount: int) -> np.ndarray:
+    """The same Eval, built node for node with the pkg/ml op API and run by GraphCompute."""
+    t, p = _toks(tokens)
+    check(lib().lb_eval_graph(lctx._h, p, t.size, pastCount, lctx.Logits.ctypes.data_as(_f32p)))
+    return lctx.Logits
+
+
+def DecodeResident(lctx: Context, tokens, pastCount: int) -> float:
+    """Teacher-forced single-token evals enqueued back to back, no host copies; returns CUDA-event ms."""
+    t, p = _toks(tokens)
+    ms = C.c_float(0)
+    check(lib().lb_decode_resident(lctx._h, p, t.size, pastCount, C.byref(ms)))
+    return ms.value
+
+
+def ReadLogits(lctx: Context) -> np.ndarray:
+    check(lib().lb_context_read_logits(lctx._h, lctx.Logits.ctypes.data_as(_f32p)))
+    return lctx.Logits
