@@ -106,6 +106,20 @@ LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint
 LB_API float *lb_context_hidden_buffer(lb_context *c);   /* device [max_batch][dim] scratch for hand-offs */
 LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
 
+/* ---- multi-GPU layer sharding: one process per GPU, NCCL send/recv of the residual stream ----
+ * rank r owns the stage created with lb_model_create(hp, dev, r*L/G, (r+1)*L/G).  NCCL is bound at
+ * run time (dlopen), so the library itself loads without it. */
+LB_API int  lb_comm_unique_id(void *out128);                 /* rank 0: ncclGetUniqueId (128 bytes) */
+LB_API int  lb_comm_init(const void *id128, int rank, int world, int device);   /* ncclCommInitRank */
+LB_API void lb_comm_destroy(void);
+LB_API int  lb_nccl_version(void);
+/* Pipelined steady-state decode of `n_seq` in-flight sequences ("pods", server.go:84-106) for `steps`
+ * tokens each, starting at position `past`: per (step, sequence) this rank receives the residual
+ * [dim] from rank-1, runs its layers, sends it to rank+1; all on one stream, no host sync.  tokens
+ * ([n_seq][steps], teacher-forced) are read on stage 0 only.  ms_out = CUDA-event time on this rank. */
+LB_API int  lb_pipeline_decode(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps,
+                               uint32_t past, float *ms_out);
+
 /* ---- op-level mirror of pkg/ml -------------------------------------------------------- */
 LB_API lb_mlctx  *lb_ml_new_context(int device);                   /* ml.NewContext (ml.go:59-74) */
 LB_API void       lb_ml_release_context(lb_mlctx *ctx);            /* ReleaseContext (ml.go:77-80) */

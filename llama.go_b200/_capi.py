@@ -50,6 +50,11 @@ _SIGS = {
     "lb_eval_stage": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, _vp, _vp, _f32p]),
     "lb_context_hidden_buffer": (_vp, [_vp]),
     "lb_context_stream": (_vp, [_vp]),
+    "lb_comm_unique_id": (C.c_int, [_vp]),
+    "lb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "lb_comm_destroy": (None, []),
+    "lb_nccl_version": (C.c_int, []),
+    "lb_pipeline_decode": (C.c_int, [C.POINTER(_vp), C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _f32p]),
     "lb_ml_new_context": (_vp, [C.c_int]),
     "lb_ml_release_context": (None, [_vp]),
     "lb_new_tensor": (_vp, [_vp, C.c_int] + [C.c_uint32] * 5 + [_f32p]),

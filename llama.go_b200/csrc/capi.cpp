@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "llama.hpp"
 #include "ml.hpp"
@@ -153,6 +154,21 @@ int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t pa
 }
 float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
 void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }
+
+// ---- multi-GPU pipeline ----
+int lb_comm_unique_id(void *out128) { LB_TRY_INT(LB_CHECK(out128, "nil argument"); pipe::unique_id(out128)); }
+int lb_comm_init(const void *id128, int rank, int world, int device) {
+    LB_TRY_INT(LB_CHECK(id128, "nil argument"); require_device(device); pipe::comm_init(id128, rank, world, device));
+}
+void lb_comm_destroy(void) { try { pipe::comm_destroy(); } catch (...) {} }
+int lb_nccl_version(void) { try { return pipe::nccl_version(); } catch (const std::exception &e) { g_err = e.what(); return 0; } }
+int lb_pipeline_decode(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps, uint32_t past, float *ms_out) {
+    LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1, "nil argument");
+               std::vector<llama::Context *> v(n_seq);
+               for (uint32_t i = 0; i < n_seq; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+               float ms = pipe::pipeline_decode(v.data(), n_seq, tokens, steps, past);
+               if (ms_out) *ms_out = ms);
+}
 
 // ---- pkg/ml mirror ----
 lb_mlctx *lb_ml_new_context(int device) {

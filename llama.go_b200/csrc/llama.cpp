@@ -175,6 +175,7 @@ Context::~Context() {
     cudaSetDevice(model->device);
     if (stream) cudaStreamSynchronize(stream);
     if (decode_graph) cudaGraphExecDestroy(decode_graph);
+    if (stage_graph) cudaGraphExecDestroy(stage_graph);
     for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits})
         if (p) cudaFree(p);
     if (tokens_dev) cudaFree(tokens_dev);
@@ -263,6 +264,35 @@ void Context::build_decode_graph() {
     LB_CUDA(cudaStreamEndCapture(stream, &g));
     LB_CUDA(cudaGraphInstantiate(&decode_graph, g, 0));
     cudaGraphDestroy(g);
+}
+
+void Context::ensure_stage_graph(cudaStream_t st) {
+    if (stage_graph) return;
+    LB_CUDA(cudaSetDevice(model->device));
+    cudaStream_t saved = stream;
+    stream = st;
+    // eager warm-up run first (sets kernel attributes; leaves state untouched: no advance)
+    try {
+        forward(1, true, false, x, nullptr);
+        LB_CUDA(cudaStreamSynchronize(st));
+        cudaGraph_t g = nullptr;
+        LB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            forward(1, true, false, x, nullptr);
+            k::advance_state(state_dev, 1, 1, st);
+        } catch (...) {
+            cudaStreamEndCapture(st, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        LB_CUDA(cudaStreamEndCapture(st, &g));
+        LB_CUDA(cudaGraphInstantiate(&stage_graph, g, 0));
+        cudaGraphDestroy(g);
+    } catch (...) {
+        stream = saved;
+        throw;
+    }
+    stream = saved;
 }
 
 void Context::eval(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out, bool all_rows,

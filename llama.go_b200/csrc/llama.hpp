@@ -72,6 +72,7 @@ struct Context {
     uint32_t *tokens_host = nullptr; // pinned staging
     float *logits_host = nullptr;    // pinned staging [vocab]
     cudaGraphExec_t decode_graph = nullptr;
+    cudaGraphExec_t stage_graph = nullptr;   // this stage's layers for one token (pipeline mode)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_n = 0;
     bool use_graph = true;
@@ -86,12 +87,24 @@ struct Context {
     void eval_graph(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
     float decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t past);
     float bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch);
+    // capture (once) the single-token forward of this stage's layers on stream `st`:
+    // [embedding gather on stage 0] -> layers -> [norm + lm_head on the last stage] -> advance {past, step}
+    void ensure_stage_graph(cudaStream_t st);
 
    private:
     void forward(uint32_t n, bool tokens_indirect, bool all_rows, const float *hidden_in, float *hidden_out);
     void build_decode_graph();
 };
 
+}  // namespace llama
+namespace pipe {
+void unique_id(void *out128);
+void comm_init(const void *id128, int rank, int world, int device);
+void comm_destroy();
+int nccl_version();
+float pipeline_decode(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps, uint32_t past);
+}  // namespace pipe
+namespace llama {
 void synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma);
 
 }  // namespace llama

@@ -1,0 +1,154 @@
+// pipeline.cpp — multi-GPU layer sharding: one process per GPU, stage g owns layers
+// [g*L/G, (g+1)*L/G) and the KV slabs of those layers; the only exchange is a point-to-point NCCL
+// send/recv of the residual stream [dim] FP32 between consecutive stages (llama.go:369 `inpL`).
+// No collective is invented: there is no all-reduce/all-gather anywhere on this path.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2": the copy torch already loaded if the host
+// process imported torch, else the system one) so that libllamab200.so itself loads on machines
+// without NCCL or a GPU.
+#include <dlfcn.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "llama.hpp"
+
+namespace lb {
+namespace pipe {
+
+// minimal NCCL ABI (nccl.h: ncclUniqueId is 128 opaque bytes; ncclFloat32 = 7, ncclUint32 = 3... see below)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclFloat32 = 7 };
+
+struct Nccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+static Nccl g_nccl;
+static std::mutex g_mu;
+static ncclComm_t g_comm = nullptr;
+static int g_rank = 0, g_world = 1, g_device = 0;
+
+static void load_nccl() {
+    if (g_nccl.h) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !g_nccl.h; i++) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    LB_CHECK(g_nccl.h != nullptr, std::string("cannot load NCCL: ") + dlerror());
+#define LB_SYM(field, sym)                                              \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.h, sym)); \
+    LB_CHECK(g_nccl.field != nullptr, std::string("NCCL symbol missing: ") + sym)
+    LB_SYM(GetUniqueId, "ncclGetUniqueId");
+    LB_SYM(CommInitRank, "ncclCommInitRank");
+    LB_SYM(CommDestroy, "ncclCommDestroy");
+    LB_SYM(Send, "ncclSend");
+    LB_SYM(Recv, "ncclRecv");
+    LB_SYM(GroupStart, "ncclGroupStart");
+    LB_SYM(GroupEnd, "ncclGroupEnd");
+    LB_SYM(GetErrorString, "ncclGetErrorString");
+    LB_SYM(GetVersion, "ncclGetVersion");
+#undef LB_SYM
+}
+#define LB_NCCL(expr)                                                                                   \
+    do {                                                                                                \
+        ncclResult_t _r = (expr);                                                                       \
+        if (_r != 0) throw lb::Error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));            \
+    } while (0)
+
+void unique_id(void *out128) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    load_nccl();
+    ncclUniqueId id;
+    LB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+}
+
+void comm_init(const void *id128, int rank, int world, int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    LB_CHECK(world >= 1 && rank >= 0 && rank < world, "comm_init: bad rank/world");
+    load_nccl();
+    LB_CHECK(g_comm == nullptr, "comm_init: communicator already initialised");
+    LB_CUDA(cudaSetDevice(device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    LB_NCCL(g_nccl.CommInitRank(&g_comm, world, id, rank));
+    g_rank = rank; g_world = world; g_device = device;
+}
+
+void comm_destroy() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+}
+
+int nccl_version() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    load_nccl();
+    int v = 0;
+    g_nccl.GetVersion(&v);
+    return v;
+}
+
+// Steady-state pipelined decode.  `ctxs[s]` = this stage's context of in-flight sequence s (its own
+// KV slabs and activations).  For step k = 0..steps-1 and sequence s = 0..S-1, in that order on ONE
+// stream:   [recv residual from stage-1]  ->  this stage's layers (CUDA-graph replay)  ->
+//           [send residual to stage+1].
+// Tokens are teacher-forced: stage 0 holds tokens[s][k] (the sampler that would feed tokens back is
+// host code outside this path, pkg/server/server.go:200-214).  The chain is feed-forward, so the
+// blocking send/recv pairs cannot form a cycle.  Returns the CUDA-event time of the whole run on
+// this rank's stream.
+float pipeline_decode(llama::Context **ctxs, uint32_t S, const uint32_t *tokens, uint32_t steps, uint32_t past) {
+    LB_CHECK(S >= 1 && steps >= 1 && ctxs != nullptr, "pipeline_decode: bad arguments");
+    llama::Context *c0 = ctxs[0];
+    llama::Model *m = c0->model;
+    const uint32_t d = m->hp.dim;
+    const bool first = m->has_embedding(), last = m->has_head();
+    const int world = (first && last) ? 1 : g_world;
+    if (world > 1) LB_CHECK(g_comm != nullptr, "pipeline_decode: call lb_comm_init first");
+    LB_CHECK((uint64_t)past + steps <= c0->ctx_size, "pipeline_decode: past + steps exceeds the context size");
+    LB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = c0->stream;
+    for (uint32_t s = 0; s < S; s++) {
+        llama::Context *c = ctxs[s];
+        LB_CHECK(c->model == m, "pipeline_decode: contexts must share the stage model");
+        LB_CHECK(steps <= c->tokens_cap, "pipeline_decode: too many steps");
+        if (first) {
+            LB_CHECK(tokens != nullptr, "pipeline_decode: stage 0 needs tokens");
+            for (uint32_t k = 0; k < steps; k++) {
+                LB_CHECK(tokens[(size_t)s * steps + k] < m->hp.vocab, "pipeline_decode: token id out of range");
+                c->tokens_host[k] = tokens[(size_t)s * steps + k];
+            }
+            LB_CUDA(cudaMemcpyAsync(c->tokens_dev, c->tokens_host, steps * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
+        c->state_host[0] = past; c->state_host[1] = 0;
+        LB_CUDA(cudaMemcpyAsync(c->state_dev, c->state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        c->ensure_stage_graph(st);
+    }
+    LB_CUDA(cudaStreamSynchronize(st));
+    LB_CUDA(cudaEventRecord(c0->ev0, st));
+    for (uint32_t k = 0; k < steps; k++) {
+        for (uint32_t s = 0; s < S; s++) {
+            llama::Context *c = ctxs[s];
+            if (!first) LB_NCCL(g_nccl.Recv(c->x, d, ncclFloat32, g_rank - 1, g_comm, st));
+            LB_CUDA(cudaGraphLaunch(c->stage_graph, st));
+            count_launch(m->layers.size() * 8 + 4);
+            if (!last) LB_NCCL(g_nccl.Send(c->x, d, ncclFloat32, g_rank + 1, g_comm, st));
+        }
+    }
+    LB_CUDA(cudaEventRecord(c0->ev1, st));
+    LB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    LB_CUDA(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
+    return ms;
+}
+
+}  // namespace pipe
+}  // namespace lb
