@@ -1,0 +1,113 @@
+"""Multi-GPU arm of bench.py: LLaMA-7B FP32 decode, layer-sharded over N GPUs (one process per GPU,
+launched by torchrun), N sequences in flight, NCCL send/recv of the residual between stages.
+
+A step = every in-flight sequence advances one token (N tokens per step, "scaling": "weak": each GPU
+streams 1/N of the weights N times per step = the same bytes per step as the single-GPU arm)."""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from bench import CTX, METRIC, PROMPT_LEN, UNIT, ClockSampler, measured_peak, rank_world
+
+
+def run_pipeline(args):
+    import torch
+    import torch.distributed as dist
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import _capi, pipeline, synth
+
+    rank, world, local = rank_world()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _capi.require_gpu()
+    lib = _capi.lib()
+    uid = pipeline.exchange_unique_id(rank, dist)
+    _capi.check(lib.lb_comm_init(uid, rank, world, local))
+
+    hp = synth.LLAMA_7B
+    K, W = args.steps, args.warmup
+    S = world                                   # sequences in flight
+    ctx_size = max(CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
+    t_setup = time.time()
+    stage = pipeline.Stage(hp, rank, world, local, ctx_size, S, seed=0)
+    rs = np.random.RandomState(0)
+    prompt = rs.randint(3, hp.vocab, size=(S, PROMPT_LEN)).astype(np.uint32)
+    gen = rs.randint(3, hp.vocab, size=(S, 2 * W + 2 * K)).astype(np.uint32)
+    stage.prefill(prompt, 0)                    # setup, untimed
+    t_setup = time.time() - t_setup
+
+    def sync_all():
+        for c in stage.ctxs[:1]:
+            _capi.check(lib.lb_context_synchronize(c._h))
+        dist.barrier()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: K pipelined steps, device timed, max over ranks
+    stage.decode(gen[:, :W], PROMPT_LEN)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.lb_kernel_launches()
+    ms = stage.decode(gen[:, W:W + K], PROMPT_LEN + W)
+    sync_all()
+    launches = lib.lb_kernel_launches() - l0
+    ms = max_over_ranks(ms)
+    value = S * K / (ms / 1e3)
+
+    # ---- e2e: host-driven, one synchronous pipelined step at a time (token ids H2D on rank 0,
+    #      logits of every sequence D2H on the last rank, inside the timed region)
+    past = PROMPT_LEN + W + K
+    for i in range(W):
+        stage.decode(gen[:, W + K + i:W + K + i + 1], past + i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        stage.decode(gen[:, 2 * W + K + i:2 * W + K + i + 1], past + W + i)
+        if stage.is_last:
+            for s in range(S):
+                stage.logits(s)
+    sync_all()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = S * K / e2e_s
+
+    all_launches = torch.tensor([float(launches)], dtype=torch.float64)
+    dist.all_reduce(all_launches, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        T_mid = PROMPT_LEN + W + K / 2.0
+        bytes_per_token = 26429390848 + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+        agg_gbs = bytes_per_token * value / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LLaMA-7B FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
+                                   % (ctx_size, PROMPT_LEN, S),
+                       "parallelism": "pp%d (layer-sharded, %d layers/GPU, NCCL send/recv of the residual)" % (world, hp.layers // world),
+                       "sequences_in_flight": S, "tokens_per_step": S, "weights": "random-init (device RNG, seed 0)",
+                       "kv_cache": "fp32 in HBM", "l2": "inputs>L2", "setup_s": round(t_setup, 1),
+                       "note": "a single sequence gains nothing from layer sharding (dependency chain); "
+                               "throughput is aggregate over the in-flight sequences (the reference's pods)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * S + 8 * S, "d2h_bytes_per_step": 4 * hp.vocab * S,
+                    "api": "lb_pipeline_decode(steps=1) + lb_context_read_logits per sequence, synchronous per step"},
+            "gpu_launches": int(all_launches.item()),
+            "roofline": {"bound": "hbm", "kernel": "whole step (aggregate over GPUs)", "achieved": round(agg_gbs, 1),
+                         "peak": peak * world, "unit": "GB/s", "frac": round(agg_gbs / (peak * world), 4), "traffic": None,
+                         "peak_source": peak_src + " x n_gpus"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    lib.lb_comm_destroy()
+    dist.destroy_process_group()

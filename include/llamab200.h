@@ -120,6 +120,9 @@ LB_API int  lb_nccl_version(void);
 LB_API int  lb_pipeline_decode(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps,
                                uint32_t past, float *ms_out);
 
+/* One pipelined pass of n tokens per sequence (prompt prefill) through this rank's layers. */
+LB_API int  lb_pipeline_prefill(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past);
+
 /* ---- op-level mirror of pkg/ml -------------------------------------------------------- */
 LB_API lb_mlctx  *lb_ml_new_context(int device);                   /* ml.NewContext (ml.go:59-74) */
 LB_API void       lb_ml_release_context(lb_mlctx *ctx);            /* ReleaseContext (ml.go:77-80) */

@@ -55,6 +55,7 @@ _SIGS = {
     "lb_comm_destroy": (None, []),
     "lb_nccl_version": (C.c_int, []),
     "lb_pipeline_decode": (C.c_int, [C.POINTER(_vp), C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _f32p]),
+    "lb_pipeline_prefill": (C.c_int, [C.POINTER(_vp), C.c_uint32, _u32p, C.c_uint32, C.c_uint32]),
     "lb_ml_new_context": (_vp, [C.c_int]),
     "lb_ml_release_context": (None, [_vp]),
     "lb_new_tensor": (_vp, [_vp, C.c_int] + [C.c_uint32] * 5 + [_f32p]),

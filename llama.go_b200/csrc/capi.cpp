@@ -170,6 +170,13 @@ int lb_pipeline_decode(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens
                if (ms_out) *ms_out = ms);
 }
 
+int lb_pipeline_prefill(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past) {
+    LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1, "nil argument");
+               std::vector<llama::Context *> v(n_seq);
+               for (uint32_t i = 0; i < n_seq; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+               pipe::pipeline_prefill(v.data(), n_seq, tokens, n, past));
+}
+
 // ---- pkg/ml mirror ----
 lb_mlctx *lb_ml_new_context(int device) {
     try {

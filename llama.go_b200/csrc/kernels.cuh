@@ -58,6 +58,11 @@ void rope_qk_store(float *q, const float *k, const float *v, uint32_t ld, float 
 // max_T bounds past+N (sizes the shared-memory score buffer at launch/capture time).
 void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,
                const uint32_t *past_dev, uint32_t max_T, uint32_t dim, uint32_t heads, cudaStream_t st);
+// decode (N == 1) variant: T split over many CTAs per head + merge; scratch from
+// attention_decode_scratch_floats() must be zero-initialised once (ticket counters).
+void attention_decode(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
+                      uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, cudaStream_t st);
+size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd);
 // single-token embedding gather for graph replay: row = table[tokens[*step_dev + n]]
 void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, const uint32_t *step_dev,
                        uint32_t nr, float *dst, cudaStream_t st);

@@ -89,6 +89,172 @@ attention_kernel(const float *__restrict__ q, uint32_t ldq, const float *__restr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Decode attention (N == 1): split the T cached positions over SPLITS CTAs per head so that the
+// whole chip streams the layer's K/V slab (2*T*dim*4 bytes) instead of one CTA per head.
+// Each CTA: scores for its key range, local max m, e = f32(exp(f64(s - m))), local sum l, partial
+// O = sum_t e_t * V[t]; the last CTA to finish a head (atomic ticket) merges the partials:
+// M = max m_s, L = sum l_s * w_s, out = (sum O_s * w_s) * f32(1/L), w_s = f32(exp(f64(m_s - M))).
+// Versus the reference's single-pass softmax this reassociates the sums and applies the
+// normaliser after P·V — a few 1e-7 relative.
+// ------------------------------------------------------------------------------------------
+constexpr int DEC_THREADS = 128;
+constexpr int DEC_MAX_SPLITS = 32;
+
+template <int HD>
+__global__ void __launch_bounds__(DEC_THREADS)
+attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ Kc, const float *__restrict__ Vc,
+                        float *__restrict__ out, const uint32_t *__restrict__ past_dev, uint32_t dim,
+                        float scale, float *__restrict__ part_o, float *__restrict__ part_ml,
+                        unsigned int *__restrict__ tickets, uint32_t chunk_cap) {
+    extern __shared__ float sm[];  // scores[chunk_cap]
+    __shared__ float red[DEC_THREADS / 32];
+    __shared__ float s_bcast;
+    __shared__ unsigned int s_ticket;
+    const uint32_t h = blockIdx.x, sp = blockIdx.y, S = gridDim.y;
+    const uint32_t Tn = *past_dev + 1;
+    const uint32_t chunk = min((Tn + S - 1) / S, chunk_cap);
+    const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn);
+    const uint32_t nk = t1 - t0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int LANES = HD / 4;  // lanes that hold a float4 of the head
+    const float *qh = q + (size_t)h * HD;
+    const float *kbase = Kc + (size_t)h * HD, *vbase = Vc + (size_t)h * HD;
+
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < LANES) qv = *reinterpret_cast<const float4 *>(qh + lane * 4);
+    // ---- scores: warp w takes keys t0 + w, t0 + w + 4, ...; 4 keys in flight per warp
+    constexpr int NW = DEC_THREADS / 32;
+    for (uint32_t i = warp; i < nk; i += NW * 4) {
+        float4 kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t ii = i + u * NW;
+            kv[u] = (ii < nk && lane < LANES) ? ld_stream_f4(kbase + (size_t)(t0 + ii) * dim + lane * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t ii = i + u * NW;
+            float d = kv[u].x * qv.x;
+            d = fmaf(kv[u].y, qv.y, d); d = fmaf(kv[u].z, qv.z, d); d = fmaf(kv[u].w, qv.w, d);
+            d = warp_sum(d);
+            if (lane == 0 && ii < nk) sm[ii] = __fmul_rn(d, scale);
+        }
+    }
+    __syncthreads();
+    // ---- local softmax statistics
+    float m = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < nk; i += DEC_THREADS) m = fmaxf(m, sm[i]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int i = 1; i < NW; i++) t = fmaxf(t, red[i]);
+        s_bcast = t;
+    }
+    __syncthreads();
+    m = s_bcast;
+    float l = 0.f;
+    for (uint32_t i = threadIdx.x; i < nk; i += DEC_THREADS) {
+        float e = (float)exp((double)__fsub_rn(sm[i], m));
+        sm[i] = e;
+        l += e;
+    }
+    l = warp_sum(l);
+    __syncthreads();
+    if (lane == 0) red[warp] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < NW; i++) t += red[i];
+        part_ml[((size_t)h * S + sp) * 2 + 0] = m;
+        part_ml[((size_t)h * S + sp) * 2 + 1] = t;
+    }
+    // ---- partial P·V: DEC_THREADS/HD groups, thread (g, d) takes keys g, g+G, ... (8 loads in flight)
+    constexpr int G = DEC_THREADS / HD;
+    const uint32_t g = threadIdx.x / HD, d = threadIdx.x % HD;
+    float acc = 0.f;
+    {
+        const float *vp = vbase + d;
+        uint32_t i = g;
+        for (; i + 7 * G < nk; i += 8 * G) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldg(vp + (size_t)(t0 + i + u * G) * dim);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fmaf(v[u], sm[i + u * G], acc);
+        }
+        for (; i < nk; i += G) acc = fmaf(__ldg(vp + (size_t)(t0 + i) * dim), sm[i], acc);
+    }
+    if (G > 1) {
+        __shared__ float pv[DEC_THREADS];
+        pv[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < HD) {
+            for (int i = 1; i < G; i++) acc += pv[i * HD + threadIdx.x];
+        }
+    }
+    if (threadIdx.x < HD) part_o[((size_t)h * S + sp) * HD + threadIdx.x] = acc;
+    // ---- ticket: the last CTA of this head merges
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[h], 1u);
+    __syncthreads();
+    if (s_ticket != S - 1) return;
+    __threadfence();
+    float M = -INFINITY;
+    for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&part_ml[((size_t)h * S + s2) * 2]));
+    float L = 0.f, o = 0.f;
+    if (threadIdx.x < HD) {
+        for (uint32_t s2 = 0; s2 < S; s2++) {
+            float ms = __ldcg(&part_ml[((size_t)h * S + s2) * 2]);
+            float ls = __ldcg(&part_ml[((size_t)h * S + s2) * 2 + 1]);
+            if (ls > 0.f) {
+                float w = (float)exp((double)__fsub_rn(ms, M));
+                L = fmaf(ls, w, L);
+                o = fmaf(__ldcg(&part_o[((size_t)h * S + s2) * HD + threadIdx.x]), w, o);
+            }
+        }
+        out[(size_t)h * HD + threadIdx.x] = __fmul_rn(o, __fdiv_rn(1.0f, L));
+    }
+    if (threadIdx.x == 0) tickets[h] = 0;  // ready for the next launch / graph replay
+}
+
+uint32_t attention_decode_splits(uint32_t max_T) {
+    uint32_t s = (max_T + 31) / 32;
+    if (s < 1) s = 1;
+    if (s > DEC_MAX_SPLITS) s = DEC_MAX_SPLITS;
+    return s;
+}
+size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd) {
+    // part_o [H][S][hd] + part_ml [H][S][2] + tickets [H] (as uint32)
+    return (size_t)heads * DEC_MAX_SPLITS * (hd + 2) + heads;
+}
+
+void attention_decode(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
+                      uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, cudaStream_t st) {
+    const uint32_t hd = dim / heads;
+    LB_CHECK(hd == 32 || hd == 64 || hd == 128, "attention: head dim must be 32, 64 or 128");
+    const uint32_t S = attention_decode_splits(max_T);
+    const uint32_t chunk_cap = (max_T + S - 1) / S;
+    float *part_o = scratch;
+    float *part_ml = part_o + (size_t)heads * DEC_MAX_SPLITS * hd;
+    unsigned int *tickets = reinterpret_cast<unsigned int *>(part_ml + (size_t)heads * DEC_MAX_SPLITS * 2);
+    float scale = (float)(1.0 / sqrt((double)dim / (double)heads));  // llama.go:306
+    size_t smem = (size_t)chunk_cap * sizeof(float);
+    LB_CHECK(smem <= 40 * 1024, "attention_decode: context too long");
+    dim3 grid(heads, S);
+    if (hd == 128)
+        attention_decode_kernel<128><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+    else if (hd == 64)
+        attention_decode_kernel<64><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+    else
+        attention_decode_kernel<32><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+    LB_LAUNCH_CHECK();
+}
+
 void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,
                const uint32_t *past_dev, uint32_t max_T, uint32_t dim, uint32_t heads, cudaStream_t st) {
     const uint32_t hd = dim / heads;

@@ -74,9 +74,61 @@ __global__ void __launch_bounds__(256) rms_norm_kernel(const float *__restrict__
         yr[i] = w ? __fmul_rn(w[i], v) : v;
     }
 }
+// Fast path (nc % 4 == 0, nc <= 8192): the row is read ONCE with 128-bit loads into registers
+// (all loads issued before the first use), reduced, and written back from registers.
+template <int VPT>  // float4 per thread
+__global__ void __launch_bounds__(256) rms_norm_reg_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                           float *__restrict__ y, uint32_t nc) {
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)blockIdx.x * nc);
+    float4 *yr = reinterpret_cast<float4 *>(y + (size_t)blockIdx.x * nc);
+    const uint32_t n4 = nc >> 2;
+    float4 v[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        uint32_t idx = threadIdx.x + i * 256;
+        v[i] = idx < n4 ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        acc += (double)__fmul_rn(v[i].x, v[i].x);
+        acc += (double)__fmul_rn(v[i].y, v[i].y);
+        acc += (double)__fmul_rn(v[i].z, v[i].z);
+        acc += (double)__fmul_rn(v[i].w, v[i].w);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        s_scale = (float)(1.0 / sqrt(t / (double)nc + 1e-5));
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    const float4 *wr = reinterpret_cast<const float4 *>(w);
+#pragma unroll
+    for (int i = 0; i < VPT; i++) {
+        uint32_t idx = threadIdx.x + i * 256;
+        if (idx < n4) {
+            float4 o;
+            o.x = __fmul_rn(v[i].x, sc); o.y = __fmul_rn(v[i].y, sc); o.z = __fmul_rn(v[i].z, sc); o.w = __fmul_rn(v[i].w, sc);
+            if (w) {
+                float4 ww = __ldg(wr + idx);
+                o.x = __fmul_rn(ww.x, o.x); o.y = __fmul_rn(ww.y, o.y); o.z = __fmul_rn(ww.z, o.z); o.w = __fmul_rn(ww.w, o.w);
+            }
+            yr[idx] = o;
+        }
+    }
+}
 void rms_norm(const float *x, const float *w, float *y, uint32_t nc, uint32_t nr, cudaStream_t st) {
     if (!nr) return;
-    rms_norm_kernel<<<nr, 256, 0, st>>>(x, w, y, nc);
+    const bool aligned = (nc & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w & 15) == 0;
+    if (aligned && nc <= 4096) rms_norm_reg_kernel<4><<<nr, 256, 0, st>>>(x, w, y, nc);
+    else if (aligned && nc <= 8192) rms_norm_reg_kernel<8><<<nr, 256, 0, st>>>(x, w, y, nc);
+    else rms_norm_kernel<<<nr, 256, 0, st>>>(x, w, y, nc);
     LB_LAUNCH_CHECK();
 }
 

@@ -158,6 +158,7 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     qkv = dalloc((size_t)max_batch * 3 * d); attn = dalloc((size_t)max_batch * d);
     act = dalloc((size_t)max_batch * ff); up = dalloc((size_t)max_batch * ff);
     logits = dalloc(V);
+    attn_scratch = dalloc(k::attention_decode_scratch_floats(hp.heads, hp.head_dim()));
     tokens_cap = max_batch + 4096;
     LB_CUDA(cudaMalloc(&tokens_dev, tokens_cap * sizeof(uint32_t)));
     LB_CUDA(cudaMemset(tokens_dev, 0, tokens_cap * sizeof(uint32_t)));
@@ -176,7 +177,7 @@ Context::~Context() {
     if (stream) cudaStreamSynchronize(stream);
     if (decode_graph) cudaGraphExecDestroy(decode_graph);
     if (stage_graph) cudaGraphExecDestroy(stage_graph);
-    for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits})
+    for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits, attn_scratch})
         if (p) cudaFree(p);
     if (tokens_dev) cudaFree(tokens_dev);
     if (state_dev) cudaFree(state_dev);
@@ -221,7 +222,8 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         k::rms_norm(x, L.attention_norm, cur, d, n, st);
         matmul(L.wqkv, 3 * d, d, cur, d, n, qkv, 3 * d, nullptr, st);
         k::rope_qk_store(qkv, qkv + d, qkv + 2 * d, 3 * d, Kc, Vc, n, past_dev, d, H, st);
-        k::attention(qkv, 3 * d, Kc, Vc, attn, n, past_dev, ctx_size, d, H, st);
+        if (n == 1) k::attention_decode(qkv, Kc, Vc, attn, past_dev, ctx_size, d, H, attn_scratch, st);
+        else k::attention(qkv, 3 * d, Kc, Vc, attn, n, past_dev, ctx_size, d, H, st);
         matmul(L.wo, d, d, attn, d, n, y, d, x, st);
         k::rms_norm(y, L.ffn_norm, cur, d, n, st);
         if (n <= 8) {
@@ -264,6 +266,19 @@ void Context::build_decode_graph() {
     LB_CUDA(cudaStreamEndCapture(stream, &g));
     LB_CUDA(cudaGraphInstantiate(&decode_graph, g, 0));
     cudaGraphDestroy(g);
+}
+
+void Context::forward_on(cudaStream_t st, uint32_t n) {
+    cudaStream_t saved = stream;
+    stream = st;
+    try {
+        forward(n, false, false, x, nullptr);
+    } catch (...) {
+        stream = saved;
+        throw;
+    }
+    stream = saved;
+    last_n = n;
 }
 
 void Context::ensure_stage_graph(cudaStream_t st) {
@@ -392,7 +407,7 @@ float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *
             case 3: k::gemv_f32(L.w2, d, ff, act, ff, 1, up, d, y, stream); break;
             case 4: LB_CHECK(model->has_head(), "no lm_head on this stage");
                     k::gemv_f32(model->output, V, d, cur, d, 1, logits, V, nullptr, stream); break;
-            case 5: k::attention(qkv, 3 * d, Kc, Vc, attn, 1, state_dev, ctx_size, d, H, stream); break;
+            case 5: k::attention_decode(qkv, Kc, Vc, attn, state_dev, ctx_size, d, H, attn_scratch, stream); break;
             case 6: k::rms_norm(x, L.attention_norm, cur, d, 1, stream); break;
             default: LB_CHECK(false, "bench_kernel : unknown kernel id");
         }

@@ -63,6 +63,7 @@ struct Context {
 
     float *kv_k = nullptr, *kv_v = nullptr;  // [local_layers][ctx][dim]  (llama.go:93-97)
     float *x = nullptr, *y = nullptr, *cur = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *up = nullptr;
+    float *attn_scratch = nullptr; // split-T decode attention partials + tickets
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
@@ -90,6 +91,8 @@ struct Context {
     // capture (once) the single-token forward of this stage's layers on stream `st`:
     // [embedding gather on stage 0] -> layers -> [norm + lm_head on the last stage] -> advance {past, step}
     void ensure_stage_graph(cudaStream_t st);
+    // this stage's layers for n tokens, eagerly, on stream `st` (x holds the incoming residual on stages > 0)
+    void forward_on(cudaStream_t st, uint32_t n);
 
    private:
     void forward(uint32_t n, bool tokens_indirect, bool all_rows, const float *hidden_in, float *hidden_out);
@@ -103,6 +106,7 @@ void comm_init(const void *id128, int rank, int world, int device);
 void comm_destroy();
 int nccl_version();
 float pipeline_decode(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps, uint32_t past);
+void pipeline_prefill(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past);
 }  // namespace pipe
 namespace llama {
 void synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma);

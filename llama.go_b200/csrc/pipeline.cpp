@@ -150,5 +150,38 @@ float pipeline_decode(llama::Context **ctxs, uint32_t S, const uint32_t *tokens,
     return ms;
 }
 
+// One pipelined pass of `n` tokens per sequence (prompt prefill): per sequence this rank receives
+// the residual [n][dim], runs its layers eagerly (GEMM path for n > 8), sends it on.
+void pipeline_prefill(llama::Context **ctxs, uint32_t S, const uint32_t *tokens, uint32_t n, uint32_t past) {
+    LB_CHECK(S >= 1 && n >= 1 && ctxs != nullptr, "pipeline_prefill: bad arguments");
+    llama::Context *c0 = ctxs[0];
+    llama::Model *m = c0->model;
+    const uint32_t d = m->hp.dim;
+    const bool first = m->has_embedding(), last = m->has_head();
+    const int world = (first && last) ? 1 : g_world;
+    if (world > 1) LB_CHECK(g_comm != nullptr, "pipeline_prefill: call lb_comm_init first");
+    LB_CHECK((uint64_t)past + n <= c0->ctx_size && n <= c0->max_batch, "pipeline_prefill: past + n exceeds the context size");
+    LB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = c0->stream;
+    for (uint32_t s = 0; s < S; s++) {
+        llama::Context *c = ctxs[s];
+        LB_CHECK(c->model == m, "pipeline_prefill: contexts must share the stage model");
+        if (first) {
+            LB_CHECK(tokens != nullptr, "pipeline_prefill: stage 0 needs tokens");
+            for (uint32_t i = 0; i < n; i++) {
+                LB_CHECK(tokens[(size_t)s * n + i] < m->hp.vocab, "pipeline_prefill: token id out of range");
+                c->tokens_host[i] = tokens[(size_t)s * n + i];
+            }
+            LB_CUDA(cudaMemcpyAsync(c->tokens_dev, c->tokens_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
+        c->state_host[0] = past; c->state_host[1] = 0;
+        LB_CUDA(cudaMemcpyAsync(c->state_dev, c->state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (!first) LB_NCCL(g_nccl.Recv(c->x, (size_t)n * d, ncclFloat32, g_rank - 1, g_comm, st));
+        c->forward_on(st, n);
+        if (!last) LB_NCCL(g_nccl.Send(c->x, (size_t)n * d, ncclFloat32, g_rank + 1, g_comm, st));
+        LB_CUDA(cudaStreamSynchronize(st));  // pinned staging buffers are reused by the next sequence
+    }
+}
+
 }  // namespace pipe
 }  // namespace lb
