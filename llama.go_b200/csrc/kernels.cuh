@@ -69,5 +69,15 @@ void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, 
 // state[0] (= past) += dp; state[1] (= step) += ds
 void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
 
+// ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
+void quantize_q8(const float *W, int8_t *q, float *d, size_t nelem, cudaStream_t st);
+void dequantize_q8(const int8_t *q, const float *d, float *out, size_t nelem, cudaStream_t st);
+void gemv_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N,
+             float *y, uint32_t ldy, const float *residual, cudaStream_t st);
+void gemv_q8_swiglu(const int8_t *Q1, const float *D1, const int8_t *Q3, const float *D3, uint32_t M, uint32_t K,
+                    const float *x, uint32_t ldx, uint32_t N, float *act, uint32_t ldy, cudaStream_t st);
+void gemm_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+             float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
+
 }  // namespace k
 }  // namespace lb

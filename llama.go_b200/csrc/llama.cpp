@@ -33,109 +33,161 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     LB_CHECK(hp.dim % hp.heads == 0, "model: dim must be divisible by heads");
     LB_CHECK(hp.dim % 4 == 0, "model: dim must be a multiple of 4");
     LB_CHECK(layer_begin < layer_end && layer_end <= hp.layers, "model: bad layer range");
-    LB_CHECK(wt == 0, "model: only LB_TYPE_F32 weights are implemented in this build");
+    LB_CHECK(wt == 0 || wt == 16, "model: weight type must be LB_TYPE_F32 or LB_TYPE_Q8_0");
+    if (q8()) LB_CHECK(hp.dim % 32 == 0 && hp.ff() % 32 == 0, "model: Q8_0 needs dim and ff to be multiples of 32");
     LB_CUDA(cudaSetDevice(device));
     const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
     const size_t A = 64;  // floats: 256-byte alignment of every tensor
-    size_t total = 0;
+    size_t total = 0, qtotal = 0, dtotal = 0;
     auto reserve = [&](size_t n) { size_t off = total; total += align_up(n, A); return off; };
-    size_t o_emb = 0, o_norm = 0, o_out = 0;
+    // a MulMat matrix: float slab (F32) or q/d planes (Q8_0); returns {float off, q off, d off}
+    struct MOff { size_t f, q, d; };
+    auto reserve_mat = [&](size_t n) {
+        MOff o{0, 0, 0};
+        if (q8()) { o.q = qtotal; qtotal += align_up(n, 256); o.d = dtotal; dtotal += align_up(n / 32, A); }
+        else o.f = reserve(n);
+        return o;
+    };
+    size_t o_emb = 0, o_norm = 0;
+    MOff o_out{0, 0, 0};
     if (has_embedding()) o_emb = reserve(V * d);
-    if (has_head()) { o_norm = reserve(d); o_out = reserve(V * d); }
-    struct LOff { size_t an, qkv, wo, fn, w1, w2, w3; };
+    if (has_head()) { o_norm = reserve(d); o_out = reserve_mat(V * d); }
+    struct LOff { size_t an, fn; MOff qkv, wo, w1, w2, w3; };
     std::vector<LOff> lo(layer_end - layer_begin);
     for (auto &l : lo) {
-        l.an = reserve(d); l.qkv = reserve(3 * d * d); l.wo = reserve(d * d); l.fn = reserve(d);
-        l.w1 = reserve(ff * d); l.w3 = reserve(ff * d); l.w2 = reserve(d * ff);
+        l.an = reserve(d); l.qkv = reserve_mat(3 * d * d); l.wo = reserve_mat(d * d); l.fn = reserve(d);
+        l.w1 = reserve_mat(ff * d); l.w3 = reserve_mat(ff * d); l.w2 = reserve_mat(d * ff);
     }
     slab_floats = total;
-    LB_CUDA(cudaMalloc(&slab, total * sizeof(float)));
-    LB_CUDA(cudaMemset(slab, 0, total * sizeof(float)));
-    const float sd = 1.0f / sqrtf((float)d), sff = 1.0f / sqrtf((float)ff);
+    LB_CUDA(cudaMalloc(&slab, (total ? total : 1) * sizeof(float)));
+    LB_CUDA(cudaMemset(slab, 0, (total ? total : 1) * sizeof(float)));
+    if (q8()) {
+        LB_CUDA(cudaMalloc(&qslab, qtotal ? qtotal : 1));
+        LB_CUDA(cudaMemset(qslab, 0, qtotal ? qtotal : 1));
+        LB_CUDA(cudaMalloc(&dslab, (dtotal ? dtotal : 1) * sizeof(float)));
+        LB_CUDA(cudaMemset(dslab, 0, (dtotal ? dtotal : 1) * sizeof(float)));
+    }
+    auto fptr = [&](const MOff &o) { return q8() ? nullptr : slab + o.f; };
+    auto qmat = [&](const MOff &o, size_t row_off_elems = 0) {
+        Q8Mat m;
+        if (q8()) { m.q = qslab + o.q + row_off_elems; m.d = dslab + o.d + row_off_elems / 32; }
+        return m;
+    };
+    const float sdd = (float)pow((double)d, -0.5), sf = (float)pow((double)ff, -0.5);
     if (has_embedding()) {
         tok_embeddings = slab + o_emb;
-        tensors["tok_embeddings.weight"] = {tok_embeddings, V * d, 1, 0.f, 1.f};
+        tensors["tok_embeddings.weight"] = {tok_embeddings, V * d, 1, 0.f, 1.f, Q8Mat()};
     }
     if (has_head()) {
-        norm = slab + o_norm; output = slab + o_out;
-        tensors["norm.weight"] = {norm, d, 2, 1.f, 0.1f};
-        tensors["output.weight"] = {output, V * d, 3, 0.f, (float)pow((double)d, -0.5)};
+        norm = slab + o_norm; output = fptr(o_out); output8 = qmat(o_out);
+        tensors["norm.weight"] = {norm, d, 2, 1.f, 0.1f, Q8Mat()};
+        tensors["output.weight"] = {output, V * d, 3, 0.f, sdd, output8};
     }
     layers.resize(lo.size());
     for (size_t i = 0; i < lo.size(); i++) {
         Layer &L = layers[i];
-        L.attention_norm = slab + lo[i].an; L.wqkv = slab + lo[i].qkv; L.wo = slab + lo[i].wo;
-        L.ffn_norm = slab + lo[i].fn; L.w1 = slab + lo[i].w1; L.w3 = slab + lo[i].w3; L.w2 = slab + lo[i].w2;
+        L.attention_norm = slab + lo[i].an; L.ffn_norm = slab + lo[i].fn;
+        L.wqkv = fptr(lo[i].qkv); L.wo = fptr(lo[i].wo); L.w1 = fptr(lo[i].w1); L.w3 = fptr(lo[i].w3); L.w2 = fptr(lo[i].w2);
+        L.wqkv8 = qmat(lo[i].qkv); L.wo8 = qmat(lo[i].wo); L.w18 = qmat(lo[i].w1); L.w38 = qmat(lo[i].w3); L.w28 = qmat(lo[i].w2);
         uint32_t il = layer_begin + (uint32_t)i;
         std::string p = "layers." + std::to_string(il) + ".";
         uint64_t base = 16ull * (il + 1);
-        const float sdd = (float)pow((double)d, -0.5), sf = (float)pow((double)ff, -0.5);
-        (void)sd; (void)sff;
-        tensors[p + "attention_norm.weight"] = {L.attention_norm, d, base + 0, 1.f, 0.1f};
-        tensors[p + "attention.wq.weight"] = {L.wqkv, d * d, base + 1, 0.f, sdd};
-        tensors[p + "attention.wk.weight"] = {L.wqkv + d * d, d * d, base + 2, 0.f, sdd};
-        tensors[p + "attention.wv.weight"] = {L.wqkv + 2 * d * d, d * d, base + 3, 0.f, sdd};
-        tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd};
-        tensors[p + "ffn_norm.weight"] = {L.ffn_norm, d, base + 5, 1.f, 0.1f};
-        tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd};
-        tensors[p + "feed_forward.w2.weight"] = {L.w2, d * ff, base + 7, 0.f, sf};
-        tensors[p + "feed_forward.w3.weight"] = {L.w3, ff * d, base + 8, 0.f, sdd};
+        auto fq = [&](size_t rows_off) { return q8() ? nullptr : L.wqkv + rows_off; };
+        tensors[p + "attention_norm.weight"] = {L.attention_norm, d, base + 0, 1.f, 0.1f, Q8Mat()};
+        tensors[p + "attention.wq.weight"] = {fq(0), d * d, base + 1, 0.f, sdd, qmat(lo[i].qkv, 0)};
+        tensors[p + "attention.wk.weight"] = {fq(d * d), d * d, base + 2, 0.f, sdd, qmat(lo[i].qkv, d * d)};
+        tensors[p + "attention.wv.weight"] = {fq(2 * d * d), d * d, base + 3, 0.f, sdd, qmat(lo[i].qkv, 2 * d * d)};
+        tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd, L.wo8};
+        tensors[p + "ffn_norm.weight"] = {L.ffn_norm, d, base + 5, 1.f, 0.1f, Q8Mat()};
+        tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd, L.w18};
+        tensors[p + "feed_forward.w2.weight"] = {L.w2, d * ff, base + 7, 0.f, sf, L.w28};
+        tensors[p + "feed_forward.w3.weight"] = {L.w3, ff * d, base + 8, 0.f, sdd, L.w38};
     }
 }
 
 Model::~Model() {
     cudaSetDevice(device);
     if (slab) cudaFree(slab);
+    if (qslab) cudaFree(qslab);
+    if (dslab) cudaFree(dslab);
 }
 
 void Model::set_tensor(const std::string &name, int dtype, const void *host, size_t nbytes) {
     // LoadModel's tensor loop, llama.go:889-959: unknown names abort (:906-910); only F32 and F16
-    // are accepted (:937-959), F16 is widened to FP32.
+    // are accepted (:937-959), F16 is widened to FP32.  With Q8_0 weights the MulMat matrices are
+    // block-quantised on the device as they arrive.
     LB_CHECK(known_name(hp, name), "Unknown tensor '" + name + "' in model file");
     auto it = tensors.find(name);
     if (it == tensors.end()) return;  // belongs to another pipeline stage
     LB_CHECK(dtype == 0 || dtype == 1, "Tensor data type is not supported yet!");
+    const Entry &e = it->second;
     const size_t esz = dtype == 0 ? 4 : 2;
-    LB_CHECK(nbytes == it->second.nelem * esz, "tensor '" + name + "' has the wrong size");
+    LB_CHECK(nbytes == e.nelem * esz, "tensor '" + name + "' has the wrong size");
     LB_CUDA(cudaSetDevice(device));
+    const bool quant = e.q8.q != nullptr;
+    float *dst = e.ptr;
+    void *tmp16 = nullptr, *tmp32 = nullptr;
+    if (quant) { LB_CUDA(cudaMalloc(&tmp32, e.nelem * sizeof(float))); dst = static_cast<float *>(tmp32); }
     if (dtype == 0) {
-        LB_CUDA(cudaMemcpy(it->second.ptr, host, nbytes, cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMemcpy(dst, host, nbytes, cudaMemcpyHostToDevice));
     } else {
-        void *tmp = nullptr;
-        LB_CUDA(cudaMalloc(&tmp, nbytes));
-        LB_CUDA(cudaMemcpy(tmp, host, nbytes, cudaMemcpyHostToDevice));
-        k::f16_to_f32(static_cast<const uint16_t *>(tmp), it->second.ptr, it->second.nelem, 0);
-        LB_CUDA(cudaDeviceSynchronize());
-        cudaFree(tmp);
+        LB_CUDA(cudaMalloc(&tmp16, nbytes));
+        LB_CUDA(cudaMemcpy(tmp16, host, nbytes, cudaMemcpyHostToDevice));
+        k::f16_to_f32(static_cast<const uint16_t *>(tmp16), dst, e.nelem, 0);
     }
+    if (quant) k::quantize_q8(dst, e.q8.q, e.q8.d, e.nelem, 0);
+    LB_CUDA(cudaDeviceSynchronize());
+    if (tmp16) cudaFree(tmp16);
+    if (tmp32) cudaFree(tmp32);
 }
 
 void Model::get_tensor(const std::string &name, float *host, size_t nelem) {
     auto it = tensors.find(name);
     LB_CHECK(it != tensors.end(), "tensor '" + name + "' is not held by this stage");
-    LB_CHECK(nelem == it->second.nelem, "tensor '" + name + "' has the wrong size");
+    const Entry &e = it->second;
+    LB_CHECK(nelem == e.nelem, "tensor '" + name + "' has the wrong size");
     LB_CUDA(cudaSetDevice(device));
-    LB_CUDA(cudaMemcpy(host, it->second.ptr, nelem * sizeof(float), cudaMemcpyDeviceToHost));
+    if (e.q8.q) {
+        void *tmp = nullptr;
+        LB_CUDA(cudaMalloc(&tmp, nelem * sizeof(float)));
+        k::dequantize_q8(e.q8.q, e.q8.d, static_cast<float *>(tmp), nelem, 0);
+        LB_CUDA(cudaMemcpy(host, tmp, nelem * sizeof(float), cudaMemcpyDeviceToHost));
+        cudaFree(tmp);
+    } else {
+        LB_CUDA(cudaMemcpy(host, e.ptr, nelem * sizeof(float), cudaMemcpyDeviceToHost));
+    }
 }
 
 void Model::init_random(uint64_t seed) {
     LB_CUDA(cudaSetDevice(device));
+    void *tmp = nullptr;
+    size_t tmp_elems = 0;
+    for (auto &kv : tensors)
+        if (kv.second.q8.q && kv.second.nelem > tmp_elems) tmp_elems = kv.second.nelem;
+    if (tmp_elems) LB_CUDA(cudaMalloc(&tmp, tmp_elems * sizeof(float)));
     for (auto &kv : tensors) {
         const Entry &e = kv.second;
         // float32(sigma / IH_STD): the division is done in double on the host exactly like numpy does
         float sscale = (float)((double)e.sigma / IH_STD);
-        k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
+        if (e.q8.q) {
+            k::init_random(static_cast<float *>(tmp), e.nelem, seed, e.tid, e.mean, sscale, 0);
+            k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, e.nelem, 0);
+        } else {
+            k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
+        }
     }
     LB_CUDA(cudaDeviceSynchronize());
+    if (tmp) cudaFree(tmp);
 }
 
 uint64_t Model::weight_bytes_per_token() const {
     // every layer matrix + both norms, lm_head, final norm, one embedding row
     const uint64_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
-    uint64_t b = (uint64_t)(layer_end - layer_begin) * (4 * d * d + 3 * d * ff + 2 * d);
-    if (has_head()) b += V * d + d;
-    if (has_embedding()) b += d;
-    return b * 4;
+    // matrices cost 4 B/weight (F32) or 36 B per 32 weights (Q8_0); vectors are always F32
+    const uint64_t nl = layer_end - layer_begin;
+    uint64_t mat = nl * (4 * d * d + 3 * d * ff) + (has_head() ? V * d : 0);
+    uint64_t vec = nl * 2 * d + (has_head() ? d : 0) + (has_embedding() ? d : 0);
+    return (q8() ? mat / 32 * 36 : mat * 4) + vec * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,10 +241,16 @@ Context::~Context() {
     if (stream) cudaStreamDestroy(stream);
 }
 
-static void matmul(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,
-                   uint32_t ldy, const float *res, cudaStream_t st) {
-    if (N <= 8) k::gemv_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
-    else k::gemm_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
+// MulMat of a weight matrix: F32 or Q8_0 planes, GEMV (N <= 8) or GEMM
+static void matmul(const float *W, const Q8Mat &W8, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+                   float *Y, uint32_t ldy, const float *res, cudaStream_t st) {
+    if (W8.q) {
+        if (N <= 8) k::gemv_q8(W8.q, W8.d, M, K, X, ldx, N, Y, ldy, res, st);
+        else k::gemm_q8(W8.q, W8.d, M, K, X, ldx, N, Y, ldy, res, st);
+    } else {
+        if (N <= 8) k::gemv_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
+        else k::gemm_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
+    }
 }
 
 // The fused forward pass.  Per layer (llama.go:246-370):
@@ -220,20 +278,21 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         const Layer &L = model->layers[li];
         float *Kc = kv_k + li * (size_t)ctx_size * d, *Vc = kv_v + li * (size_t)ctx_size * d;
         k::rms_norm(x, L.attention_norm, cur, d, n, st);
-        matmul(L.wqkv, 3 * d, d, cur, d, n, qkv, 3 * d, nullptr, st);
+        matmul(L.wqkv, L.wqkv8, 3 * d, d, cur, d, n, qkv, 3 * d, nullptr, st);
         k::rope_qk_store(qkv, qkv + d, qkv + 2 * d, 3 * d, Kc, Vc, n, past_dev, d, H, st);
         if (n == 1) k::attention_decode(qkv, Kc, Vc, attn, past_dev, ctx_size, d, H, attn_scratch, st);
         else k::attention(qkv, 3 * d, Kc, Vc, attn, n, past_dev, ctx_size, d, H, st);
-        matmul(L.wo, d, d, attn, d, n, y, d, x, st);
+        matmul(L.wo, L.wo8, d, d, attn, d, n, y, d, x, st);
         k::rms_norm(y, L.ffn_norm, cur, d, n, st);
         if (n <= 8) {
-            k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, n, act, ff, st);
+            if (model->q8()) k::gemv_q8_swiglu(L.w18.q, L.w18.d, L.w38.q, L.w38.d, ff, d, cur, d, n, act, ff, st);
+            else k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, n, act, ff, st);
         } else {
-            k::gemm_f32(L.w3, ff, d, cur, d, n, up, ff, nullptr, st);
-            k::gemm_f32(L.w1, ff, d, cur, d, n, act, ff, nullptr, st);
+            matmul(L.w3, L.w38, ff, d, cur, d, n, up, ff, nullptr, st);
+            matmul(L.w1, L.w18, ff, d, cur, d, n, act, ff, nullptr, st);
             k::swiglu(act, up, act, (size_t)n * ff, st);
         }
-        matmul(L.w2, d, ff, act, ff, n, x, d, y, st);
+        matmul(L.w2, L.w28, d, ff, act, ff, n, x, d, y, st);
     }
     if (hidden_out && hidden_out != x)
         LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -243,11 +302,11 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
                 LB_CUDA(cudaMalloc(&all_logits, (size_t)max_batch * V * sizeof(float)));
             }
             k::rms_norm(x, model->norm, cur, d, n, st);
-            matmul(model->output, V, d, cur, d, n, all_logits, V, nullptr, st);
+            matmul(model->output, model->output8, V, d, cur, d, n, all_logits, V, nullptr, st);
         } else {
             // only row n-1 is ever read (llama.go:394-401); the reference computes all n (:384)
             k::rms_norm(x + (size_t)(n - 1) * d, model->norm, cur, d, 1, st);
-            k::gemv_f32(model->output, V, d, cur, d, 1, logits, V, nullptr, st);
+            matmul(model->output, model->output8, V, d, cur, d, 1, logits, V, nullptr, st);
         }
     }
 }
@@ -401,24 +460,27 @@ float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *
         const Layer &L = model->layers[i % nl];
         float *Kc = kv_k + (i % nl) * (size_t)ctx_size * d, *Vc = kv_v + (i % nl) * (size_t)ctx_size * d;
         switch (which) {
-            case 0: k::gemv_f32(L.wqkv, 3 * d, d, cur, d, 1, qkv, 3 * d, nullptr, stream); break;
-            case 1: k::gemv_f32(L.wo, d, d, attn, d, 1, y, d, x, stream); break;
-            case 2: k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, 1, act, ff, stream); break;
-            case 3: k::gemv_f32(L.w2, d, ff, act, ff, 1, up, d, y, stream); break;
+            case 0: matmul(L.wqkv, L.wqkv8, 3 * d, d, cur, d, 1, qkv, 3 * d, nullptr, stream); break;
+            case 1: matmul(L.wo, L.wo8, d, d, attn, d, 1, y, d, x, stream); break;
+            case 2: if (model->q8()) k::gemv_q8_swiglu(L.w18.q, L.w18.d, L.w38.q, L.w38.d, ff, d, cur, d, 1, act, ff, stream);
+                    else k::gemv_f32_swiglu(L.w1, L.w3, ff, d, cur, d, 1, act, ff, stream);
+                    break;
+            case 3: matmul(L.w2, L.w28, d, ff, act, ff, 1, up, d, y, stream); break;
             case 4: LB_CHECK(model->has_head(), "no lm_head on this stage");
-                    k::gemv_f32(model->output, V, d, cur, d, 1, logits, V, nullptr, stream); break;
+                    matmul(model->output, model->output8, V, d, cur, d, 1, logits, V, nullptr, stream); break;
             case 5: k::attention_decode(qkv, Kc, Vc, attn, state_dev, ctx_size, d, H, attn_scratch, stream); break;
             case 6: k::rms_norm(x, L.attention_norm, cur, d, 1, stream); break;
             default: LB_CHECK(false, "bench_kernel : unknown kernel id");
         }
     };
     const uint64_t T = (uint64_t)past + 1;
+    auto wb = [&](uint64_t nw) { return model->q8() ? nw / 32 * 36 : nw * 4; };  // weight bytes
     switch (which) {  // algorithmic bytes: weights + activations in + out
-        case 0: *bytes_per_launch = 4ull * (3ull * d * d + d + 3ull * d); break;
-        case 1: *bytes_per_launch = 4ull * ((uint64_t)d * d + 3ull * d); break;
-        case 2: *bytes_per_launch = 4ull * (2ull * ff * d + d + ff); break;
-        case 3: *bytes_per_launch = 4ull * ((uint64_t)d * ff + ff + 2ull * d); break;
-        case 4: *bytes_per_launch = 4ull * ((uint64_t)V * d + d + V); break;
+        case 0: *bytes_per_launch = wb(3ull * d * d) + 4ull * (d + 3ull * d); break;
+        case 1: *bytes_per_launch = wb((uint64_t)d * d) + 4ull * 3ull * d; break;
+        case 2: *bytes_per_launch = wb(2ull * ff * d) + 4ull * (d + ff); break;
+        case 3: *bytes_per_launch = wb((uint64_t)d * ff) + 4ull * (ff + 2ull * d); break;
+        case 4: *bytes_per_launch = wb((uint64_t)V * d) + 4ull * (d + V); break;
         case 5: *bytes_per_launch = 4ull * (2ull * T * d + 2ull * d); break;
         default: *bytes_per_launch = 4ull * 3ull * d; break;
     }
@@ -471,6 +533,7 @@ void Context::eval_graph(const uint32_t *tokens, uint32_t N, uint32_t pastCount,
     using namespace ml;
     const HParams &hp = model->hp;
     LB_CHECK(model->has_embedding() && model->has_head(), "eval_graph : needs a single-stage model");
+    LB_CHECK(!model->q8(), "eval_graph : the pkg/ml op API is FP32 only (like the reference)");
     LB_CHECK(N >= 1 && (uint64_t)pastCount + N <= ctx_size, "Eval : pastCount + N exceeds the context size");
     LB_CUDA(cudaSetDevice(model->device));
     const uint32_t embdSize = hp.dim, layersCount = hp.layers, ctxSize = ctx_size, headsCount = hp.heads;

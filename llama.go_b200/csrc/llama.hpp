@@ -19,12 +19,18 @@ struct HParams {  // llama.go:149-158
     uint32_t head_dim() const { return dim / heads; }
 };
 
+struct Q8Mat {  // Q8_0 planes of one matrix (kernels_q8.cu): q[M][K] int8, d[M][K/32] float
+    int8_t *q = nullptr;
+    float *d = nullptr;
+};
+
 struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] matrix
     float *attention_norm = nullptr;
     float *wqkv = nullptr;  // rows [0,dim) = wq, [dim,2dim) = wk, [2dim,3dim) = wv
     float *wo = nullptr;
     float *ffn_norm = nullptr;
     float *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+    Q8Mat wqkv8, wo8, w18, w28, w38;  // used instead of the float matrices when weight_type == Q8_0
 };
 
 // llama.Model (llama.go:181-193) for one pipeline stage: layers [layer_begin, layer_end).
@@ -39,9 +45,13 @@ struct Model {
     float *slab = nullptr;  // one allocation for every weight of the stage
     size_t slab_floats = 0;
     float *tok_embeddings = nullptr, *norm = nullptr, *output = nullptr;
+    Q8Mat output8;
+    int8_t *qslab = nullptr;  // Q8_0: int8 plane of every MulMat matrix of the stage
+    float *dslab = nullptr;   //       and the per-block scales
     std::vector<Layer> layers;  // index = global layer - layer_begin
+    bool q8() const { return weight_type == 16; }
 
-    struct Entry { float *ptr; size_t nelem; uint64_t tid; float mean, sigma; };
+    struct Entry { float *ptr; size_t nelem; uint64_t tid; float mean, sigma; Q8Mat q8; };
     std::map<std::string, Entry> tensors;  // ggjt names (llama.go:826-861) owned by this stage
 
     Model(const HParams &hp, int device, uint32_t lb, uint32_t le, int weight_type);

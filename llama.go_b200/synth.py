@@ -156,6 +156,33 @@ def synth_model(seed: int, hp: HParams):
         yield name, synth_values(seed, tid, 0, cnt, mean, sigma).reshape(shape)
 
 
+# --------------------------------------------------------------------------- Q8_0 reference (numpy)
+def quantize_q8(w: np.ndarray):
+    """Q8_0 as defined in DESIGN.md §6 / csrc/kernels_q8.cu: blocks of 32 along the last axis,
+    d = max|w| / 127 (FP32), q = rint(w / d) (FP32 divide, round-half-even) clamped to [-127, 127]."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    assert w.shape[-1] % 32 == 0
+    blocks = w.reshape(-1, 32)
+    d = (np.abs(blocks).max(axis=1) / np.float32(127.0)).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.where(d[:, None] > 0, np.rint(blocks / d[:, None]), 0.0)
+    q = np.clip(q, -127, 127).astype(np.int8)
+    return q.reshape(w.shape), d.reshape(w.shape[:-1] + (w.shape[-1] // 32,))
+
+
+def dequantize_q8(q: np.ndarray, d: np.ndarray) -> np.ndarray:
+    return (q.astype(np.float32).reshape(-1, 32) * d.reshape(-1, 1).astype(np.float32)).astype(np.float32).reshape(q.shape)
+
+
+Q8_MATRICES = ("attention.wq.weight", "attention.wk.weight", "attention.wv.weight", "attention.wo.weight",
+               "feed_forward.w1.weight", "feed_forward.w2.weight", "feed_forward.w3.weight", "output.weight")
+
+
+def is_q8_matrix(name: str) -> bool:
+    """The MulMat weights that a Q8_0 model block-quantises (norm vectors and the embedding table stay FP32)."""
+    return name.endswith(Q8_MATRICES)
+
+
 # --------------------------------------------------------------------------- vocab
 def byte_vocab(vocab_size: int):
     """Synthetic vocab under which the reference tokenizer (pkg/ml/ml.go:2761-2848) maps every
