@@ -48,6 +48,14 @@ void gemv_f32_swiglu(const float *W1, const float *W3, uint32_t M, uint32_t K, c
 void gemm_f32(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
               float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
 void swiglu(const float *gate, const float *up, float *dst, size_t n, cudaStream_t st);
+// prefill GEMM on tcgen05 tensor cores (kernels_tc.cu): TMA-fed kind::tf32 tiles, TMEM accumulators,
+// FP32 operands split hi/lo in the shared-memory stage (3xTF32) so the result is FP32-class.
+bool gemm_tf32x3_supported(uint32_t M, uint32_t K, uint32_t ldx, const float *W, const float *X);
+void gemm_tf32x3(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+                 float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
+// dispatcher for N > 8: tensor-core path when the shape allows (and LB_NO_TC is unset), else gemm_f32
+void gemm_auto(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+               float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
 // q (rows ldq apart, [N][dim]) rotated in place at positions past+n; k rotated and stored to
 // Kc[(past+n)][dim]; v stored to Vc[(past+n)][dim]   (llama.go:274-297 — K is cached rotated)
 // `past_dev` is a DEVICE pointer to the position of the first new token, so that a captured CUDA

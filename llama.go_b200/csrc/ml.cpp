@@ -241,7 +241,7 @@ static void ComputeForward(Context *ctx, Tensor *t) {
             if (plain2d && s1->ne[1] <= 8)
                 k::gemv_f32(s0->data, s0->ne[1], s0->ne[0], s1->data, s1->ne[0], s1->ne[1], t->data, t->ne[0], nullptr, st);
             else if (plain2d)
-                k::gemm_f32(s0->data, s0->ne[1], s0->ne[0], s1->data, s1->ne[0], s1->ne[1], t->data, t->ne[0], nullptr, st);
+                k::gemm_auto(s0->data, s0->ne[1], s0->ne[0], s1->data, s1->ne[0], s1->ne[1], t->data, t->ne[0], nullptr, st);
             else
                 k::mul_mat_generic(s0->view(), s1->view(), t->view(), st);
             break;
