@@ -10,12 +10,20 @@
 // identical swizzled layout, and three MMAs accumulate  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  into the
 // same TMEM tile: products accurate to ~2^-20, i.e. FP32-class results.
 //
-// Warp roles (192 threads, 1 CTA per SM, one 128x128 output tile per CTA):
+// The tensor core adds into its FP32 accumulator with truncation (measured: relative error grows
+// linearly with the number of dependent accumulations, 3e-5 at K = 4096 with one accumulator), so the
+// accumulation is two-level, like FP8 "promotion": TMEM holds the sum of only TC_CHUNK_KB k-blocks
+// (K = 256), then an accumulate warp-group adds that partial tile into FP32 registers (round to
+// nearest) while the MMA warp fills the other TMEM buffer.
+//
+// Warp roles (320 threads, 1 CTA per SM, one 128x128 output tile per CTA):
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  : transform (hi/lo split) during the main loop, then epilogue (TMEM -> regs -> HBM)
+//   warps 2..5  : transform (hi/lo split of every stage)
+//   warps 6..9  : accumulate (TMEM chunk -> registers, FP32 RN) and epilogue (registers -> HBM)
 // Pipelines: full_raw[s] (TMA -> transform, MMA), full_lo[s] (transform -> MMA),
-//            empty[s] (tcgen05.commit -> TMA), tmem_full (last commit -> epilogue).
+//            empty[s] (tcgen05.commit -> TMA), tmem_full[b] (chunk commit -> accumulate),
+//            tmem_empty[b] (accumulate -> MMA).
 // Every wait has a clock-based timeout that traps instead of hanging the GPU.
 #include <cuda.h>
 #include <stdlib.h>
@@ -31,7 +39,8 @@ constexpr int TC_BN = 128;      // tokens per tile       (UMMA N)
 constexpr int TC_BK = 32;       // floats per stage along K = one 128-byte swizzle row
 constexpr int TC_UK = 8;        // K per tcgen05.mma for kind::tf32 (32 bytes)
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int TC_CHUNK_KB = 8;  // k-blocks (of 32) summed inside TMEM before promotion to registers
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // raw + lo for A and B
@@ -132,9 +141,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     auto full_raw = [&](int s) { return bars + 8u * s; };
     auto full_lo = [&](int s) { return bars + 8u * (TC_STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
-    const uint32_t tmem_full = bars + 8u * (3 * TC_STAGES);
-    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 1);
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 8u * (3 * TC_STAGES + 1));
+    auto tmem_full = [&](int b) { return bars + 8u * (3 * TC_STAGES + b); };
+    auto tmem_empty = [&](int b) { return bars + 8u * (3 * TC_STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 8u * (3 * TC_STAGES + 4));
     auto a_raw = [&](int s) { return base + s * TC_STAGE_BYTES; };
     auto a_lo = [&](int s) { return base + s * TC_STAGE_BYTES + TC_A_BYTES; };
     auto b_raw = [&](int s) { return base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES; };
@@ -150,10 +160,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             mbar_init(full_lo(s), 128);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tmem_full(b), 1);
+            mbar_init(tmem_empty(b), 128);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TC_BN);  // 128 FP32 accumulator columns
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * TC_BN);  // two 128-column FP32 accumulator buffers
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -178,6 +191,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             for (uint32_t kb = 0; kb < num_kb; kb++) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
+                const uint32_t chunk = kb / TC_CHUNK_KB, buf = chunk & 1;
+                const uint32_t tmem_d = tmem_base + buf * TC_BN;
+                const bool first_of_chunk = (kb % TC_CHUNK_KB) == 0;
+                if (first_of_chunk) {
+                    mbar_wait(tmem_empty(buf), ((chunk >> 1) & 1) ^ 1);  // accumulate warps drained this buffer
+                    tc_fence_after();
+                }
                 mbar_wait(full_raw(s), ph);
                 mbar_wait(full_lo(s), ph);
                 tc_fence_after();
@@ -186,15 +206,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                     const uint32_t koff = kk * TC_UK * 4;  // 32 bytes per K step inside the swizzled row
                     const uint64_t dA = make_smem_desc(a_raw(s) + koff), dAl = make_smem_desc(a_lo(s) + koff);
                     const uint64_t dB = make_smem_desc(b_raw(s) + koff), dBl = make_smem_desc(b_lo(s) + koff);
-                    tc_mma_tf32(tmem_base, dAl, dB, idesc, (kb | kk) ? 1u : 0u);  // a_lo * b_hi
-                    tc_mma_tf32(tmem_base, dA, dBl, idesc, 1u);                    // a_hi * b_lo
-                    tc_mma_tf32(tmem_base, dA, dB, idesc, 1u);                     // a_hi * b_hi
+                    tc_mma_tf32(tmem_d, dAl, dB, idesc, (first_of_chunk && kk == 0) ? 0u : 1u);  // a_lo * b_hi
+                    tc_mma_tf32(tmem_d, dA, dBl, idesc, 1u);                                     // a_hi * b_lo
+                    tc_mma_tf32(tmem_d, dA, dB, idesc, 1u);                                      // a_hi * b_hi
                 }
                 tc_commit(empty(s));  // frees the stage once these MMAs have read it
+                if ((kb % TC_CHUNK_KB) == TC_CHUNK_KB - 1 || kb == num_kb - 1) tc_commit(tmem_full(buf));
             }
-            tc_commit(tmem_full);     // accumulator complete
         }
-    } else {
+    } else if (warp < 6) {
         // ================= transform warps: a_lo = a - trunc_tf32(a), same swizzled offsets =================
         const int t = threadIdx.x - 64;  // 0..127
         for (uint32_t kb = 0; kb < num_kb; kb++) {
@@ -219,24 +239,36 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(full_lo(s));
         }
-        // ================= epilogue: TMEM -> registers -> HBM =================
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
+    } else {
+        // ================= accumulate (TMEM chunk -> FP32 registers, RN) + epilogue =================
         const uint32_t q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
         const uint32_t m = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; c++) {
-            float v[32];
-            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(c * 32), v);
-            if (m < M) {
+        float acc[TC_BN];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t n = n0 + c * 32 + j;
-                    if (n < N) {
-                        float o = v[j];
-                        if (res) o = __fadd_rn(o, res[(size_t)n * ldy + m]);
-                        Y[(size_t)n * ldy + m] = o;  // lanes = consecutive m: coalesced
-                    }
+        for (int j = 0; j < TC_BN; j++) acc[j] = 0.f;
+        const uint32_t num_chunks = (num_kb + TC_CHUNK_KB - 1) / TC_CHUNK_KB;
+        for (uint32_t chunk = 0; chunk < num_chunks; chunk++) {
+            const uint32_t buf = chunk & 1;
+            mbar_wait(tmem_full(buf), (chunk >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < TC_BN / 32; c++) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + buf * TC_BN + ((q * 32u) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], v[j]);
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty(buf));
+        }
+        if (m < M) {
+#pragma unroll
+            for (int j = 0; j < TC_BN; j++) {
+                const uint32_t n = n0 + j;
+                if (n < N) {
+                    float o = acc[j];
+                    if (res) o = __fadd_rn(o, res[(size_t)n * ldy + m]);
+                    Y[(size_t)n * ldy + m] = o;  // lanes = consecutive m: coalesced
                 }
             }
         }
@@ -245,7 +277,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TC_BN);
+        tmem_dealloc(tmem_base, 2 * TC_BN);
     }
 }
 
