@@ -74,7 +74,8 @@ LB_API int       lb_synth_fill_host(float *dst, uint64_t count, uint64_t seed, u
                                     uint64_t start, float mean, double sigma);
 /* Micro-benchmark of one hot-path kernel for the roofline report: launches kernel `which`
  * (0 qkv gemv, 1 wo gemv+residual, 2 w1/w3 swiglu gemv, 3 w2 gemv+residual, 4 lm_head gemv,
- * 5 attention at `past`, 6 rmsnorm) `iters` times back to back on the context's stream, cycling
+ * 5 attention at `past`, 6 rmsnorm, 7 prefill GEMM w1 x min(512, ctx) tokens — bytes_out then holds its
+ * FLOPs) `iters` times back to back on the context's stream, cycling
  * through the layers so the weights never sit in L2; ms_out = CUDA-event time of all launches,
  * bytes_out = algorithmic bytes of ONE launch. */
 LB_API int       lb_bench_kernel(lb_context *c, int which, uint32_t iters, uint32_t past, float *ms_out,

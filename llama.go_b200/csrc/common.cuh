@@ -37,7 +37,27 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 constexpr int kNumSMs = 148;
 
+// Programmatic dependent launch (PDL): decode kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that kernel k+1's CTAs are scheduled into the
+// tail of kernel k; each such kernel issues its weight prefetch first, then `griddepcontrol.wait`
+// (= cudaGridDependencySynchronize) before it touches anything the predecessor wrote.
+extern bool g_use_pdl;
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    count_launch();
+}
+
 #ifdef __CUDACC__
+// PDL device side: let the dependent grid start launching / wait for the predecessor grid's memory
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

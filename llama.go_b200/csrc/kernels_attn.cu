@@ -112,6 +112,8 @@ attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ K
     __shared__ float s_bcast;
     __shared__ unsigned int s_ticket;
     const uint32_t h = blockIdx.x, sp = blockIdx.y, S = gridDim.y;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t Tn = *past_dev + 1;
     const uint32_t chunk = min((Tn + S - 1) / S, chunk_cap);
     const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn);
@@ -247,12 +249,11 @@ void attention_decode(const float *q, const float *Kc, const float *Vc, float *o
     LB_CHECK(smem <= 40 * 1024, "attention_decode: context too long");
     dim3 grid(heads, S);
     if (hd == 128)
-        attention_decode_kernel<128><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+        launch_pdl(attention_decode_kernel<128>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
     else if (hd == 64)
-        attention_decode_kernel<64><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+        launch_pdl(attention_decode_kernel<64>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
     else
-        attention_decode_kernel<32><<<grid, DEC_THREADS, smem, st>>>(q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
-    LB_LAUNCH_CHECK();
+        launch_pdl(attention_decode_kernel<32>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
 }
 
 void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,

@@ -6,9 +6,11 @@
 
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace lb {
 std::atomic<uint64_t> g_launches{0};
+bool g_use_pdl = getenv("LB_NO_PDL") == nullptr;
 namespace k {
 
 static inline unsigned blocks_for(size_t n, unsigned per_block, unsigned cap = 148 * 16) {
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(256) rms_norm_reg_kernel(const float *__restri
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)blockIdx.x * nc);
     float4 *yr = reinterpret_cast<float4 *>(y + (size_t)blockIdx.x * nc);
     const uint32_t n4 = nc >> 2;
+    pdl_launch_dependents();
+    pdl_wait();
     float4 v[VPT];
 #pragma unroll
     for (int i = 0; i < VPT; i++) {
@@ -126,9 +130,9 @@ __global__ void __launch_bounds__(256) rms_norm_reg_kernel(const float *__restri
 void rms_norm(const float *x, const float *w, float *y, uint32_t nc, uint32_t nr, cudaStream_t st) {
     if (!nr) return;
     const bool aligned = (nc & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w & 15) == 0;
-    if (aligned && nc <= 4096) rms_norm_reg_kernel<4><<<nr, 256, 0, st>>>(x, w, y, nc);
-    else if (aligned && nc <= 8192) rms_norm_reg_kernel<8><<<nr, 256, 0, st>>>(x, w, y, nc);
-    else rms_norm_kernel<<<nr, 256, 0, st>>>(x, w, y, nc);
+    if (aligned && nc <= 4096) { launch_pdl(rms_norm_reg_kernel<4>, dim3(nr), dim3(256), 0, st, x, w, y, nc); return; }
+    if (aligned && nc <= 8192) { launch_pdl(rms_norm_reg_kernel<8>, dim3(nr), dim3(256), 0, st, x, w, y, nc); return; }
+    rms_norm_kernel<<<nr, 256, 0, st>>>(x, w, y, nc);
     LB_LAUNCH_CHECK();
 }
 
@@ -301,6 +305,8 @@ void rope(float *x, uint32_t ne0, uint32_t ne1, uint32_t ne2, uint32_t past, uin
 __global__ void rope_qk_store_kernel(float *q, const float *__restrict__ k, const float *__restrict__ v, uint32_t ld,
                                      float *__restrict__ Kc, float *__restrict__ Vc, uint32_t N,
                                      const uint32_t *__restrict__ past_dev, uint32_t dim, uint32_t hd) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t past = *past_dev;
     uint32_t half = dim / 2;
     size_t n = (size_t)half * N;
@@ -331,13 +337,14 @@ __global__ void rope_qk_store_kernel(float *q, const float *__restrict__ k, cons
 void rope_qk_store(float *q, const float *k, const float *v, uint32_t ld, float *Kc, float *Vc, uint32_t N,
                    const uint32_t *past_dev, uint32_t dim, uint32_t heads, cudaStream_t st) {
     size_t n = (size_t)(dim / 2) * N;
-    rope_qk_store_kernel<<<blocks_for(n, 128), 128, 0, st>>>(q, k, v, ld, Kc, Vc, N, past_dev, dim, dim / heads);
-    LB_LAUNCH_CHECK();
+    launch_pdl(rope_qk_store_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, st, q, k, v, ld, Kc, Vc, N, past_dev, dim, dim / heads);
 }
 
 __global__ void get_rows_indirect_kernel(const float *__restrict__ table, uint32_t nc, const uint32_t *__restrict__ tokens,
                                          const uint32_t *__restrict__ step_dev, float *__restrict__ dst) {
     uint32_t row = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     size_t r = tokens[*step_dev + row];
     const float *src = table + r * nc;
     float *d = dst + (size_t)row * nc;
@@ -347,16 +354,15 @@ __global__ void get_rows_indirect_kernel(const float *__restrict__ table, uint32
 void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, const uint32_t *step_dev, uint32_t nr,
                        float *dst, cudaStream_t st) {
     LB_CHECK((nc & 3) == 0, "get_rows_indirect: row length must be a multiple of 4");
-    get_rows_indirect_kernel<<<nr, 256, 0, st>>>(table, nc, tokens, step_dev, dst);
-    LB_LAUNCH_CHECK();
+    launch_pdl(get_rows_indirect_kernel, dim3(nr), dim3(256), 0, st, table, nc, tokens, step_dev, dst);
 }
 __global__ void advance_state_kernel(uint32_t *state, uint32_t dp, uint32_t ds) {
+    pdl_wait();
     state[0] += dp;
     state[1] += ds;
 }
 void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st) {
-    advance_state_kernel<<<1, 1, 0, st>>>(state, dp, ds);
-    LB_LAUNCH_CHECK();
+    launch_pdl(advance_state_kernel, dim3(1), dim3(1), 0, st, state, dp, ds);
 }
 
 // ---- synthetic weights: same integer recipe as llama.go_b200/synth.py (bit-identical)

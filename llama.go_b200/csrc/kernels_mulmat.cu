@@ -36,8 +36,10 @@ gemv_kernel(const float *__restrict__ W, uint32_t M, uint32_t K, const float *__
 #pragma unroll
     for (int r = 0; r < RPW; r++) wr[r] = W + (size_t)min(row0 + r, M - 1) * K;
 
-    for (uint32_t kk = lane * 4; kk < K; kk += 128 * UNROLL) {
-        float4 w[UNROLL][RPW];
+    // first batch of weight loads is issued BEFORE waiting on the predecessor grid (weights are
+    // read-only): under PDL this CTA streams while the previous kernel drains.
+    float4 w[UNROLL][RPW];
+    auto load_batch = [&](uint32_t kk) {
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             uint32_t kq = kk + u * 128;
@@ -45,23 +47,34 @@ gemv_kernel(const float *__restrict__ W, uint32_t M, uint32_t K, const float *__
             for (int r = 0; r < RPW; r++)
                 w[u][r] = (kq < K) ? ld_stream_f4(wr[r] + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    pdl_launch_dependents();
+    load_batch(lane * 4);
+    pdl_wait();
+    for (uint32_t kk = lane * 4; kk < K;) {
+        float4 xv[UNROLL][NC];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             uint32_t kq = kk + u * 128;
-            if (kq < K) {
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx + kq));
+            for (int c = 0; c < NC; c++)
+                xv[u][c] = (kq < K) ? __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx + kq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-                    for (int r = 0; r < RPW; r++) {
-                        acc[r][c] = fmaf(w[u][r].x, xv.x, acc[r][c]);
-                        acc[r][c] = fmaf(w[u][r].y, xv.y, acc[r][c]);
-                        acc[r][c] = fmaf(w[u][r].z, xv.z, acc[r][c]);
-                        acc[r][c] = fmaf(w[u][r].w, xv.w, acc[r][c]);
-                    }
+        for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+#pragma unroll
+                for (int r = 0; r < RPW; r++) {
+                    acc[r][c] = fmaf(w[u][r].x, xv[u][c].x, acc[r][c]);
+                    acc[r][c] = fmaf(w[u][r].y, xv[u][c].y, acc[r][c]);
+                    acc[r][c] = fmaf(w[u][r].z, xv[u][c].z, acc[r][c]);
+                    acc[r][c] = fmaf(w[u][r].w, xv[u][c].w, acc[r][c]);
                 }
             }
         }
+        kk += 128 * UNROLL;
+        if (kk < K) load_batch(kk);
     }
 #pragma unroll
     for (int r = 0; r < RPW; r++)
@@ -94,14 +107,19 @@ gemv_swiglu_kernel(const float *__restrict__ W1, const float *__restrict__ W3, u
 #pragma unroll
     for (int c = 0; c < NC; c++) a1[c] = a3[c] = 0.f;
     const float *w1 = W1 + (size_t)row * K, *w3 = W3 + (size_t)row * K;
-    for (uint32_t kk = lane * 4; kk < K; kk += 128 * GEMV_UNROLL) {
-        float4 p[GEMV_UNROLL], q[GEMV_UNROLL];
+    float4 p[GEMV_UNROLL], q[GEMV_UNROLL];
+    auto load_batch = [&](uint32_t kk) {
 #pragma unroll
         for (int u = 0; u < GEMV_UNROLL; u++) {
             uint32_t kq = kk + u * 128;
             p[u] = (kq < K) ? ld_stream_f4(w1 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
             q[u] = (kq < K) ? ld_stream_f4(w3 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    pdl_launch_dependents();
+    load_batch(lane * 4);   // weights first, then wait for the predecessor grid (PDL)
+    pdl_wait();
+    for (uint32_t kk = lane * 4; kk < K;) {
 #pragma unroll
         for (int u = 0; u < GEMV_UNROLL; u++) {
             uint32_t kq = kk + u * 128;
@@ -116,6 +134,8 @@ gemv_swiglu_kernel(const float *__restrict__ W1, const float *__restrict__ W3, u
                 }
             }
         }
+        kk += 128 * GEMV_UNROLL;
+        if (kk < K) load_batch(kk);
     }
 #pragma unroll
     for (int c = 0; c < NC; c++) { a1[c] = warp_sum(a1[c]); a3[c] = warp_sum(a3[c]); }
@@ -134,12 +154,11 @@ static void gemv_launch(const float *W, uint32_t M, uint32_t K, const float *x, 
     constexpr bool two = (NC <= 2);
     if (two && M >= 8192) {
         unsigned grid = (M + 15) / 16;
-        gemv_kernel<NC, 2, 8, 4><<<grid, 256, 0, st>>>(W, M, K, x, ldx, y, ldy, res);
+        launch_pdl(gemv_kernel<NC, 2, 8, 4>, dim3(grid), dim3(256), 0, st, W, M, K, x, ldx, y, ldy, res);
     } else {
         unsigned grid = (M + 3) / 4;
-        gemv_kernel<NC, 1, 4, (NC <= 4 ? 8 : 4)><<<grid, 128, 0, st>>>(W, M, K, x, ldx, y, ldy, res);
+        launch_pdl(gemv_kernel<NC, 1, 4, (NC <= 4 ? 8 : 4)>, dim3(grid), dim3(128), 0, st, W, M, K, x, ldx, y, ldy, res);
     }
-    LB_LAUNCH_CHECK();
 }
 
 void gemv_f32(const float *W, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N, float *y,
@@ -162,8 +181,7 @@ template <int NC>
 static void swiglu_launch(const float *W1, const float *W3, uint32_t M, uint32_t K, const float *x, uint32_t ldx,
                           float *act, uint32_t ldy, cudaStream_t st) {
     unsigned grid = (M + GEMV_WARPS - 1) / GEMV_WARPS;
-    gemv_swiglu_kernel<NC><<<grid, GEMV_WARPS * 32, 0, st>>>(W1, W3, M, K, x, ldx, act, ldy);
-    LB_LAUNCH_CHECK();
+    launch_pdl(gemv_swiglu_kernel<NC>, dim3(grid), dim3(GEMV_WARPS * 32), 0, st, W1, W3, M, K, x, ldx, act, ldy);
 }
 void gemv_f32_swiglu(const float *W1, const float *W3, uint32_t M, uint32_t K, const float *x, uint32_t ldx,
                      uint32_t N, float *act, uint32_t ldy, cudaStream_t st) {

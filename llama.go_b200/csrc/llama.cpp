@@ -456,6 +456,7 @@ float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *
     LB_CUDA(cudaSetDevice(model->device));
     state_host[0] = past; state_host[1] = 0;
     LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    const uint32_t pf_n = max_batch < 512 ? max_batch : 512;  // tokens of the prefill GEMM probe
     auto launch = [&](uint32_t i) {
         const Layer &L = model->layers[i % nl];
         float *Kc = kv_k + (i % nl) * (size_t)ctx_size * d, *Vc = kv_v + (i % nl) * (size_t)ctx_size * d;
@@ -470,6 +471,7 @@ float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *
                     matmul(model->output, model->output8, V, d, cur, d, 1, logits, V, nullptr, stream); break;
             case 5: k::attention_decode(qkv, Kc, Vc, attn, state_dev, ctx_size, d, H, attn_scratch, stream); break;
             case 6: k::rms_norm(x, L.attention_norm, cur, d, 1, stream); break;
+            case 7: matmul(L.w1, L.w18, ff, d, cur, d, pf_n, act, ff, nullptr, stream); break;  // prefill GEMM
             default: LB_CHECK(false, "bench_kernel : unknown kernel id");
         }
     };
@@ -482,6 +484,7 @@ float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *
         case 3: *bytes_per_launch = wb((uint64_t)d * ff) + 4ull * (ff + 2ull * d); break;
         case 4: *bytes_per_launch = wb((uint64_t)V * d) + 4ull * (d + V); break;
         case 5: *bytes_per_launch = 4ull * (2ull * T * d + 2ull * d); break;
+        case 7: *bytes_per_launch = 2ull * ff * d * pf_n; break;  // FLOPs (not bytes) of the GEMM
         default: *bytes_per_launch = 4ull * 3ull * d; break;
     }
     for (uint32_t i = 0; i < 3; i++) launch(i);  // warm-up

@@ -52,8 +52,8 @@ def test_tensor_core_gemm_handles_special_values(ml):
     x = np.zeros((16, 64), np.float32)
     w[3, 5] = 1.0; x[2, 5] = 3.0
     w[7, :] = 1e-30; x[4, :] = 1e-30          # products underflow to zero cleanly
-    w[9, 0] = 16777217.0; x[1, 0] = 1.0        # not representable in TF32: needs the lo term
+    w[9, 0] = np.float32(1.0 + 2.0 ** -20); x[1, 0] = 1.0   # FP32 value that TF32 cannot hold: needs the lo term
     got = run_mul_mat(ml, w, x)
     assert got[2, 3] == 3.0
-    assert got[1, 9] == np.float32(16777217.0)
+    assert got[1, 9] == np.float32(1.0 + 2.0 ** -20)
     assert np.count_nonzero(got) == 2
