@@ -77,6 +77,26 @@ void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, 
 // state[0] (= past) += dp; state[1] (= step) += ds
 void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
 
+// ---- persistent single-token megakernel (kernels_mega.cu) ----
+struct MegaLayerHost {  // one per layer, array lives in device memory
+    const float *attention_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2;
+    float *Kc, *Vc;
+};
+struct MegaParamsHost {
+    const MegaLayerHost *layers_dev;
+    uint32_t n_layers;
+    const float *tok_embeddings;      // nullptr: residual comes in through x (pipeline stage > 0)
+    const uint32_t *tokens, *state;   // device: token ids, {past, step}
+    const float *final_norm, *output; // nullptr: no lm_head on this stage
+    float *x, *y, *qkv, *attn, *act, *logits;
+    float *part_o, *part_ml;
+    unsigned *tickets, *barrier;
+    uint32_t dim, ff, heads, vocab, ctx;
+};
+bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads);
+uint32_t decode_mega_splits(uint32_t heads);
+void decode_mega(const MegaParamsHost &p, cudaStream_t st);
+
 // ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
 void quantize_q8(const float *W, int8_t *q, float *d, size_t nelem, cudaStream_t st);
 void dequantize_q8(const int8_t *q, const float *d, float *out, size_t nelem, cudaStream_t st);

@@ -1,0 +1,470 @@
+// kernels_mega.cu — the whole single-token forward pass (llama.Eval with N = 1,
+// pkg/llama/llama.go:211-426) of a range of layers as ONE persistent cooperative kernel.
+//
+// Why: decode is HBM-bound (0.5 flop/byte) and a layer is only ~115 us of weight streaming; split
+// into 7-8 kernels per layer, each kernel's ramp-up and tail leave HBM idle (measured: 162 us per
+// layer with per-op kernels + PDL = 78 % of the measured-peak roofline).  Here 148 CTAs (one per
+// SM, 16 warps) stay resident for the whole token and walk a static schedule of phases separated by
+// grid barriers:
+//   per layer:  P1 rmsnorm + [wq;wk;wv] GEMV | P2 RoPE + KV store + split-T attention (+ merge)
+//               P3 wo GEMV + residual        | P4 rmsnorm + w1,w3 GEMV + SiLU*mul | P5 w2 GEMV + residual
+//   then:       final rmsnorm + lm_head GEMV
+// Work split of a GEMV phase: CTA c owns a contiguous block of ~M/148 output rows (balanced to one
+// row); inside the CTA every warp owns a fixed 1/16 slice of K, so its slice of the activation vector
+// lives in REGISTERS for the whole phase (no activation re-reads at all) and a weight row is read by
+// 16 warps x 512-byte coalesced requests.  Row partials are combined through shared memory in a fixed
+// order (deterministic).  Before arriving at a grid barrier each warp issues cp.async.bulk.prefetch.L2
+// for its slice of the CTA's first rows of the NEXT phase, so HBM keeps streaming while the barrier
+// settles and the first loads after the barrier hit L2.
+// Numerics are those of the per-op kernels (see kernels_elementwise.cu / kernels_attn.cu); only the
+// association order of the FP32 dot-product sums differs.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace lb {
+namespace k {
+
+constexpr int MG_WARPS = 16;
+constexpr int MG_THREADS = MG_WARPS * 32;
+constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
+constexpr uint32_t MG_PREFETCH_BYTES = 160 * 1024;  // per CTA, next phase's first rows
+
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+struct MegaShared {
+    float part[2][2][MG_ROWBLK][MG_WARPS];  // [buffer][matrix (w1|w3)][row][warp]
+    double red[MG_WARPS];
+    float fred[MG_WARPS];
+    float bcast;
+    unsigned ticket;
+    float pv[MG_THREADS];
+};
+
+// ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+    target += nctas;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a scheduling bug
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// this CTA's contiguous row range of an M-row matrix
+__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
+    r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
+    r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
+}
+
+// L2 prefetch of this CTA's first rows of a matrix used in a later phase (each lane one row slice)
+__device__ __forceinline__ void prefetch_matrix(const float *W, uint32_t M, uint32_t K) {
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const uint32_t KS = K / MG_WARPS;
+    uint32_t nrows = MG_PREFETCH_BYTES / (K * 4);
+    if (nrows < 1) nrows = 1;
+    if (nrows > 32) nrows = 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((uint32_t)lane < nrows && r0 + lane < r1)
+        prefetch_l2_bulk(W + (size_t)(r0 + lane) * K + (size_t)warp * KS, KS * 4);
+}
+
+// y = x * f32(1/sqrt(mean_f64(x^2)+1e-5)) * w, only this warp's K-slice, into registers
+// (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812, llama.go:255-259).  x may have been written by
+// other CTAs during this launch -> L2 loads (ld.global.cg).
+template <int V>
+__device__ __forceinline__ void rms_slice(const float *x, const float *w, uint32_t K, float4 (&xs)[V], MegaShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x * 4; i < K; i += MG_THREADS * 4) {
+        float4 v = ldcg4(x + i);
+        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
+        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < MG_WARPS; i++) t += sh.red[i];
+        sh.bcast = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+    }
+    __syncthreads();
+    const float sc = sh.bcast;
+    const uint32_t KS = K / MG_WARPS;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const uint32_t e = (j * 32 + lane) * 4;
+        if (e < KS) {
+            float4 v = ldcg4(x + (size_t)warp * KS + e);
+            float4 ww = __ldg(reinterpret_cast<const float4 *>(w + (size_t)warp * KS + e));
+            xs[j].x = __fmul_rn(ww.x, __fmul_rn(v.x, sc)); xs[j].y = __fmul_rn(ww.y, __fmul_rn(v.y, sc));
+            xs[j].z = __fmul_rn(ww.z, __fmul_rn(v.z, sc)); xs[j].w = __fmul_rn(ww.w, __fmul_rn(v.w, sc));
+        } else {
+            xs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&xs)[V]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const uint32_t e = (j * 32 + lane) * 4;
+        xs[j] = e < KS ? ldcg4(x + (size_t)warp * KS + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
+template <int V, bool SWIGLU>
+__device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
+                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh) {
+    constexpr int NM = SWIGLU ? 2 : 1;
+    constexpr int RB = (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8;  // rows per load batch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const float *w1 = W + (size_t)warp * KS + lane * 4;
+    const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
+    int buf = 0;
+    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK, buf ^= 1) {
+        const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
+        for (uint32_t r = 0; r < nrb; r += RB) {
+            float4 a[RB][NM][V];
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+                const bool rok = r + i < nrb;
+                const size_t off = (size_t)(rb + r + i) * K;
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
+                    a[i][0][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+#pragma unroll
+                for (int mtx = 0; mtx < NM; mtx++) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < V; j++) {
+                        acc = fmaf(a[i][mtx][j].x, xs[j].x, acc); acc = fmaf(a[i][mtx][j].y, xs[j].y, acc);
+                        acc = fmaf(a[i][mtx][j].z, xs[j].z, acc); acc = fmaf(a[i][mtx][j].w, xs[j].w, acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < nrb) {
+            float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < MG_WARPS; wv++) {
+                s1 += sh.part[buf][0][threadIdx.x][wv];
+                if (SWIGLU) s3 += sh.part[buf][NM - 1][threadIdx.x][wv];
+            }
+            const uint32_t row = rb + threadIdx.x;
+            float v;
+            if (SWIGLU) v = __fmul_rn(silu_ref(s1), s3);
+            else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
+            out[row] = v;
+        }
+        // the other partial buffer is used by the next block; this one is reused only after the next __syncthreads
+    }
+}
+
+struct MegaLayer {
+    const float *attention_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2;
+    float *Kc, *Vc;
+};
+struct MegaParams {
+    const MegaLayer *layers;
+    uint32_t n_layers;
+    const float *tok_embeddings;  // nullptr: the residual stream comes in through x
+    const uint32_t *tokens;
+    const uint32_t *state;        // {past, step}
+    const float *final_norm, *output;  // nullptr: no lm_head on this stage
+    float *x, *y, *qkv, *attn, *act, *logits;
+    float *part_o, *part_ml;
+    unsigned *tickets, *barrier;
+    uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
+};
+
+// ---- attention phase: items (head, split) round-robin over CTAs; 16 warps share the item's keys
+template <int HD>
+__device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaLayer &L, uint32_t past, MegaShared &sh, float *scores) {
+    constexpr int LANES = HD / 4;
+    constexpr int G = MG_THREADS / HD;  // P·V groups
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t dim = p.dim, S = p.splits, Tn = past + 1;
+    const float scale = (float)(1.0 / sqrt((double)HD));  // f32(1/sqrt(dim/heads)), llama.go:306
+    const uint32_t chunk = min((Tn + S - 1) / S, p.chunk_cap);
+    const uint32_t items = p.heads * S;
+    for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const uint32_t h = item / S, sp = item % S;
+        const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn), nk = t1 - t0;
+        float *Kh = L.Kc + (size_t)h * HD;
+        float *Vh = L.Vc + (size_t)h * HD;
+        // RoPE of q (every warp, its own copy) and, in the item that owns position `past`, of k; store k,v
+        // (ComputeForwardRopeFP32 ml.go:2253-2328; llama.go:274-297 — K is cached rotated)
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < LANES) {
+            const float4 qr = ldcg4(p.qkv + (size_t)h * HD + lane * 4);
+            double s0, c0, s1, c1;
+            sincos((double)past * pow(10000.0, ((double)(-(lane * 4))) / (double)HD), &s0, &c0);
+            sincos((double)past * pow(10000.0, ((double)(-(lane * 4 + 2))) / (double)HD), &s1, &c1);
+            qv.x = (float)(__dsub_rn(__dmul_rn((double)qr.x, c0), __dmul_rn((double)qr.y, s0)));
+            qv.y = (float)(__dadd_rn(__dmul_rn((double)qr.x, s0), __dmul_rn((double)qr.y, c0)));
+            qv.z = (float)(__dsub_rn(__dmul_rn((double)qr.z, c1), __dmul_rn((double)qr.w, s1)));
+            qv.w = (float)(__dadd_rn(__dmul_rn((double)qr.z, s1), __dmul_rn((double)qr.w, c1)));
+            if (warp == 0 && past >= t0 && past < t1) {
+                const float4 kr = ldcg4(p.qkv + dim + (size_t)h * HD + lane * 4);
+                float4 ko;
+                ko.x = (float)(__dsub_rn(__dmul_rn((double)kr.x, c0), __dmul_rn((double)kr.y, s0)));
+                ko.y = (float)(__dadd_rn(__dmul_rn((double)kr.x, s0), __dmul_rn((double)kr.y, c0)));
+                ko.z = (float)(__dsub_rn(__dmul_rn((double)kr.z, c1), __dmul_rn((double)kr.w, s1)));
+                ko.w = (float)(__dadd_rn(__dmul_rn((double)kr.z, s1), __dmul_rn((double)kr.w, c1)));
+                *reinterpret_cast<float4 *>(Kh + (size_t)past * dim + lane * 4) = ko;
+                *reinterpret_cast<float4 *>(Vh + (size_t)past * dim + lane * 4) = ldcg4(p.qkv + 2 * dim + (size_t)h * HD + lane * 4);
+            }
+        }
+        __syncthreads();  // the freshly stored K/V row is visible to the CTA (read back through L2)
+        // scores (MulMat K·Q, Scale): warp w takes keys w, w+16, ...
+        for (uint32_t i = warp; i < nk; i += MG_WARPS * 2) {
+            float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
+            const uint32_t i1 = i + MG_WARPS;
+            if (lane < LANES) {
+                k0 = ldcg4(Kh + (size_t)(t0 + i) * dim + lane * 4);
+                if (i1 < nk) k1 = ldcg4(Kh + (size_t)(t0 + i1) * dim + lane * 4);
+            }
+            float d0 = k0.x * qv.x; d0 = fmaf(k0.y, qv.y, d0); d0 = fmaf(k0.z, qv.z, d0); d0 = fmaf(k0.w, qv.w, d0);
+            float d1 = k1.x * qv.x; d1 = fmaf(k1.y, qv.y, d1); d1 = fmaf(k1.z, qv.z, d1); d1 = fmaf(k1.w, qv.w, d1);
+            d0 = warp_sum(d0); d1 = warp_sum(d1);
+            if (lane == 0) {
+                scores[i] = __fmul_rn(d0, scale);
+                if (i1 < nk) scores[i1] = __fmul_rn(d1, scale);
+            }
+        }
+        __syncthreads();
+        // local softmax statistics (SoftMax, ml.go:2472-2499, per split)
+        float m = -INFINITY;
+        for (uint32_t i = threadIdx.x; i < nk; i += MG_THREADS) m = fmaxf(m, scores[i]);
+        m = warp_max(m);
+        if (lane == 0) sh.fred[warp] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = sh.fred[0];
+            for (int i = 1; i < MG_WARPS; i++) t = fmaxf(t, sh.fred[i]);
+            sh.bcast = t;
+        }
+        __syncthreads();
+        m = sh.bcast;
+        float l = 0.f;
+        for (uint32_t i = threadIdx.x; i < nk; i += MG_THREADS) {
+            float e = (float)exp((double)__fsub_rn(scores[i], m));
+            scores[i] = e;
+            l += e;
+        }
+        l = warp_sum(l);
+        __syncthreads();
+        if (lane == 0) sh.fred[warp] = l;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < MG_WARPS; i++) t += sh.fred[i];
+            p.part_ml[((size_t)h * S + sp) * 2 + 0] = m;
+            p.part_ml[((size_t)h * S + sp) * 2 + 1] = t;
+        }
+        // partial P·V
+        const uint32_t g = threadIdx.x / HD, d = threadIdx.x % HD;
+        float acc = 0.f;
+        {
+            const float *vp = Vh + d;
+            uint32_t i = g;
+            for (; i + 3 * G < nk; i += 4 * G) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = __ldcg(vp + (size_t)(t0 + i + u * G) * dim);
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc = fmaf(v[u], scores[i + u * G], acc);
+            }
+            for (; i < nk; i += G) acc = fmaf(__ldcg(vp + (size_t)(t0 + i) * dim), scores[i], acc);
+        }
+        sh.pv[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < HD) {
+            float r = 0.f;
+            for (int i = 0; i < G; i++) r += sh.pv[i * HD + threadIdx.x];
+            p.part_o[((size_t)h * S + sp) * HD + threadIdx.x] = r;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) sh.ticket = atomicAdd(&p.tickets[h], 1u);
+        __syncthreads();
+        if (sh.ticket == S - 1) {  // last split of this head: merge
+            __threadfence();
+            if (threadIdx.x < HD) {
+                float M = -INFINITY;
+                for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]));
+                float Lsum = 0.f, o = 0.f;
+                for (uint32_t s2 = 0; s2 < S; s2++) {
+                    const float ms = __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]);
+                    const float ls = __ldcg(&p.part_ml[((size_t)h * S + s2) * 2 + 1]);
+                    if (ls > 0.f) {
+                        const float wgt = (float)exp((double)__fsub_rn(ms, M));
+                        Lsum = fmaf(ls, wgt, Lsum);
+                        o = fmaf(__ldcg(&p.part_o[((size_t)h * S + s2) * HD + threadIdx.x]), wgt, o);
+                    }
+                }
+                p.attn[(size_t)h * HD + threadIdx.x] = __fmul_rn(o, __fdiv_rn(1.0f, Lsum));
+            }
+            if (threadIdx.x == 0) p.tickets[h] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+template <int VD, int VF, int HD>
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+    extern __shared__ float scores[];  // [chunk_cap]
+    __shared__ MegaShared sh;
+    unsigned target = 0;
+    const uint32_t past = p.state[0];
+    const uint32_t dim = p.dim, ff = p.ff;
+    const float *xin = p.x;
+    if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
+
+    for (uint32_t li = 0; li < p.n_layers; li++) {
+        const MegaLayer L = p.layers[li];
+        {   // ---- P1: rmsnorm * attention_norm, then [wq;wk;wv] (llama.go:255-265)
+            float4 xs[VD];
+            rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
+            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh);
+            prefetch_matrix(L.wo, dim, dim);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        // ---- P2: RoPE, KV store, attention (llama.go:274-333)
+        attention_phase<HD>(p, L, past, sh, scores);
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // ---- P3: wo + residual (llama.go:336-340)
+            float4 xs[VD];
+            load_slice<VD>(p.attn, dim, xs);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh);
+            prefetch_matrix(L.w1, ff, dim);
+            prefetch_matrix(L.w3, ff, dim);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
+            float4 xs[VD];
+            rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
+            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh);
+            prefetch_matrix(L.w2, dim, ff);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // ---- P5: w2 + residual (llama.go:363-366)
+            float4 xf[VF];
+            load_slice<VF>(p.act, ff, xf);
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh);
+            if (li + 1 < p.n_layers) prefetch_matrix(p.layers[li + 1].wqkv, 3 * dim, dim);
+            else if (p.output) prefetch_matrix(p.output, p.vocab, dim);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        xin = p.x;
+    }
+    if (p.output) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
+        float4 xs[VD];
+        rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
+        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+struct MegaHost {
+    MegaParams p;
+};
+
+static bool pick_variant(uint32_t dim, uint32_t ff, uint32_t hd, int &vd, int &vf) {
+    if (dim % (MG_WARPS * 4) || ff % (MG_WARPS * 4)) return false;
+    if (hd != 128 && hd != 64 && hd != 32) return false;
+    vd = (int)((dim / MG_WARPS + 127) / 128);
+    vf = (int)((ff / MG_WARPS + 127) / 128);
+    return true;
+}
+
+template <int VD, int VF>
+static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (hd == 128) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 128>, p);
+    if (hd == 64) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 64>, p);
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 32>, p);
+}
+
+bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads) {
+    int vd, vf;
+    if (heads == 0 || dim % heads) return false;
+    if (!pick_variant(dim, ff, dim / heads, vd, vf)) return false;
+    // instantiated variants: (1,1) tiny test models, (2,6) 7B, (3,7) 13B, (4,9) 30B, (4,11) 65B
+    return (vd == 1 && vf == 1) || (vd == 2 && vf == 6) || (vd == 3 && vf == 7) || (vd == 4 && vf == 9) || (vd == 4 && vf == 11);
+}
+
+uint32_t decode_mega_splits(uint32_t heads) {
+    uint32_t s = (2 * kNumSMs) / heads;  // <= 2 attention items per CTA
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+
+void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
+    MegaParams p;
+    p.layers = reinterpret_cast<const MegaLayer *>(h.layers_dev);
+    p.n_layers = h.n_layers;
+    p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
+    p.final_norm = h.final_norm; p.output = h.output;
+    p.x = h.x; p.y = h.y; p.qkv = h.qkv; p.attn = h.attn; p.act = h.act; p.logits = h.logits;
+    p.part_o = h.part_o; p.part_ml = h.part_ml; p.tickets = h.tickets; p.barrier = h.barrier;
+    p.dim = h.dim; p.ff = h.ff; p.heads = h.heads; p.vocab = h.vocab; p.ctx = h.ctx;
+    p.splits = decode_mega_splits(h.heads);
+    p.chunk_cap = (h.ctx + p.splits - 1) / p.splits;
+    int vd, vf;
+    const uint32_t hd = h.dim / h.heads;
+    LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
+    const size_t smem = (size_t)p.chunk_cap * sizeof(float);
+    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned), st));
+    cudaError_t e;
+    if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
+    else if (vd == 2 && vf == 6) e = launch_hd<2, 6>(p, hd, smem, st);
+    else if (vd == 3 && vf == 7) e = launch_hd<3, 7>(p, hd, smem, st);
+    else if (vd == 4 && vf == 9) e = launch_hd<4, 9>(p, hd, smem, st);
+    else e = launch_hd<4, 11>(p, hd, smem, st);
+    LB_CUDA(e);
+    count_launch();
+}
+
+static_assert(sizeof(MegaLayer) == sizeof(MegaLayerHost), "MegaLayer / MegaLayerHost layout mismatch");
+
+}  // namespace k
+}  // namespace lb

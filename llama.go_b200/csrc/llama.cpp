@@ -222,6 +222,20 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     LB_CUDA(cudaEventCreate(&ev0));
     LB_CUDA(cudaEventCreate(&ev1));
     use_graph = getenv("LB_NO_GRAPH") == nullptr;  // profiling aid: plain launches instead of graph replay
+    // persistent megakernel for N == 1 (FP32 weights, supported shapes); LB_NO_MEGA=1 keeps the per-op kernels
+    use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
+    if (use_mega) {
+        std::vector<k::MegaLayerHost> ml(nl);
+        for (size_t i = 0; i < nl; i++) {
+            const Layer &L = m->layers[i];
+            ml[i] = {L.attention_norm, L.wqkv, L.wo, L.ffn_norm, L.w1, L.w3, L.w2,
+                     kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d};
+        }
+        LB_CUDA(cudaMalloc(&mega_layers_dev, nl * sizeof(k::MegaLayerHost)));
+        LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
+        LB_CUDA(cudaMalloc(&mega_barrier, 64));
+        LB_CUDA(cudaMemset(mega_barrier, 0, 64));
+    }
 }
 
 Context::~Context() {
@@ -231,6 +245,8 @@ Context::~Context() {
     if (stage_graph) cudaGraphExecDestroy(stage_graph);
     for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits, attn_scratch})
         if (p) cudaFree(p);
+    if (mega_layers_dev) cudaFree(mega_layers_dev);
+    if (mega_barrier) cudaFree(mega_barrier);
     if (tokens_dev) cudaFree(tokens_dev);
     if (state_dev) cudaFree(state_dev);
     if (state_host) cudaFreeHost(state_host);
@@ -267,6 +283,31 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
     const uint32_t d = hp.dim, ff = hp.ff(), V = hp.vocab, H = hp.heads;
     const uint32_t *past_dev = state_dev, *step_dev = state_dev + 1;
     cudaStream_t st = stream;
+    if (use_mega && n == 1 && !all_rows) {
+        // the whole token in one persistent cooperative kernel (kernels_mega.cu)
+        if (!model->has_embedding()) {
+            LB_CHECK(hidden_in != nullptr, "eval_stage: this stage needs hidden_in");
+            if (hidden_in != x) LB_CUDA(cudaMemcpyAsync(x, hidden_in, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+        k::MegaParamsHost mp;
+        mp.layers_dev = static_cast<const k::MegaLayerHost *>(mega_layers_dev);
+        mp.n_layers = (uint32_t)model->layers.size();
+        mp.tok_embeddings = model->has_embedding() ? model->tok_embeddings : nullptr;
+        mp.tokens = tokens_dev; mp.state = state_dev;
+        mp.final_norm = model->has_head() ? model->norm : nullptr;
+        mp.output = model->has_head() ? model->output : nullptr;
+        mp.x = x; mp.y = y; mp.qkv = qkv; mp.attn = attn; mp.act = act; mp.logits = logits;
+        const uint32_t hd = hp.head_dim();
+        mp.part_o = attn_scratch;
+        mp.part_ml = attn_scratch + (size_t)H * 32 * hd;
+        mp.tickets = reinterpret_cast<unsigned *>(mp.part_ml + (size_t)H * 32 * 2);
+        mp.barrier = mega_barrier;
+        mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
+        k::decode_mega(mp, st);
+        if (hidden_out && hidden_out != x)
+            LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return;
+    }
     if (model->has_embedding()) {
         if (tokens_indirect) k::get_rows_indirect(model->tok_embeddings, d, tokens_dev, step_dev, n, x, st);
         else k::get_rows_u32ids(model->tok_embeddings, d, tokens_dev, n, x, st);
@@ -395,7 +436,7 @@ void Context::eval(const uint32_t *tokens, uint32_t n, uint32_t past, float *log
             build_decode_graph();
         } else {
             LB_CUDA(cudaGraphLaunch(decode_graph, stream));
-            count_launch(model->layers.size() * 8 + 4);
+            count_launch(use_mega ? 2 : model->layers.size() * 8 + 4);
         }
     } else {
         forward(n, false, all_rows, hidden_in, hidden_out);
@@ -437,7 +478,7 @@ float Context::decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t 
     LB_CUDA(cudaEventRecord(ev0, stream));
     for (uint32_t i = done; i < steps; i++) {
         LB_CUDA(cudaGraphLaunch(decode_graph, stream));
-        count_launch(model->layers.size() * 8 + 4);
+        count_launch(use_mega ? 2 : model->layers.size() * 8 + 4);
     }
     LB_CUDA(cudaEventRecord(ev1, stream));
     LB_CUDA(cudaStreamSynchronize(stream));

@@ -74,6 +74,9 @@ struct Context {
     float *kv_k = nullptr, *kv_v = nullptr;  // [local_layers][ctx][dim]  (llama.go:93-97)
     float *x = nullptr, *y = nullptr, *cur = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *up = nullptr;
     float *attn_scratch = nullptr; // split-T decode attention partials + tickets
+    void *mega_layers_dev = nullptr;   // k::MegaLayerHost[local layers]
+    unsigned *mega_barrier = nullptr;  // grid-barrier counter of the megakernel
+    bool use_mega = false;             // single-token forward = one persistent cooperative kernel
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]

@@ -139,7 +139,7 @@ float pipeline_decode(llama::Context **ctxs, uint32_t S, const uint32_t *tokens,
             llama::Context *c = ctxs[s];
             if (!first) LB_NCCL(g_nccl.Recv(c->x, d, ncclFloat32, g_rank - 1, g_comm, st));
             LB_CUDA(cudaGraphLaunch(c->stage_graph, st));
-            count_launch(m->layers.size() * 8 + 4);
+            count_launch(c->use_mega ? 2 : m->layers.size() * 8 + 4);
             if (!last) LB_NCCL(g_nccl.Send(c->x, d, ncclFloat32, g_rank + 1, g_comm, st));
         }
     }
