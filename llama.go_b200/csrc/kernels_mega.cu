@@ -13,12 +13,16 @@
 // row); inside the CTA every warp owns a fixed 1/16 slice of K, so its slice of the activation vector
 // lives in REGISTERS for the whole phase (no activation re-reads at all) and a weight row is read by
 // 16 warps x 512-byte coalesced requests.  Row partials are combined through shared memory in a fixed
-// order (deterministic).  Before arriving at a grid barrier each warp issues cp.async.bulk.prefetch.L2
-// for its slice of the CTA's first rows of the NEXT phase, so HBM keeps streaming while the barrier
-// settles and the first loads after the barrier hit L2.
+// order (deterministic).
+// A 17th warp per CTA is a PREFETCHER: it walks the same static schedule of weight row-blocks ahead of
+// the consumers and issues cp.async.bulk.prefetch.L2 for them, throttled to a window of bytes ahead of
+// the consumers' progress counter (the 126 MB L2 is the staging ring, sized 148 x window).  It never
+// waits on a grid barrier, so HBM keeps streaming through barriers, the attention phase and the
+// redundant per-CTA rmsnorm; the consumers' loads then hit L2.
 // Numerics are those of the per-op kernels (see kernels_elementwise.cu / kernels_attn.cu); only the
 // association order of the FP32 dot-product sums differs.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -26,10 +30,14 @@
 namespace lb {
 namespace k {
 
-constexpr int MG_WARPS = 16;
-constexpr int MG_THREADS = MG_WARPS * 32;
+constexpr int MG_WARPS = 16;                 // consumer warps
+constexpr int MG_THREADS = MG_WARPS * 32;    // consumer threads (named barrier 1)
+constexpr int MG_ALL_THREADS = MG_THREADS + 32;  // + the prefetch warp
+constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
-constexpr uint32_t MG_PREFETCH_BYTES = 160 * 1024;  // per CTA, next phase's first rows
+// consumer-only barriers (the prefetch warp never participates)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_THREADS) : "memory"); }
+__device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(MG_HALF) : "memory"); }
 
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -44,16 +52,18 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) 
 struct MegaShared {
     float part[2][2][MG_ROWBLK][MG_WARPS];  // [buffer][matrix (w1|w3)][row][warp]
     double red[MG_WARPS];
-    float fred[MG_WARPS];
+    float fred[2][MG_WARPS / 2];            // per attention half
     float bcast;
-    unsigned ticket;
+    float hbcast[2];
+    unsigned ticket[2];
     float pv[MG_THREADS];
+    volatile unsigned long long consumed;   // weight bytes the consumers are done with (single writer)
 };
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
     target += nctas;
-    __syncthreads();
+    csync();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
@@ -63,7 +73,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
         }
         __threadfence();
     }
-    __syncthreads();
+    csync();
 }
 
 // this CTA's contiguous row range of an M-row matrix
@@ -72,18 +82,32 @@ __device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1)
     r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
 }
 
-// L2 prefetch of this CTA's first rows of a matrix used in a later phase (each lane one row slice)
-__device__ __forceinline__ void prefetch_matrix(const float *W, uint32_t M, uint32_t K) {
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
-    const uint32_t KS = K / MG_WARPS;
-    uint32_t nrows = MG_PREFETCH_BYTES / (K * 4);
-    if (nrows < 1) nrows = 1;
-    if (nrows > 32) nrows = 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if ((uint32_t)lane < nrows && r0 + lane < r1)
-        prefetch_l2_bulk(W + (size_t)(r0 + lane) * K + (size_t)warp * KS, KS * 4);
-}
+// ---- prefetch warp: same row-block order as gemv_phase; stays <= `window` bytes ahead of sh.consumed
+struct Prefetcher {
+    unsigned long long issued = 0;
+    unsigned long long window;
+    MegaShared *sh;
+    __device__ __forceinline__ void matrix(const float *W, const float *W3, uint32_t M, uint32_t K) {
+        const int lane = threadIdx.x & 31;
+        uint32_t r0, r1;
+        cta_rows(M, r0, r1);
+        const unsigned long long row_bytes = (unsigned long long)K * 4;
+        for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) {
+            const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
+            const unsigned long long bytes = row_bytes * nrb * (W3 ? 2 : 1);
+            const long long t0 = clock64();
+            while (issued + bytes > sh->consumed + window) {
+                __nanosleep(200);
+                if (clock64() - t0 > 8000000000LL) return;  // consumers are gone (trap elsewhere); do not spin forever
+            }
+            if ((uint32_t)lane < nrb) {
+                prefetch_l2_bulk(W + (size_t)(rb + lane) * K, (uint32_t)row_bytes);
+                if (W3) prefetch_l2_bulk(W3 + (size_t)(rb + lane) * K, (uint32_t)row_bytes);
+            }
+            issued += bytes;
+        }
+    }
+};
 
 // y = x * f32(1/sqrt(mean_f64(x^2)+1e-5)) * w, only this warp's K-slice, into registers
 // (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812, llama.go:255-259).  x may have been written by
@@ -99,13 +123,13 @@ __device__ __forceinline__ void rms_slice(const float *x, const float *w, uint32
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.red[warp] = acc;
-    __syncthreads();
+    csync();
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < MG_WARPS; i++) t += sh.red[i];
         sh.bcast = (float)(1.0 / sqrt(t / (double)K + 1e-5));
     }
-    __syncthreads();
+    csync();
     const float sc = sh.bcast;
     const uint32_t KS = K / MG_WARPS;
 #pragma unroll
@@ -176,7 +200,8 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
                 }
             }
         }
-        __syncthreads();
+        csync();
+        if (threadIdx.x == 0) sh.consumed += (unsigned long long)K * 4 * nrb * NM;  // this block's weights are in registers/done
         if (threadIdx.x < nrb) {
             float s1 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -209,19 +234,25 @@ struct MegaParams {
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
+    unsigned long long prefetch_window;  // bytes per CTA the prefetch warp may run ahead
 };
 
-// ---- attention phase: items (head, split) round-robin over CTAs; 16 warps share the item's keys
+// ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
+// (8 warps, own named barrier), so the latency chain of an item is paid once per layer.
 template <int HD>
-__device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaLayer &L, uint32_t past, MegaShared &sh, float *scores) {
+__device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaLayer &L, uint32_t past, MegaShared &sh, float *scores_all) {
     constexpr int LANES = HD / 4;
-    constexpr int G = MG_THREADS / HD;  // P·V groups
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int HW = MG_WARPS / 2;     // warps per half
+    constexpr int G = MG_HALF / HD;      // P·V groups per half
+    const int half = threadIdx.x / MG_HALF, ht = threadIdx.x % MG_HALF;
+    const int hwarp = ht >> 5, lane = threadIdx.x & 31;
     const uint32_t dim = p.dim, S = p.splits, Tn = past + 1;
     const float scale = (float)(1.0 / sqrt((double)HD));  // f32(1/sqrt(dim/heads)), llama.go:306
     const uint32_t chunk = min((Tn + S - 1) / S, p.chunk_cap);
     const uint32_t items = p.heads * S;
-    for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+    float *scores = scores_all + (size_t)half * p.chunk_cap;
+    float *pv = sh.pv + half * MG_HALF;
+    for (uint32_t item = blockIdx.x * 2 + half; item < items; item += gridDim.x * 2) {
         const uint32_t h = item / S, sp = item % S;
         const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn), nk = t1 - t0;
         float *Kh = L.Kc + (size_t)h * HD;
@@ -238,7 +269,7 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
             qv.y = (float)(__dadd_rn(__dmul_rn((double)qr.x, s0), __dmul_rn((double)qr.y, c0)));
             qv.z = (float)(__dsub_rn(__dmul_rn((double)qr.z, c1), __dmul_rn((double)qr.w, s1)));
             qv.w = (float)(__dadd_rn(__dmul_rn((double)qr.z, s1), __dmul_rn((double)qr.w, c1)));
-            if (warp == 0 && past >= t0 && past < t1) {
+            if (hwarp == 0 && past >= t0 && past < t1) {
                 const float4 kr = ldcg4(p.qkv + dim + (size_t)h * HD + lane * 4);
                 float4 ko;
                 ko.x = (float)(__dsub_rn(__dmul_rn((double)kr.x, c0), __dmul_rn((double)kr.y, s0)));
@@ -249,82 +280,83 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
                 *reinterpret_cast<float4 *>(Vh + (size_t)past * dim + lane * 4) = ldcg4(p.qkv + 2 * dim + (size_t)h * HD + lane * 4);
             }
         }
-        __syncthreads();  // the freshly stored K/V row is visible to the CTA (read back through L2)
-        // scores (MulMat K·Q, Scale): warp w takes keys w, w+16, ...
-        for (uint32_t i = warp; i < nk; i += MG_WARPS * 2) {
-            float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
-            const uint32_t i1 = i + MG_WARPS;
-            if (lane < LANES) {
-                k0 = ldcg4(Kh + (size_t)(t0 + i) * dim + lane * 4);
-                if (i1 < nk) k1 = ldcg4(Kh + (size_t)(t0 + i1) * dim + lane * 4);
+        hsync(half);  // the freshly stored K/V row is visible to this half (read back through L2)
+        // scores (MulMat K·Q, Scale): warp w takes keys w, w+HW, ... (4 keys in flight)
+        for (uint32_t i = hwarp; i < nk; i += HW * 4) {
+            float4 kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t ii = i + u * HW;
+                kk[u] = (ii < nk && lane < LANES) ? ldcg4(Kh + (size_t)(t0 + ii) * dim + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float d0 = k0.x * qv.x; d0 = fmaf(k0.y, qv.y, d0); d0 = fmaf(k0.z, qv.z, d0); d0 = fmaf(k0.w, qv.w, d0);
-            float d1 = k1.x * qv.x; d1 = fmaf(k1.y, qv.y, d1); d1 = fmaf(k1.z, qv.z, d1); d1 = fmaf(k1.w, qv.w, d1);
-            d0 = warp_sum(d0); d1 = warp_sum(d1);
-            if (lane == 0) {
-                scores[i] = __fmul_rn(d0, scale);
-                if (i1 < nk) scores[i1] = __fmul_rn(d1, scale);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t ii = i + u * HW;
+                float dd = kk[u].x * qv.x;
+                dd = fmaf(kk[u].y, qv.y, dd); dd = fmaf(kk[u].z, qv.z, dd); dd = fmaf(kk[u].w, qv.w, dd);
+                dd = warp_sum(dd);
+                if (lane == 0 && ii < nk) scores[ii] = __fmul_rn(dd, scale);
             }
         }
-        __syncthreads();
+        hsync(half);
         // local softmax statistics (SoftMax, ml.go:2472-2499, per split)
         float m = -INFINITY;
-        for (uint32_t i = threadIdx.x; i < nk; i += MG_THREADS) m = fmaxf(m, scores[i]);
+        for (uint32_t i = ht; i < nk; i += MG_HALF) m = fmaxf(m, scores[i]);
         m = warp_max(m);
-        if (lane == 0) sh.fred[warp] = m;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = sh.fred[0];
-            for (int i = 1; i < MG_WARPS; i++) t = fmaxf(t, sh.fred[i]);
-            sh.bcast = t;
+        if (lane == 0) sh.fred[half][hwarp] = m;
+        hsync(half);
+        if (ht == 0) {
+            float t = sh.fred[half][0];
+            for (int i = 1; i < HW; i++) t = fmaxf(t, sh.fred[half][i]);
+            sh.hbcast[half] = t;
         }
-        __syncthreads();
-        m = sh.bcast;
+        hsync(half);
+        m = sh.hbcast[half];
         float l = 0.f;
-        for (uint32_t i = threadIdx.x; i < nk; i += MG_THREADS) {
+        for (uint32_t i = ht; i < nk; i += MG_HALF) {
             float e = (float)exp((double)__fsub_rn(scores[i], m));
             scores[i] = e;
             l += e;
         }
         l = warp_sum(l);
-        __syncthreads();
-        if (lane == 0) sh.fred[warp] = l;
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        hsync(half);
+        if (lane == 0) sh.fred[half][hwarp] = l;
+        hsync(half);
+        if (ht == 0) {
             float t = 0.f;
-            for (int i = 0; i < MG_WARPS; i++) t += sh.fred[i];
+            for (int i = 0; i < HW; i++) t += sh.fred[half][i];
             p.part_ml[((size_t)h * S + sp) * 2 + 0] = m;
             p.part_ml[((size_t)h * S + sp) * 2 + 1] = t;
         }
         // partial P·V
-        const uint32_t g = threadIdx.x / HD, d = threadIdx.x % HD;
+        const uint32_t g = ht / HD, d = ht % HD;
         float acc = 0.f;
         {
             const float *vp = Vh + d;
             uint32_t i = g;
-            for (; i + 3 * G < nk; i += 4 * G) {
-                float v[4];
+            for (; i + 7 * G < nk; i += 8 * G) {
+                float v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = __ldcg(vp + (size_t)(t0 + i + u * G) * dim);
+                for (int u = 0; u < 8; u++) v[u] = __ldcg(vp + (size_t)(t0 + i + u * G) * dim);
 #pragma unroll
-                for (int u = 0; u < 4; u++) acc = fmaf(v[u], scores[i + u * G], acc);
+                for (int u = 0; u < 8; u++) acc = fmaf(v[u], scores[i + u * G], acc);
             }
             for (; i < nk; i += G) acc = fmaf(__ldcg(vp + (size_t)(t0 + i) * dim), scores[i], acc);
         }
-        sh.pv[threadIdx.x] = acc;
-        __syncthreads();
-        if (threadIdx.x < HD) {
+        pv[ht] = acc;
+        hsync(half);
+        if (ht < HD) {
             float r = 0.f;
-            for (int i = 0; i < G; i++) r += sh.pv[i * HD + threadIdx.x];
-            p.part_o[((size_t)h * S + sp) * HD + threadIdx.x] = r;
+            for (int i = 0; i < G; i++) r += pv[i * HD + ht];
+            p.part_o[((size_t)h * S + sp) * HD + ht] = r;
         }
         __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) sh.ticket = atomicAdd(&p.tickets[h], 1u);
-        __syncthreads();
-        if (sh.ticket == S - 1) {  // last split of this head: merge
+        hsync(half);
+        if (ht == 0) sh.ticket[half] = atomicAdd(&p.tickets[h], 1u);
+        hsync(half);
+        if (sh.ticket[half] == S - 1) {  // last split of this head: merge
             __threadfence();
-            if (threadIdx.x < HD) {
+            if (ht < HD) {
                 float M = -INFINITY;
                 for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]));
                 float Lsum = 0.f, o = 0.f;
@@ -334,24 +366,43 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
                     if (ls > 0.f) {
                         const float wgt = (float)exp((double)__fsub_rn(ms, M));
                         Lsum = fmaf(ls, wgt, Lsum);
-                        o = fmaf(__ldcg(&p.part_o[((size_t)h * S + s2) * HD + threadIdx.x]), wgt, o);
+                        o = fmaf(__ldcg(&p.part_o[((size_t)h * S + s2) * HD + ht]), wgt, o);
                     }
                 }
-                p.attn[(size_t)h * HD + threadIdx.x] = __fmul_rn(o, __fdiv_rn(1.0f, Lsum));
+                p.attn[(size_t)h * HD + ht] = __fmul_rn(o, __fdiv_rn(1.0f, Lsum));
             }
-            if (threadIdx.x == 0) p.tickets[h] = 0;
+            if (ht == 0) p.tickets[h] = 0;
         }
-        __syncthreads();
+        hsync(half);
     }
 }
 
 template <int VD, int VF, int HD>
-__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
-    extern __shared__ float scores[];  // [chunk_cap]
+__global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+    extern __shared__ float scores[];  // [2][chunk_cap]
     __shared__ MegaShared sh;
+    const uint32_t dim = p.dim, ff = p.ff;
+    if (threadIdx.x == 0) sh.consumed = 0;
+    __syncthreads();  // the only full-CTA barrier: after it the prefetch warp runs free
+
+    if (threadIdx.x >= MG_THREADS) {
+        // ================= prefetch warp: weights of every phase, in consumer order =================
+        Prefetcher pf;
+        pf.window = p.prefetch_window;
+        pf.sh = &sh;
+        for (uint32_t li = 0; li < p.n_layers; li++) {
+            const MegaLayer L = p.layers[li];
+            pf.matrix(L.wqkv, nullptr, 3 * dim, dim);
+            pf.matrix(L.wo, nullptr, dim, dim);
+            pf.matrix(L.w1, L.w3, ff, dim);
+            pf.matrix(L.w2, nullptr, dim, ff);
+        }
+        if (p.output) pf.matrix(p.output, nullptr, p.vocab, dim);
+        return;
+    }
+
     unsigned target = 0;
     const uint32_t past = p.state[0];
-    const uint32_t dim = p.dim, ff = p.ff;
     const float *xin = p.x;
     if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
 
@@ -361,7 +412,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh);
-            prefetch_matrix(L.wo, dim, dim);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         // ---- P2: RoPE, KV store, attention (llama.go:274-333)
@@ -371,23 +421,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             load_slice<VD>(p.attn, dim, xs);
             gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh);
-            prefetch_matrix(L.w1, ff, dim);
-            prefetch_matrix(L.w3, ff, dim);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh);
-            prefetch_matrix(L.w2, dim, ff);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
             gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh);
-            if (li + 1 < p.n_layers) prefetch_matrix(p.layers[li + 1].wqkv, 3 * dim, dim);
-            else if (p.output) prefetch_matrix(p.output, p.vocab, dim);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         xin = p.x;
@@ -415,7 +460,7 @@ static bool pick_variant(uint32_t dim, uint32_t ff, uint32_t hd, int &vd, int &v
 template <int VD, int VF>
 static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_ALL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
@@ -434,7 +479,7 @@ bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads) {
 }
 
 uint32_t decode_mega_splits(uint32_t heads) {
-    uint32_t s = (2 * kNumSMs) / heads;  // <= 2 attention items per CTA
+    uint32_t s = (2 * kNumSMs) / heads;  // <= 2 attention items per CTA = one per half, run concurrently
     return s < 1 ? 1 : (s > 32 ? 32 : s);
 }
 
@@ -452,7 +497,9 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     int vd, vf;
     const uint32_t hd = h.dim / h.heads;
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
-    const size_t smem = (size_t)p.chunk_cap * sizeof(float);
+    const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
+    static const unsigned long long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoull(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 448;
+    p.prefetch_window = window_kb * 1024ull;  // x 148 CTAs = 65 MB of the 126 MB L2 by default
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned), st));
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
