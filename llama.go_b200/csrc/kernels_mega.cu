@@ -14,11 +14,11 @@
 // lives in REGISTERS for the whole phase (no activation re-reads at all) and a weight row is read by
 // 16 warps x 512-byte coalesced requests.  Row partials are combined through shared memory in a fixed
 // order (deterministic).
-// A 17th warp per CTA is a PREFETCHER: it walks the same static schedule of weight row-blocks ahead of
-// the consumers and issues cp.async.bulk.prefetch.L2 for them, throttled to a window of bytes ahead of
-// the consumers' progress counter (the 126 MB L2 is the staging ring, sized 148 x window).  It never
-// waits on a grid barrier, so HBM keeps streaming through barriers, the attention phase and the
-// redundant per-CTA rmsnorm; the consumers' loads then hit L2.
+// Before a CTA stalls (grid barrier, attention phase, the redundant per-CTA rmsnorm) one warp queues
+// cp.async.bulk.prefetch.L2 requests for the first few hundred KB of the CTA's rows of the NEXT GEMV
+// phase(s): the memory system drains that queue at HBM speed while the SM waits, and the first loads
+// after the stall hit the 126 MB L2.  (A decoupled 17th "prefetch warp" with a progress window was
+// measured slower: 544 threads cap the kernel at 96 registers and the GEMV loop spills.)
 // Numerics are those of the per-op kernels (see kernels_elementwise.cu / kernels_attn.cu); only the
 // association order of the FP32 dot-product sums differs.
 #include <cooperative_groups.h>
@@ -32,7 +32,6 @@ namespace k {
 
 constexpr int MG_WARPS = 16;                 // consumer warps
 constexpr int MG_THREADS = MG_WARPS * 32;    // consumer threads (named barrier 1)
-constexpr int MG_ALL_THREADS = MG_THREADS + 32;  // + the prefetch warp
 constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
 // consumer-only barriers (the prefetch warp never participates)
@@ -57,7 +56,6 @@ struct MegaShared {
     float hbcast[2];
     unsigned ticket[2];
     float pv[MG_THREADS];
-    volatile unsigned long long consumed;   // weight bytes the consumers are done with (single writer)
 };
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
@@ -82,32 +80,22 @@ __device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1)
     r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
 }
 
-// ---- prefetch warp: same row-block order as gemv_phase; stays <= `window` bytes ahead of sh.consumed
-struct Prefetcher {
-    unsigned long long issued = 0;
-    unsigned long long window;
-    MegaShared *sh;
-    __device__ __forceinline__ void matrix(const float *W, const float *W3, uint32_t M, uint32_t K) {
-        const int lane = threadIdx.x & 31;
-        uint32_t r0, r1;
-        cta_rows(M, r0, r1);
-        const unsigned long long row_bytes = (unsigned long long)K * 4;
-        for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) {
-            const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
-            const unsigned long long bytes = row_bytes * nrb * (W3 ? 2 : 1);
-            const long long t0 = clock64();
-            while (issued + bytes > sh->consumed + window) {
-                __nanosleep(200);
-                if (clock64() - t0 > 8000000000LL) return;  // consumers are gone (trap elsewhere); do not spin forever
-            }
-            if ((uint32_t)lane < nrb) {
-                prefetch_l2_bulk(W + (size_t)(rb + lane) * K, (uint32_t)row_bytes);
-                if (W3) prefetch_l2_bulk(W3 + (size_t)(rb + lane) * K, (uint32_t)row_bytes);
-            }
-            issued += bytes;
-        }
+// Queue L2 prefetches for this CTA's rows [skip_bytes, skip_bytes + budget) (in bytes of its row range)
+// of a matrix a later phase will stream (pairs of w1/w3 rows when W3 is given).  Issued by the last warp.
+__device__ __forceinline__ void prefetch_rows(const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t skip_bytes,
+                                              uint32_t budget_bytes) {
+    if ((threadIdx.x >> 5) != MG_WARPS - 1) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const uint32_t row_bytes = K * 4 * (W3 ? 2 : 1);
+    const uint32_t first = skip_bytes / row_bytes;
+    const uint32_t n = (budget_bytes + row_bytes - 1) / row_bytes;
+    for (uint32_t i = first + lane; i < first + n && r0 + i < r1; i += 32) {
+        prefetch_l2_bulk(W + (size_t)(r0 + i) * K, K * 4);
+        if (W3) prefetch_l2_bulk(W3 + (size_t)(r0 + i) * K, K * 4);
     }
-};
+}
 
 // y = x * f32(1/sqrt(mean_f64(x^2)+1e-5)) * w, only this warp's K-slice, into registers
 // (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812, llama.go:255-259).  x may have been written by
@@ -201,7 +189,6 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
             }
         }
         csync();
-        if (threadIdx.x == 0) sh.consumed += (unsigned long long)K * 4 * nrb * NM;  // this block's weights are in registers/done
         if (threadIdx.x < nrb) {
             float s1 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -234,7 +221,7 @@ struct MegaParams {
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
-    unsigned long long prefetch_window;  // bytes per CTA the prefetch warp may run ahead
+    uint32_t prefetch_bytes;  // bytes of the next phase's rows each CTA queues into L2 before a stall
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -378,29 +365,11 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
 }
 
 template <int VD, int VF, int HD>
-__global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
     extern __shared__ float scores[];  // [2][chunk_cap]
     __shared__ MegaShared sh;
     const uint32_t dim = p.dim, ff = p.ff;
-    if (threadIdx.x == 0) sh.consumed = 0;
-    __syncthreads();  // the only full-CTA barrier: after it the prefetch warp runs free
-
-    if (threadIdx.x >= MG_THREADS) {
-        // ================= prefetch warp: weights of every phase, in consumer order =================
-        Prefetcher pf;
-        pf.window = p.prefetch_window;
-        pf.sh = &sh;
-        for (uint32_t li = 0; li < p.n_layers; li++) {
-            const MegaLayer L = p.layers[li];
-            pf.matrix(L.wqkv, nullptr, 3 * dim, dim);
-            pf.matrix(L.wo, nullptr, dim, dim);
-            pf.matrix(L.w1, L.w3, ff, dim);
-            pf.matrix(L.w2, nullptr, dim, ff);
-        }
-        if (p.output) pf.matrix(p.output, nullptr, p.vocab, dim);
-        return;
-    }
-
+    const uint32_t PF = p.prefetch_bytes;  // bytes queued per CTA before a stall
     unsigned target = 0;
     const uint32_t past = p.state[0];
     const float *xin = p.x;
@@ -412,27 +381,33 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh);
+            prefetch_rows(L.wo, nullptr, dim, dim, 0, PF);            // streams in during barrier + attention
         }
         grid_barrier(p.barrier, target, gridDim.x);
         // ---- P2: RoPE, KV store, attention (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
+        prefetch_rows(L.w1, L.w3, ff, dim, 0, PF / 2);
         grid_barrier(p.barrier, target, gridDim.x);
         {   // ---- P3: wo + residual (llama.go:336-340)
             float4 xs[VD];
             load_slice<VD>(p.attn, dim, xs);
             gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh);
+            prefetch_rows(L.w1, L.w3, ff, dim, PF / 2, PF / 2);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh);
+            prefetch_rows(L.w2, nullptr, dim, ff, 0, PF);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
             gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh);
+            if (li + 1 < p.n_layers) prefetch_rows(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 0, PF);
+            else if (p.output) prefetch_rows(p.output, nullptr, p.vocab, dim, 0, PF);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         xin = p.x;
@@ -460,7 +435,7 @@ static bool pick_variant(uint32_t dim, uint32_t ff, uint32_t hd, int &vd, int &v
 template <int VD, int VF>
 static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_ALL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
@@ -498,8 +473,8 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     const uint32_t hd = h.dim / h.heads;
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
-    static const unsigned long long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoull(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 448;
-    p.prefetch_window = window_kb * 1024ull;  // x 148 CTAs = 65 MB of the 126 MB L2 by default
+    static const unsigned long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoul(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 320;
+    p.prefetch_bytes = (uint32_t)(window_kb * 1024ul);  // x 148 CTAs = 47 MB of the 126 MB L2 by default
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned), st));
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
