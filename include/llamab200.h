@@ -100,6 +100,9 @@ LB_API int lb_context_read_logits(lb_context *c, float *logits_out);            
 LB_API int lb_context_read_kv(lb_context *c, uint32_t layer, uint32_t t0, uint32_t nt, float *k_out, float *v_out);
 LB_API int lb_context_read_hidden(lb_context *c, uint32_t n, float *hidden_out);  /* residual stream before final norm */
 LB_API int lb_context_synchronize(lb_context *c);
+/* profiling aid: 13 globaltimer (ns) stamps per layer of the last single-token megakernel launch
+ * (CTA 0), valid when the context was created with LB_MEGA_TRACE=1 in the environment */
+LB_API int lb_context_mega_trace(lb_context *c, uint64_t *out, uint32_t n);
 /* pipeline stages (multi-GPU layer sharding): run only this stage's layers.
  * hidden_in/out are DEVICE pointers to [n][dim] FP32 (NULL on the first/last stage). */
 LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past,

@@ -47,6 +47,7 @@ _SIGS = {
     "lb_context_read_kv": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _f32p]),
     "lb_context_read_hidden": (C.c_int, [_vp, C.c_uint32, _f32p]),
     "lb_context_synchronize": (C.c_int, [_vp]),
+    "lb_context_mega_trace": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_uint32]),
     "lb_eval_stage": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, _vp, _vp, _f32p]),
     "lb_context_hidden_buffer": (_vp, [_vp]),
     "lb_context_stream": (_vp, [_vp]),

@@ -145,6 +145,12 @@ int lb_context_read_hidden(lb_context *c, uint32_t n, float *out) {
                LB_CUDA(cudaSetDevice(x->model->device)); LB_CUDA(cudaStreamSynchronize(x->stream));
                LB_CUDA(cudaMemcpy(out, x->x, (size_t)n * x->model->hp.dim * 4, cudaMemcpyDeviceToHost)));
 }
+int lb_context_mega_trace(lb_context *c, uint64_t *out, uint32_t n) {
+    LB_TRY_INT(LB_CHECK(c && out, "nil argument"); LB_CHECK(c->c->mega_trace != nullptr, "no trace (set LB_MEGA_TRACE=1 before creating the context)");
+               LB_CHECK(n <= c->c->model->layers.size() * 13, "trace: n too large");
+               LB_CUDA(cudaSetDevice(c->c->model->device)); LB_CUDA(cudaStreamSynchronize(c->c->stream));
+               LB_CUDA(cudaMemcpy(out, c->c->mega_trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost)));
+}
 int lb_context_synchronize(lb_context *c) {
     LB_TRY_INT(LB_CHECK(c, "nil context"); LB_CUDA(cudaSetDevice(c->c->model->device)); LB_CUDA(cudaStreamSynchronize(c->c->stream)));
 }

@@ -92,6 +92,7 @@ struct MegaParamsHost {
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx;
+    void *trace = nullptr;            // optional uint64[n_layers*13] phase time stamps (profiling aid)
 };
 bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads);
 uint32_t decode_mega_splits(uint32_t heads);

@@ -222,6 +222,7 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     uint32_t prefetch_bytes;  // bytes of the next phase's rows each CTA queues into L2 before a stall
+    unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -375,41 +376,64 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     const float *xin = p.x;
     if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
 
+    unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    auto stamp = [&](uint32_t li, int i) {
+        if (tr) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[li * 13 + i] = t;
+        }
+    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
+        stamp(li, 0);
         {   // ---- P1: rmsnorm * attention_norm, then [wq;wk;wv] (llama.go:255-265)
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
+            stamp(li, 1);
             gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh);
-            prefetch_rows(L.wo, nullptr, dim, dim, 0, PF);            // streams in during barrier + attention
+            if (PF) prefetch_rows(L.wo, nullptr, dim, dim, 0, PF);  // streams in during barrier + attention
         }
+        stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 3);
         // ---- P2: RoPE, KV store, attention (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
-        prefetch_rows(L.w1, L.w3, ff, dim, 0, PF / 2);
+        if (PF) prefetch_rows(L.w1, L.w3, ff, dim, 0, PF / 2);
+        stamp(li, 4);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 5);
         {   // ---- P3: wo + residual (llama.go:336-340)
             float4 xs[VD];
             load_slice<VD>(p.attn, dim, xs);
             gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh);
-            prefetch_rows(L.w1, L.w3, ff, dim, PF / 2, PF / 2);
+            if (PF) prefetch_rows(L.w1, L.w3, ff, dim, PF / 2, PF / 2);
         }
+        stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
+            stamp(li, 8);
             gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh);
-            prefetch_rows(L.w2, nullptr, dim, ff, 0, PF);
+            if (PF) prefetch_rows(L.w2, nullptr, dim, ff, 0, PF);
         }
+        stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
             gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh);
-            if (li + 1 < p.n_layers) prefetch_rows(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 0, PF);
-            else if (p.output) prefetch_rows(p.output, nullptr, p.vocab, dim, 0, PF);
+            if (PF) {
+                if (li + 1 < p.n_layers) prefetch_rows(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 0, PF);
+                else if (p.output) prefetch_rows(p.output, nullptr, p.vocab, dim, 0, PF);
+            }
         }
+        stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 12);
         xin = p.x;
     }
     if (p.output) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
@@ -473,8 +497,9 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     const uint32_t hd = h.dim / h.heads;
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
-    static const unsigned long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoul(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 320;
-    p.prefetch_bytes = (uint32_t)(window_kb * 1024ul);  // x 148 CTAs = 47 MB of the 126 MB L2 by default
+    static const unsigned long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoul(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 0;
+    p.prefetch_bytes = (uint32_t)(window_kb * 1024ul);  // measured: 0 (off) is best; kept as a tunable
+    p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned), st));
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);

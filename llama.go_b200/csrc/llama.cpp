@@ -235,6 +235,10 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
         LB_CUDA(cudaMalloc(&mega_barrier, 64));
         LB_CUDA(cudaMemset(mega_barrier, 0, 64));
+        if (getenv("LB_MEGA_TRACE")) {
+            LB_CUDA(cudaMalloc(&mega_trace, nl * 13 * sizeof(unsigned long long)));
+            LB_CUDA(cudaMemset(mega_trace, 0, nl * 13 * sizeof(unsigned long long)));
+        }
     }
 }
 
@@ -247,6 +251,7 @@ Context::~Context() {
         if (p) cudaFree(p);
     if (mega_layers_dev) cudaFree(mega_layers_dev);
     if (mega_barrier) cudaFree(mega_barrier);
+    if (mega_trace) cudaFree(mega_trace);
     if (tokens_dev) cudaFree(tokens_dev);
     if (state_dev) cudaFree(state_dev);
     if (state_host) cudaFreeHost(state_host);
@@ -302,6 +307,7 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.part_ml = attn_scratch + (size_t)H * 32 * hd;
         mp.tickets = reinterpret_cast<unsigned *>(mp.part_ml + (size_t)H * 32 * 2);
         mp.barrier = mega_barrier;
+        mp.trace = mega_trace;
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
         k::decode_mega(mp, st);
         if (hidden_out && hidden_out != x)

@@ -76,6 +76,7 @@ struct Context {
     float *attn_scratch = nullptr; // split-T decode attention partials + tickets
     void *mega_layers_dev = nullptr;   // k::MegaLayerHost[local layers]
     unsigned *mega_barrier = nullptr;  // grid-barrier counter of the megakernel
+    void *mega_trace = nullptr;        // LB_MEGA_TRACE=1: per-phase globaltimer stamps of CTA 0
     bool use_mega = false;             // single-token forward = one persistent cooperative kernel
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
