@@ -56,6 +56,7 @@ struct MegaShared {
     float hbcast[2];
     unsigned ticket[2];
     float pv[MG_THREADS];
+    double rope_cs[64][2];  // cos,sin(past * 10000^(-2j/hd)) for this token, j < hd/2 (once per launch)
 };
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
@@ -145,22 +146,79 @@ __device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&
     }
 }
 
+// rows per load batch of a phase with V float4 per lane and NM matrices
+__host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
+// rows of the batch that is preloaded across a barrier (half a batch: it must stay in registers, unspilled)
+__host__ __device__ constexpr int mg_rbp(int V, int NM) { return mg_rb(V, NM) >= 2 ? mg_rb(V, NM) / 2 : 1; }
+
+// Load the FIRST batch of a phase's weights into registers.  Called BEFORE the grid barrier that
+// precedes the phase: weights are read-only, so these requests stream from HBM while the barrier
+// settles (the same trick as the prefetch-before-griddepcontrol.wait of the per-op kernels).
+template <int V, bool SWIGLU>
+__device__ __forceinline__ void gemv_preload(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
+                                             float4 (&a)[mg_rbp(V, SWIGLU ? 2 : 1)][SWIGLU ? 2 : 1][V]) {
+    constexpr int NM = SWIGLU ? 2 : 1;
+    constexpr int RB = mg_rbp(V, NM);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - r0);
+    const float *w1 = W + (size_t)warp * KS + lane * 4;
+    const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
+#pragma unroll
+    for (int i = 0; i < RB; i++) {
+        const bool rok = (uint32_t)i < nrb;
+        const size_t off = (size_t)(r0 + i) * K;
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
+            a[i][0][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 // One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
+// `pre` arrives holding the first mg_rbp rows of the CTA's first row block (gemv_preload).
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
-                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh) {
+                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh,
+                                           float4 (&pre)[mg_rbp(V, SWIGLU ? 2 : 1)][SWIGLU ? 2 : 1][V]) {
     constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int RB = (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8;  // rows per load batch
+    constexpr int RB = mg_rb(V, NM), RBP = mg_rbp(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KS = K / MG_WARPS;
     uint32_t r0, r1;
     cta_rows(M, r0, r1);
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
+    // dot products of `count` rows held in registers -> per-warp partials in shared memory
+    auto reduce_rows = [&](auto &a, int count, uint32_t r, uint32_t nrb, int buf) {
+#pragma unroll
+        for (int i = 0; i < count; i++) {
+#pragma unroll
+            for (int mtx = 0; mtx < NM; mtx++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < V; j++) {
+                    acc = fmaf(a[i][mtx][j].x, xs[j].x, acc); acc = fmaf(a[i][mtx][j].y, xs[j].y, acc);
+                    acc = fmaf(a[i][mtx][j].z, xs[j].z, acc); acc = fmaf(a[i][mtx][j].w, xs[j].w, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
+            }
+        }
+    };
     int buf = 0;
     for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK, buf ^= 1) {
         const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
-        for (uint32_t r = 0; r < nrb; r += RB) {
+        uint32_t r = 0;
+        if (rb == r0) {  // the first rows were loaded before the barrier
+            reduce_rows(pre, RBP, 0, nrb, buf);
+            r = RBP;
+        }
+        for (; r < nrb; r += RB) {
             float4 a[RB][NM][V];
 #pragma unroll
             for (int i = 0; i < RB; i++) {
@@ -173,20 +231,7 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
                     if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < RB; i++) {
-#pragma unroll
-                for (int mtx = 0; mtx < NM; mtx++) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < V; j++) {
-                        acc = fmaf(a[i][mtx][j].x, xs[j].x, acc); acc = fmaf(a[i][mtx][j].y, xs[j].y, acc);
-                        acc = fmaf(a[i][mtx][j].z, xs[j].z, acc); acc = fmaf(a[i][mtx][j].w, xs[j].w, acc);
-                    }
-                    acc = warp_sum(acc);
-                    if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
-                }
-            }
+            reduce_rows(a, RB, r, nrb, buf);
         }
         csync();
         if (threadIdx.x < nrb) {
@@ -202,7 +247,7 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
             else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
             out[row] = v;
         }
-        // the other partial buffer is used by the next block; this one is reused only after the next __syncthreads
+        // the other partial buffer is used by the next block; this one is reused only after the next csync
     }
 }
 
@@ -250,9 +295,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
         float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < LANES) {
             const float4 qr = ldcg4(p.qkv + (size_t)h * HD + lane * 4);
-            double s0, c0, s1, c1;
-            sincos((double)past * pow(10000.0, ((double)(-(lane * 4))) / (double)HD), &s0, &c0);
-            sincos((double)past * pow(10000.0, ((double)(-(lane * 4 + 2))) / (double)HD), &s1, &c1);
+            const double c0 = sh.rope_cs[lane * 2][0], s0 = sh.rope_cs[lane * 2][1];
+            const double c1 = sh.rope_cs[lane * 2 + 1][0], s1 = sh.rope_cs[lane * 2 + 1][1];
             qv.x = (float)(__dsub_rn(__dmul_rn((double)qr.x, c0), __dmul_rn((double)qr.y, s0)));
             qv.y = (float)(__dadd_rn(__dmul_rn((double)qr.x, s0), __dmul_rn((double)qr.y, c0)));
             qv.z = (float)(__dsub_rn(__dmul_rn((double)qr.z, c1), __dmul_rn((double)qr.w, s1)));
@@ -338,30 +382,39 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
             for (int i = 0; i < G; i++) r += pv[i * HD + ht];
             p.part_o[((size_t)h * S + sp) * HD + ht] = r;
         }
-        __threadfence();
-        hsync(half);
-        if (ht == 0) sh.ticket[half] = atomicAdd(&p.tickets[h], 1u);
-        hsync(half);
-        if (sh.ticket[half] == S - 1) {  // last split of this head: merge
-            __threadfence();
-            if (ht < HD) {
-                float M = -INFINITY;
-                for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]));
-                float Lsum = 0.f, o = 0.f;
-                for (uint32_t s2 = 0; s2 < S; s2++) {
-                    const float ms = __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]);
-                    const float ls = __ldcg(&p.part_ml[((size_t)h * S + s2) * 2 + 1]);
-                    if (ls > 0.f) {
-                        const float wgt = (float)exp((double)__fsub_rn(ms, M));
-                        Lsum = fmaf(ls, wgt, Lsum);
-                        o = fmaf(__ldcg(&p.part_o[((size_t)h * S + s2) * HD + ht]), wgt, o);
-                    }
+        hsync(half);  // scores / pv buffers are reused by the next item of this half
+    }
+}
+
+// P3 prologue: merge the S split partials of the heads this warp's K-slice covers, straight into the
+// register-resident activation slice:  out = (sum_s O_s * w_s) * f32(1 / sum_s l_s * w_s),
+// w_s = f32(exp(f64(m_s - M))), M = max_s m_s  (same formula as attention_decode_kernel's merge).
+template <int V, int HD>
+__device__ __forceinline__ void merged_attention_slice(const MegaParams &p, float4 (&xs)[V]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = p.dim / MG_WARPS, S = p.splits;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const uint32_t e = (j * 32 + lane) * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < KS) {
+            const uint32_t g = warp * KS + e, h = g / HD, d = g % HD;
+            float M = -INFINITY;
+            for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]));
+            float Lsum = 0.f;
+            for (uint32_t s2 = 0; s2 < S; s2++) {
+                const float2 ml = __ldcg(reinterpret_cast<const float2 *>(&p.part_ml[((size_t)h * S + s2) * 2]));
+                if (ml.y > 0.f) {
+                    const float wgt = (float)exp((double)__fsub_rn(ml.x, M));
+                    const float4 po = ldcg4(&p.part_o[((size_t)h * S + s2) * HD + d]);
+                    Lsum = fmaf(ml.y, wgt, Lsum);
+                    o.x = fmaf(po.x, wgt, o.x); o.y = fmaf(po.y, wgt, o.y); o.z = fmaf(po.z, wgt, o.z); o.w = fmaf(po.w, wgt, o.w);
                 }
-                p.attn[(size_t)h * HD + ht] = __fmul_rn(o, __fdiv_rn(1.0f, Lsum));
             }
-            if (ht == 0) p.tickets[h] = 0;
+            const float inv = __fdiv_rn(1.0f, Lsum);
+            o.x = __fmul_rn(o.x, inv); o.y = __fmul_rn(o.y, inv); o.z = __fmul_rn(o.z, inv); o.w = __fmul_rn(o.w, inv);
         }
-        hsync(half);
+        xs[j] = o;
     }
 }
 
@@ -370,7 +423,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     extern __shared__ float scores[];  // [2][chunk_cap]
     __shared__ MegaShared sh;
     const uint32_t dim = p.dim, ff = p.ff;
-    const uint32_t PF = p.prefetch_bytes;  // bytes queued per CTA before a stall
     unsigned target = 0;
     const uint32_t past = p.state[0];
     const float *xin = p.x;
@@ -384,6 +436,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             tr[li * 13 + i] = t;
         }
     };
+    // RoPE table of this token's position (ComputeForwardRopeFP32's pow/cos/sin in f64, ml.go:2307-2310)
+    if (threadIdx.x < HD / 2) {
+        double sn, cs;
+        sincos((double)past * pow(10000.0, ((double)(-(int)(2 * threadIdx.x))) / (double)HD), &sn, &cs);
+        sh.rope_cs[threadIdx.x][0] = cs;
+        sh.rope_cs[threadIdx.x][1] = sn;
+    }
+    // register arrays holding the first weight batch of the upcoming phase (loaded before its barrier)
+    float4 a_d[mg_rbp(VD, 1)][1][VD];   // phases with K = dim, one matrix (wqkv, wo, lm_head)
+    gemv_preload<VD, false>(p.n_layers ? p.layers[0].wqkv : p.output, nullptr, p.n_layers ? 3 * dim : p.vocab, dim, a_d);
+    csync();
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
         stamp(li, 0);
@@ -391,47 +454,46 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             stamp(li, 1);
-            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh);
-            if (PF) prefetch_rows(L.wo, nullptr, dim, dim, 0, PF);  // streams in during barrier + attention
+            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, a_d);
         }
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
-        // ---- P2: RoPE, KV store, attention (llama.go:274-333)
+        // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
-        if (PF) prefetch_rows(L.w1, L.w3, ff, dim, 0, PF / 2);
+        gemv_preload<VD, false>(L.wo, nullptr, dim, dim, a_d);
         stamp(li, 4);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 5);
-        {   // ---- P3: wo + residual (llama.go:336-340)
+        {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
-            load_slice<VD>(p.attn, dim, xs);
-            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh);
-            if (PF) prefetch_rows(L.w1, L.w3, ff, dim, PF / 2, PF / 2);
+            merged_attention_slice<VD, HD>(p, xs);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, a_d);
         }
         stamp(li, 6);
-        grid_barrier(p.barrier, target, gridDim.x);
-        stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
+            float4 a_s[mg_rbp(VD, 2)][2][VD];
+            gemv_preload<VD, true>(L.w1, L.w3, ff, dim, a_s);
+            grid_barrier(p.barrier, target, gridDim.x);
+            stamp(li, 7);
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             stamp(li, 8);
-            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh);
-            if (PF) prefetch_rows(L.w2, nullptr, dim, ff, 0, PF);
+            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, a_s);
         }
         stamp(li, 9);
-        grid_barrier(p.barrier, target, gridDim.x);
-        stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
+            float4 a_f[mg_rbp(VF, 1)][1][VF];
+            gemv_preload<VF, false>(L.w2, nullptr, dim, ff, a_f);
+            grid_barrier(p.barrier, target, gridDim.x);
+            stamp(li, 10);
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
-            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh);
-            if (PF) {
-                if (li + 1 < p.n_layers) prefetch_rows(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 0, PF);
-                else if (p.output) prefetch_rows(p.output, nullptr, p.vocab, dim, 0, PF);
-            }
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, a_f);
         }
         stamp(li, 11);
+        if (li + 1 < p.n_layers) gemv_preload<VD, false>(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, a_d);
+        else if (p.output) gemv_preload<VD, false>(p.output, nullptr, p.vocab, dim, a_d);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 12);
         xin = p.x;
@@ -439,7 +501,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     if (p.output) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
         float4 xs[VD];
         rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
-        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh);
+        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, a_d);
     }
 }
 
