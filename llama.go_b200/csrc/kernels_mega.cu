@@ -388,7 +388,9 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
 
 // P3 prologue: merge the S split partials of the heads this warp's K-slice covers, straight into the
 // register-resident activation slice:  out = (sum_s O_s * w_s) * f32(1 / sum_s l_s * w_s),
-// w_s = f32(exp(f64(m_s - M))), M = max_s m_s  (same formula as attention_decode_kernel's merge).
+// w_s = expf(m_s - M), M = max_s m_s.  (The split/merge is this engine's reassociation of the
+// reference's single-pass softmax; the merge weights use the FP32 expf — an f64 exp per lane and split
+// measured 8 us per layer here — while the softmax terms themselves keep the reference's f64 exp.)
 template <int V, int HD>
 __device__ __forceinline__ void merged_attention_slice(const MegaParams &p, float4 (&xs)[V]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -405,7 +407,7 @@ __device__ __forceinline__ void merged_attention_slice(const MegaParams &p, floa
             for (uint32_t s2 = 0; s2 < S; s2++) {
                 const float2 ml = __ldcg(reinterpret_cast<const float2 *>(&p.part_ml[((size_t)h * S + s2) * 2]));
                 if (ml.y > 0.f) {
-                    const float wgt = (float)exp((double)__fsub_rn(ml.x, M));
+                    const float wgt = expf(__fsub_rn(ml.x, M));
                     const float4 po = ldcg4(&p.part_o[((size_t)h * S + s2) * HD + d]);
                     Lsum = fmaf(ml.y, wgt, Lsum);
                     o.x = fmaf(po.x, wgt, o.x); o.y = fmaf(po.y, wgt, o.y); o.z = fmaf(po.z, wgt, o.z); o.w = fmaf(po.w, wgt, o.w);
