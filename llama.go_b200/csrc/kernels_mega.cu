@@ -55,15 +55,21 @@ struct MegaShared {
     float bcast;
     float hbcast[2];
     unsigned ticket[2];
+    unsigned ticket_slot[2];                // dynamic row-block tickets of the current GEMV phase
     float pv[MG_THREADS];
     double rope_cs[64][2];  // cos,sin(past * 10000^(-2j/hd)) for this token, j < hd/2 (once per launch)
 };
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr) {
     target += nctas;
     csync();
     if (threadIdx.x == 0) {
+        if (arrive) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            arrive[blockIdx.x] = t;
+        }
         __threadfence();
         atomicAdd(bar, 1u);
         const long long t0 = clock64();
@@ -148,77 +154,30 @@ __device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&
 
 // rows per load batch of a phase with V float4 per lane and NM matrices
 __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
-// rows of the batch that is preloaded across a barrier (half a batch: it must stay in registers, unspilled)
-__host__ __device__ constexpr int mg_rbp(int V, int NM) { return mg_rb(V, NM) >= 2 ? mg_rb(V, NM) / 2 : 1; }
-
-// Load the FIRST batch of a phase's weights into registers.  Called BEFORE the grid barrier that
-// precedes the phase: weights are read-only, so these requests stream from HBM while the barrier
-// settles (the same trick as the prefetch-before-griddepcontrol.wait of the per-op kernels).
-template <int V, bool SWIGLU>
-__device__ __forceinline__ void gemv_preload(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
-                                             float4 (&a)[mg_rbp(V, SWIGLU ? 2 : 1)][SWIGLU ? 2 : 1][V]) {
-    constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int RB = mg_rbp(V, NM);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t KS = K / MG_WARPS;
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
-    const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - r0);
-    const float *w1 = W + (size_t)warp * KS + lane * 4;
-    const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
-#pragma unroll
-    for (int i = 0; i < RB; i++) {
-        const bool rok = (uint32_t)i < nrb;
-        const size_t off = (size_t)(r0 + i) * K;
-#pragma unroll
-        for (int j = 0; j < V; j++) {
-            const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
-            a[i][0][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-}
+constexpr int MG_DYN_ROWS = 4;  // rows per dynamically scheduled block
 
 // One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
-// `pre` arrives holding the first mg_rbp rows of the CTA's first row block (gemv_preload).
+// Scheduling: ~80 % of the rows are assigned statically (CTA c owns a contiguous block, processed
+// 32 rows per shared-memory combine); the rest is a pool handed out 4 rows at a time through an
+// atomic ticket (`ctr`, zeroed per launch), so SMs that stream faster take more rows and all CTAs
+// reach the next grid barrier within one small block of each other (measured skew with a purely
+// static split: 3-4 us per phase).  The next ticket is fetched while the current block streams.
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
-                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh,
-                                           float4 (&pre)[mg_rbp(V, SWIGLU ? 2 : 1)][SWIGLU ? 2 : 1][V]) {
+                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr) {
     constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int RB = mg_rb(V, NM), RBP = mg_rbp(V, NM);
+    constexpr int RB = mg_rb(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KS = K / MG_WARPS;
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
-    // dot products of `count` rows held in registers -> per-warp partials in shared memory
-    auto reduce_rows = [&](auto &a, int count, uint32_t r, uint32_t nrb, int buf) {
-#pragma unroll
-        for (int i = 0; i < count; i++) {
-#pragma unroll
-            for (int mtx = 0; mtx < NM; mtx++) {
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < V; j++) {
-                    acc = fmaf(a[i][mtx][j].x, xs[j].x, acc); acc = fmaf(a[i][mtx][j].y, xs[j].y, acc);
-                    acc = fmaf(a[i][mtx][j].z, xs[j].z, acc); acc = fmaf(a[i][mtx][j].w, xs[j].w, acc);
-                }
-                acc = warp_sum(acc);
-                if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
-            }
-        }
-    };
+    const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;  // static rows per CTA
+    const uint32_t pool0 = Q * gridDim.x;
+    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);  // latency hidden behind the static part
     int buf = 0;
-    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK, buf ^= 1) {
-        const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
-        uint32_t r = 0;
-        if (rb == r0) {  // the first rows were loaded before the barrier
-            reduce_rows(pre, RBP, 0, nrb, buf);
-            r = RBP;
-        }
-        for (; r < nrb; r += RB) {
+    // rows [rb, rb+nrb) -> partials -> combine -> out
+    auto do_block = [&](uint32_t rb, uint32_t nrb) {
+        for (uint32_t r = 0; r < nrb; r += RB) {
             float4 a[RB][NM][V];
 #pragma unroll
             for (int i = 0; i < RB; i++) {
@@ -231,7 +190,20 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
                     if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            reduce_rows(a, RB, r, nrb, buf);
+#pragma unroll
+            for (int i = 0; i < RB; i++) {
+#pragma unroll
+                for (int mtx = 0; mtx < NM; mtx++) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < V; j++) {
+                        acc = fmaf(a[i][mtx][j].x, xs[j].x, acc); acc = fmaf(a[i][mtx][j].y, xs[j].y, acc);
+                        acc = fmaf(a[i][mtx][j].z, xs[j].z, acc); acc = fmaf(a[i][mtx][j].w, xs[j].w, acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
+                }
+            }
         }
         csync();
         if (threadIdx.x < nrb) {
@@ -247,7 +219,21 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
             else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
             out[row] = v;
         }
-        // the other partial buffer is used by the next block; this one is reused only after the next csync
+        buf ^= 1;  // the other partial buffer is used next; this one is reused only after the next csync
+    };
+    // static part
+    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) do_block(rb, min((uint32_t)MG_ROWBLK, r1 - rb));
+    // dynamic pool
+    int slot = 0;
+    csync();  // ticket_slot[0] written by thread 0 is visible
+    uint32_t t = sh.ticket_slot[0];
+    while ((uint64_t)pool0 + (uint64_t)t * MG_DYN_ROWS < M) {
+        const uint32_t rb = pool0 + t * MG_DYN_ROWS;
+        if (threadIdx.x == 0) sh.ticket_slot[slot ^ 1] = atomicAdd(ctr, 1u);  // next ticket, overlapped with this block
+        do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
+        slot ^= 1;
+        t = sh.ticket_slot[slot];
     }
 }
 
@@ -431,6 +417,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
 
     unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    // profiling aid: arrival time of every CTA at each of layer 5's barriers
+    auto arr = [&](uint32_t li, int b) -> unsigned long long * {
+        return (p.trace && li == 5 && p.n_layers > 6) ? p.trace + (size_t)p.n_layers * 13 + (size_t)b * gridDim.x : nullptr;
+    };
     auto stamp = [&](uint32_t li, int i) {
         if (tr) {
             unsigned long long t;
@@ -445,10 +435,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         sh.rope_cs[threadIdx.x][0] = cs;
         sh.rope_cs[threadIdx.x][1] = sn;
     }
-    // register arrays holding the first weight batch of the upcoming phase (loaded before its barrier)
-    float4 a_d[mg_rbp(VD, 1)][1][VD];   // phases with K = dim, one matrix (wqkv, wo, lm_head)
-    gemv_preload<VD, false>(p.n_layers ? p.layers[0].wqkv : p.output, nullptr, p.n_layers ? 3 * dim : p.vocab, dim, a_d);
     csync();
+    unsigned *sched = p.barrier + 1;  // [n_layers * 4 + 1] ticket counters, zeroed with the barrier
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
         stamp(li, 0);
@@ -456,54 +444,47 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             stamp(li, 1);
-            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, a_d);
+            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
         }
         stamp(li, 2);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0));
         stamp(li, 3);
         // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
-        gemv_preload<VD, false>(L.wo, nullptr, dim, dim, a_d);
         stamp(li, 4);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 1));
         stamp(li, 5);
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs);
-            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, a_d);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
         }
         stamp(li, 6);
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2));
+        stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
-            float4 a_s[mg_rbp(VD, 2)][2][VD];
-            gemv_preload<VD, true>(L.w1, L.w3, ff, dim, a_s);
-            grid_barrier(p.barrier, target, gridDim.x);
-            stamp(li, 7);
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             stamp(li, 8);
-            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, a_s);
+            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
         }
         stamp(li, 9);
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3));
+        stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
-            float4 a_f[mg_rbp(VF, 1)][1][VF];
-            gemv_preload<VF, false>(L.w2, nullptr, dim, ff, a_f);
-            grid_barrier(p.barrier, target, gridDim.x);
-            stamp(li, 10);
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
-            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, a_f);
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
         }
         stamp(li, 11);
-        if (li + 1 < p.n_layers) gemv_preload<VD, false>(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, a_d);
-        else if (p.output) gemv_preload<VD, false>(p.output, nullptr, p.vocab, dim, a_d);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
         stamp(li, 12);
         xin = p.x;
     }
     if (p.output) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
         float4 xs[VD];
         rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
-        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, a_d);
+        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4);
     }
 }
 
@@ -564,7 +545,7 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     static const unsigned long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoul(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 0;
     p.prefetch_bytes = (uint32_t)(window_kb * 1024ul);  // measured: 0 (off) is best; kept as a tunable
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
-    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned), st));
+    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
     else if (vd == 2 && vf == 6) e = launch_hd<2, 6>(p, hd, smem, st);

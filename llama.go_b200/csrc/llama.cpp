@@ -233,11 +233,11 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
         }
         LB_CUDA(cudaMalloc(&mega_layers_dev, nl * sizeof(k::MegaLayerHost)));
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
-        LB_CUDA(cudaMalloc(&mega_barrier, 64));
-        LB_CUDA(cudaMemset(mega_barrier, 0, 64));
+        LB_CUDA(cudaMalloc(&mega_barrier, (2 + 4 * nl) * sizeof(unsigned)));  // grid barrier + per-phase ticket counters
+        LB_CUDA(cudaMemset(mega_barrier, 0, (2 + 4 * nl) * sizeof(unsigned)));
         if (getenv("LB_MEGA_TRACE")) {
-            LB_CUDA(cudaMalloc(&mega_trace, nl * 13 * sizeof(unsigned long long)));
-            LB_CUDA(cudaMemset(mega_trace, 0, nl * 13 * sizeof(unsigned long long)));
+            LB_CUDA(cudaMalloc(&mega_trace, (nl * 13 + 5 * 148) * sizeof(unsigned long long)));
+            LB_CUDA(cudaMemset(mega_trace, 0, (nl * 13 + 5 * 148) * sizeof(unsigned long long)));
         }
     }
 }

@@ -16,10 +16,12 @@ c = llama.NewContext(m, 512)
 llama.Eval(c, [5, 6, 7, 8, 9, 10, 11, 12, 13], 0)
 for i in range(4):
     llama.Eval(c, [7 + i], a.past + i)
-n = a.layers * 13
+n = a.layers * 13 + 5 * 148
 buf = (C.c_uint64 * n)()
 _capi.check(_capi.lib().lb_context_mega_trace(c._h, buf, n))
-t = np.array(buf[:], dtype=np.int64).reshape(a.layers, 13)
+allv = np.array(buf[:], dtype=np.int64)
+t = allv[:a.layers * 13].reshape(a.layers, 13)
+arr = allv[a.layers * 13:].reshape(5, 148)
 d = np.diff(t, axis=1)[1:-1]          # skip first/last layer
 names = ["rms1", "gemv qkv", "barrier1", "attention", "barrier2", "gemv wo", "barrier3", "rms2", "gemv w1w3", "barrier4", "gemv w2", "barrier5"]
 ideal = {"gemv qkv": 201.4e6, "gemv wo": 67.2e6, "gemv w1w3": 360.8e6, "gemv w2": 180.4e6}
@@ -28,3 +30,8 @@ for i, nme in enumerate(names):
     extra = f"   ideal {ideal[nme] / 7.0e12 * 1e6:6.1f}" if nme in ideal else ""
     print(f"{nme:14s} {d[:, i].mean() / 1e3:8.2f} {d[:, i].min() / 1e3:8.2f} {d[:, i].max() / 1e3:8.2f}{extra}")
 print(f"layer total    {np.diff(t[:, [0, 12]], axis=1)[1:-1].mean() / 1e3:8.2f} us")
+
+print("arrival spread of the 148 CTAs at layer 5's barriers (us after the first arrival): p50 / p90 / max")
+for b, nme in enumerate(["after qkv", "after attention", "after wo", "after w1w3", "after w2"]):
+    x = (arr[b] - arr[b].min()) / 1e3
+    print(f"  barrier {b + 1} ({nme:15s}): {np.percentile(x, 50):6.2f} {np.percentile(x, 90):6.2f} {x.max():6.2f}   slowest CTAs: {np.argsort(-x)[:6].tolist()}")
