@@ -268,6 +268,7 @@ def run_single_gpu(args):
     bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
     step_gbs = bytes_per_token * value / 1e9
 
+    mega = (not q8) and os.environ.get("LB_NO_MEGA") is None
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -285,17 +286,25 @@ def run_single_gpu(args):
                                % ("Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
                    "weights": "random-init (device RNG, seed 0) %.1f GB" % (model.weight_bytes_per_token / 1e9), "kv_cache": "fp32 in HBM",
                    "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (26.4 GB weights per step)",
+                   "decode_path": "persistent cooperative megakernel, CUDA-graph replay" if mega else "per-op kernels + PDL, CUDA-graph replay",
                    "setup_s": round(t_setup, 1)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 + 8, "d2h_bytes_per_step": 4 * hp.vocab,
                 "api": "lb_eval (C-ABI, host buffers, synchronous)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "gemv_swiglu_kernel (w1,w3)", "achieved": dom["GB/s"], "peak": peak,
-                     "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4), "traffic": kernel_traffic("gemv_swiglu_kernel"),
-                     "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]},
+        "roofline": ({"bound": "hbm", "kernel": "decode_mega_kernel (whole token: 32 layers + lm_head in one persistent launch)",
+                      "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbs / peak, 4),
+                      "traffic": kernel_traffic("decode_mega_kernel"), "peak_source": peak_src,
+                      "bytes_per_launch": int(bytes_per_token), "us_per_launch": round(ms / K * 1e3, 1),
+                      "note": "algorithmic bytes of one token (SURVEY 8d: weights + KV read/write + logits) / CUDA-event time per graph replay "
+                              "(memset + megakernel + 1-thread state advance)"}
+                     if mega else
+                     {"bound": "hbm", "kernel": "gemv_swiglu_kernel (w1,w3)", "achieved": dom["GB/s"], "peak": peak,
+                      "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4), "traffic": kernel_traffic("gemv_swiglu_kernel"),
+                      "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]}),
         "step_roofline": {"bytes_per_token": int(bytes_per_token), "achieved_GBs": round(step_gbs, 1),
                           "frac": round(step_gbs / peak, 4), "roofline_tok_s": round(peak * 1e9 / bytes_per_token, 1)},
-        "kernels": kern,
+        "per_op_kernels": kern,
         "prefill_gemm": prefill_gemm,
         "cpu_baseline": cpu,
     }
