@@ -154,11 +154,11 @@ __device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&
 
 // rows per load batch of a phase with V float4 per lane and NM matrices
 __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
-constexpr uint32_t MG_DYN_BYTES = 64 * 1024;  // target size of a dynamically scheduled row block (~1.4 us of one SM's share)
+constexpr int MG_DYN_ROWS = 4;  // rows per dynamically scheduled block
 
 // One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
-// Scheduling: 85 % of the rows are assigned statically (CTA c owns a contiguous block, processed
-// 32 rows per shared-memory combine); the rest is a pool handed out in ~64 KB row blocks through an
+// Scheduling: ~80 % of the rows are assigned statically (CTA c owns a contiguous block, processed
+// 32 rows per shared-memory combine); the rest is a pool handed out 4 rows at a time through an
 // atomic ticket (`ctr`, zeroed per launch), so SMs that stream faster take more rows and all CTAs
 // reach the next grid barrier within one small block of each other (measured skew with a purely
 // static split: 3-4 us per phase).  The next ticket is fetched while the current block streams.
@@ -171,9 +171,7 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
     const uint32_t KS = K / MG_WARPS;
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
-    uint32_t DR = MG_DYN_BYTES / (K * 4 * NM);  // rows per dynamic block
-    DR = DR < 1 ? 1 : (DR > MG_ROWBLK ? MG_ROWBLK : DR);
-    const uint32_t Q = (uint32_t)(((uint64_t)M * 17) / (20 * gridDim.x));  // 85 % of the rows are static
+    const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;  // static rows per CTA
     const uint32_t pool0 = Q * gridDim.x;
     if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);  // latency hidden behind the static part
     int buf = 0;
@@ -230,10 +228,10 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
     int slot = 0;
     csync();  // ticket_slot[0] written by thread 0 is visible
     uint32_t t = sh.ticket_slot[0];
-    while ((uint64_t)pool0 + (uint64_t)t * DR < M) {
-        const uint32_t rb = pool0 + t * DR;
+    while ((uint64_t)pool0 + (uint64_t)t * MG_DYN_ROWS < M) {
+        const uint32_t rb = pool0 + t * MG_DYN_ROWS;
         if (threadIdx.x == 0) sh.ticket_slot[slot ^ 1] = atomicAdd(ctr, 1u);  // next ticket, overlapped with this block
-        do_block(rb, min(DR, M - rb));  // contains a csync after the loads: the slot write is visible after it
+        do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
         slot ^= 1;
         t = sh.ticket_slot[slot];
     }
