@@ -31,6 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "LLaMA-7B FP32 decode tokens/sec"
+MODELS = {"7b": "LLAMA_7B", "13b": "LLAMA_13B", "30b": "LLAMA_30B", "65b": "LLAMA_65B"}
+
+
+def metric_name(model):
+    return METRIC.replace("7B", model.upper())
 UNIT = "tokens/s"
 PROMPT_LEN = 384
 CTX = 512
@@ -208,10 +213,10 @@ def run_single_gpu(args):
     from llama_go_b200 import _capi, llama, synth
     _capi.require_gpu()
     lib = _capi.lib()
-    hp = synth.LLAMA_7B
+    hp = getattr(synth, MODELS[args.model])
     K, W = args.steps, args.warmup
     q8 = args.weights == "q8"
-    ctx_size = max(1024 if q8 else CTX, PROMPT_LEN + 2 * W + K + 1)   # config 3 (Q8) is quoted at context 1024
+    ctx_size = max(args.context or (1024 if q8 else CTX), PROMPT_LEN + 2 * W + K + 1)   # config 3 (Q8) is quoted at context 1024
     t_setup = time.time()
     model = llama.Model(hp, weight_type=llama.LB_TYPE_Q8_0 if q8 else llama.LB_TYPE_F32).init_random(0)
     lctx = llama.NewContext(model, ctx_size)
@@ -278,12 +283,12 @@ def run_single_gpu(args):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
     line = {
-        "metric": METRIC if not q8 else "LLaMA-7B INT8 block-quant (Q8_0) decode tokens/sec", "value": value, "unit": UNIT,
+        "metric": metric_name(args.model) if not q8 else "LLaMA-%s INT8 block-quant (Q8_0) decode tokens/sec" % args.model.upper(), "value": value, "unit": UNIT,
         "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if not q8 else "q8_0 weights x f32 activations", "data": "synthetic",
-        "config": {"workload": "LLaMA-7B %s single-sequence decode, context %d, %d-token prompt prefilled, past %d..%d"
-                               % ("Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
+        "config": {"workload": "LLaMA-%s %s single-sequence decode, context %d, %d-token prompt prefilled, past %d..%d"
+                               % (args.model.upper(), "Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
                    "weights": "random-init (device RNG, seed 0) %.1f GB" % (model.weight_bytes_per_token / 1e9), "kv_cache": "fp32 in HBM",
                    "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (26.4 GB weights per step)",
                    "decode_path": "persistent cooperative megakernel, CUDA-graph replay" if mega else "per-op kernels + PDL, CUDA-graph replay",
@@ -319,6 +324,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weights", default="f32", choices=["f32", "q8"], help="q8 = BASELINE config 3 (not the headline metric)")
+    ap.add_argument("--model", default="7b", choices=sorted(MODELS), help="default 7b = the headline metric; 13b/65b = BASELINE configs 4-5")
+    ap.add_argument("--context", type=int, default=0, help="override the context size (BASELINE config 5 uses 2048)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

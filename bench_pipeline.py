@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-from bench import CTX, METRIC, PROMPT_LEN, UNIT, ClockSampler, measured_peak, rank_world
+from bench import CTX, MODELS, PROMPT_LEN, UNIT, ClockSampler, measured_peak, metric_name, rank_world
 
 
 def run_pipeline(args):
@@ -28,10 +28,10 @@ def run_pipeline(args):
     uid = pipeline.exchange_unique_id(rank, dist)
     _capi.check(lib.lb_comm_init(uid, rank, world, local))
 
-    hp = synth.LLAMA_7B
+    hp = getattr(synth, MODELS[args.model])
     K, W = args.steps, args.warmup
     S = world                                   # sequences in flight
-    ctx_size = max(CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
+    ctx_size = max(args.context or CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
     t_setup = time.time()
     stage = pipeline.Stage(hp, rank, world, local, ctx_size, S, seed=0)
     rs = np.random.RandomState(0)
@@ -85,14 +85,15 @@ def run_pipeline(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         T_mid = PROMPT_LEN + W + K / 2.0
-        bytes_per_token = 26429390848 + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+        wbytes = 4 * (hp.layers * (4 * hp.dim ** 2 + 3 * hp.dim * hp.ff + 2 * hp.dim) + hp.vocab * hp.dim + 2 * hp.dim)
+        bytes_per_token = wbytes + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
         agg_gbs = bytes_per_token * value / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(args.model), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LLaMA-7B FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
-                                   % (ctx_size, PROMPT_LEN, S),
+            "config": {"workload": "LLaMA-%s FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
+                                   % (args.model.upper(), ctx_size, PROMPT_LEN, S),
                        "parallelism": "pp%d (layer-sharded, %d layers/GPU, NCCL send/recv of the residual)" % (world, hp.layers // world),
                        "sequences_in_flight": S, "tokens_per_step": S, "weights": "random-init (device RNG, seed 0)",
                        "kv_cache": "fp32 in HBM", "l2": "inputs>L2", "setup_s": round(t_setup, 1),

@@ -140,6 +140,24 @@ def test_7b_shaped_layers_against_live_oracle(L, synth, oracle):
     print(f"7B-shaped 2-layer: prefill rel err {e0:.3e}, last decode rel err {e:.3e}")
 
 
+@pytest.mark.parametrize("name,dims", [("13B", (32000, 5120, 256, 40, 1)), ("65B", (32000, 8192, 256, 64, 1))])
+def test_13b_65b_shaped_layer_against_live_oracle(L, synth, oracle, name, dims):
+    """Exact LLaMA-13B / 65B layer shapes (BASELINE configs 4-5), one layer + lm_head, against the oracle:
+    a 9-token prompt (tensor-core GEMM path) and two decode steps (megakernel variants (3,7) / (4,11))."""
+    hp = synth.HParams(*dims)
+    model = L.Model(hp).init_random(0)
+    lctx = L.NewContext(model, 32)
+    om = oracle.OracleModel(hp).load(synth.synth_model_fast(0, hp))
+    oc = oracle.OracleContext(om, 32)
+    ids = [1, 35, 35, 107, 104, 111, 31999, 0, 2024]
+    assert_logits_close(L.Eval(lctx, ids, 0).copy(), oc.eval(ids, 0), what=f"{name}-shape prefill")
+    past = len(ids)
+    for tok in (17, 30000):
+        e = assert_logits_close(L.Eval(lctx, [tok], past).copy(), oc.eval([tok], past), what=f"{name}-shape decode")
+        past += 1
+    print(f"{name}-shaped layer: decode rel err {e:.3e}")
+
+
 def test_full_7b_properties(L, synth):
     """Full LLaMA-7B FP32 (26.9 GB of synthetic weights generated on the device).  The oracle cannot
     run this size in test time, so check size-independent properties:
