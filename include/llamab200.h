@@ -96,6 +96,11 @@ LB_API int lb_eval_graph(lb_context *c, const uint32_t *tokens, uint32_t n, uint
  * tokens (teacher forcing), no host copies; used by bench.py for the kernel-only number.
  * ms_out (optional) = CUDA-event time of the whole batch of steps on the context's stream. */
 LB_API int lb_decode_resident(lb_context *c, const uint32_t *tokens, uint32_t steps, uint32_t past, float *ms_out);
+/* The generate loop of pkg/server.Do at temp -> 0 (server.go:153-237) with the sampler on the device
+ * (SURVEY §8f-2): prompt eval, then `predict` x [repetition-penalised argmax (llama.go:500-527) ->
+ * single-token eval], no host round trip per token.  out_tokens receives the `predict` generated ids. */
+LB_API int lb_generate_greedy(lb_context *c, const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp,
+                              float repeat_penalty, uint32_t *out_tokens);
 LB_API int lb_context_read_logits(lb_context *c, float *logits_out);              /* last eval's row */
 LB_API int lb_context_read_kv(lb_context *c, uint32_t layer, uint32_t t0, uint32_t nt, float *k_out, float *v_out);
 LB_API int lb_context_read_hidden(lb_context *c, uint32_t n, float *hidden_out);  /* residual stream before final norm */

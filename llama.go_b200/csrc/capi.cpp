@@ -125,6 +125,10 @@ int lb_eval_graph(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t pa
 int lb_decode_resident(lb_context *c, const uint32_t *tokens, uint32_t steps, uint32_t past, float *ms_out) {
     LB_TRY_INT(LB_CHECK(c && tokens, "nil argument"); float ms = c->c->decode_resident(tokens, steps, past); if (ms_out) *ms_out = ms);
 }
+int lb_generate_greedy(lb_context *c, const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp, float repeat_penalty,
+                       uint32_t *out_tokens) {
+    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->generate_greedy(prompt, n_prompt, predict, temp, repeat_penalty, out_tokens));
+}
 int lb_context_read_logits(lb_context *c, float *out) {
     LB_TRY_INT(LB_CHECK(c && out, "nil argument"); LB_CHECK(c->c->model->has_head(), "this stage has no lm_head");
                LB_CUDA(cudaSetDevice(c->c->model->device));

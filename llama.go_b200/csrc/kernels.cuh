@@ -74,6 +74,9 @@ size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd);
 // single-token embedding gather for graph replay: row = table[tokens[*step_dev + n]]
 void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, const uint32_t *step_dev,
                        uint32_t nr, float *dst, cudaStream_t st);
+// greedy (temp -> 0) sampling with the reference's repetition penalty, on the device (kernels_elementwise.cu)
+void sample_greedy(const float *logits, uint32_t V, float scale, float penalty, uint32_t *present, uint32_t *ring,
+                   uint32_t ring_size, uint32_t *ring_pos, uint32_t *tokens, const uint32_t *state, cudaStream_t st);
 // state[0] (= past) += dp; state[1] (= step) += ds
 void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
 

@@ -365,6 +365,51 @@ void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st) {
     launch_pdl(advance_state_kernel, dim3(1), dim3(1), 0, st, state, dp, ds);
 }
 
+// ---- greedy sampler on the device: the reference's SampleTopPTopK at temp -> 0
+// (pkg/llama/llama.go:455-707) degenerates to argmax of the repetition-penalised logits: every id present
+// in the last-`ring_size` ring gets  l < 0 ? l*scale*penalty : l*scale/penalty  (FP32, in that order,
+// llama.go:515-522; scale = float32(1/temp)).  One CTA: penalise + argmax (lowest index on ties), append the
+// token to tokens[*step] for the next decode step and update the ring and its per-id presence counts.
+__global__ void __launch_bounds__(1024) sample_greedy_kernel(const float *__restrict__ logits, uint32_t V, float scale,
+                                                             float penalty, uint32_t *__restrict__ present,
+                                                             uint32_t *__restrict__ ring, uint32_t ring_size,
+                                                             uint32_t *__restrict__ ring_pos, uint32_t *__restrict__ tokens,
+                                                             const uint32_t *__restrict__ state) {
+    __shared__ float bv[32];
+    __shared__ uint32_t bi[32];
+    pdl_wait();
+    float best = -INFINITY;
+    uint32_t best_i = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < V; i += blockDim.x) {
+        float l = __fmul_rn(logits[i], scale);
+        if (present[i]) l = logits[i] < 0.0f ? __fmul_rn(l, penalty) : __fdiv_rn(l, penalty);
+        if (l > best || (l == best && i < best_i)) { best = l; best_i = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        uint32_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = best_i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+            if (bv[w] > best || (bv[w] == best && bi[w] < best_i)) { best = bv[w]; best_i = bi[w]; }
+        tokens[state[1]] = best_i;                 // consumed by the next single-token eval
+        const uint32_t pos = *ring_pos;
+        const uint32_t evict = ring[pos];
+        if (present[evict]) present[evict]--;
+        ring[pos] = best_i;
+        present[best_i]++;
+        *ring_pos = (pos + 1) % ring_size;
+    }
+}
+void sample_greedy(const float *logits, uint32_t V, float scale, float penalty, uint32_t *present, uint32_t *ring,
+                   uint32_t ring_size, uint32_t *ring_pos, uint32_t *tokens, const uint32_t *state, cudaStream_t st) {
+    launch_pdl(sample_greedy_kernel, dim3(1), dim3(1024), 0, st, logits, V, scale, penalty, present, ring, ring_size, ring_pos, tokens, state);
+}
+
 // ---- synthetic weights: same integer recipe as llama.go_b200/synth.py (bit-identical)
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;

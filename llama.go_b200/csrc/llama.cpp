@@ -254,6 +254,9 @@ Context::~Context() {
     if (mega_trace) cudaFree(mega_trace);
     if (tokens_dev) cudaFree(tokens_dev);
     if (state_dev) cudaFree(state_dev);
+    if (ring_dev) cudaFree(ring_dev);
+    if (present_dev) cudaFree(present_dev);
+    if (ring_pos_dev) cudaFree(ring_pos_dev);
     if (state_host) cudaFreeHost(state_host);
     if (tokens_host) cudaFreeHost(tokens_host);
     if (logits_host) cudaFreeHost(logits_host);
@@ -492,6 +495,55 @@ float Context::decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t 
     LB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_n = 1;
     return ms;
+}
+
+void Context::generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp, float repeat_penalty,
+                              uint32_t *out_tokens) {
+    const HParams &hp = model->hp;
+    LB_CHECK(model->has_embedding() && model->has_head(), "generate_greedy : needs a single-stage model");
+    LB_CHECK(prompt && out_tokens && n_prompt >= 1 && predict >= 1, "generate_greedy : bad arguments");
+    LB_CHECK((uint64_t)n_prompt + predict - 1 <= ctx_size, "generate_greedy : prompt + predict exceeds the context (context swapping is host policy, server.go:165-172)");
+    LB_CHECK(predict <= tokens_cap, "generate_greedy : predict too large");
+    LB_CHECK(temp > 0.f, "generate_greedy : temp must be > 0 (the reference replaces 0 by 0.5, main.go:379-381)");
+    LB_CUDA(cudaSetDevice(model->device));
+    if (!ring_dev) {
+        LB_CUDA(cudaMalloc(&ring_dev, ctx_size * sizeof(uint32_t)));
+        LB_CUDA(cudaMalloc(&present_dev, hp.vocab * sizeof(uint32_t)));
+        LB_CUDA(cudaMalloc(&ring_pos_dev, sizeof(uint32_t)));
+    }
+    // ring of the last ctx_size ids: zeros, then the prompt (server.go:127-138, 190)
+    std::vector<uint32_t> ring(ctx_size, 0u), present(hp.vocab, 0u);
+    uint32_t pos = 0;
+    for (uint32_t i = 0; i < n_prompt; i++) { ring[pos] = prompt[i]; pos = (pos + 1) % ctx_size; }
+    for (uint32_t v : ring) present[v]++;
+    LB_CUDA(cudaMemcpyAsync(ring_dev, ring.data(), ctx_size * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    LB_CUDA(cudaMemcpyAsync(present_dev, present.data(), hp.vocab * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    LB_CUDA(cudaMemcpyAsync(ring_pos_dev, &pos, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+    eval(prompt, n_prompt, 0, nullptr, false);                         // prompt eval -> logits on the device
+    if (!decode_graph) {                                               // make sure the decode graph exists
+        const uint32_t t0 = prompt[n_prompt - 1];
+        LB_CHECK((uint64_t)n_prompt < ctx_size || predict == 1, "generate_greedy : no room to warm up");
+        if (predict > 1) {
+            eval(&t0, 1, n_prompt, nullptr, false);                    // eager + capture (overwrites logits, KV slot n_prompt)
+            eval(prompt, n_prompt, 0, nullptr, false);                 // restore prompt logits
+        }
+    }
+    state_host[0] = n_prompt; state_host[1] = 0;
+    LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    const float scale = 1.0f / temp;                                   // float32(1.0 / temp), llama.go:500
+    for (uint32_t i = 0; i < predict; i++) {
+        k::sample_greedy(logits, hp.vocab, scale, repeat_penalty, present_dev, ring_dev, ctx_size, ring_pos_dev, tokens_dev, state_dev, stream);
+        if (i + 1 < predict) {                                         // the last sampled token is never evaluated (server.go:153-237)
+            LB_CUDA(cudaGraphLaunch(decode_graph, stream));
+            count_launch(use_mega ? 2 : model->layers.size() * 8 + 4);
+        } else {
+            k::advance_state(state_dev, 0, 1, stream);
+        }
+    }
+    LB_CUDA(cudaMemcpyAsync(tokens_host, tokens_dev, predict * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out_tokens, tokens_host, predict * sizeof(uint32_t));
 }
 
 float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch) {

@@ -82,6 +82,7 @@ struct Context {
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
     uint32_t tokens_cap = 0;
+    uint32_t *ring_dev = nullptr, *present_dev = nullptr, *ring_pos_dev = nullptr;  // sampler state (last-N ring)
     uint32_t *state_dev = nullptr;   // {past, step}
     uint32_t *state_host = nullptr;  // pinned {past, step}
     uint32_t *tokens_host = nullptr; // pinned staging
@@ -101,6 +102,10 @@ struct Context {
     // llama.Eval built node for node with the ml:: op API (slow path)
     void eval_graph(const uint32_t *tokens, uint32_t n, uint32_t past, float *logits_out);
     float decode_resident(const uint32_t *tokens, uint32_t steps, uint32_t past);
+    // server.Do's generate loop at temp -> 0 (server.go:110-237) fully on the device: prompt eval, then
+    // `predict` x (penalised argmax -> single-token eval); returns the generated ids
+    void generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp, float repeat_penalty,
+                         uint32_t *out_tokens);
     float bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch);
     // capture (once) the single-token forward of this stage's layers on stream `st`:
     // [embedding gather on stage 0] -> layers -> [norm + lm_head on the last stage] -> advance {past, step}

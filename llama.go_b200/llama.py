@@ -148,6 +148,14 @@ def DecodeResident(lctx: Context, tokens, pastCount: int) -> float:
     return ms.value
 
 
+def GenerateGreedy(lctx: Context, prompt_ids, predict: int, temp: float = 1e-6, repeat_penalty: float = 1.10):
+    """pkg/server.Do's generate loop at temp -> 0 with the sampler on the device; returns the generated ids."""
+    t, p = _toks(prompt_ids)
+    out = np.zeros(predict, np.uint32)
+    check(lib().lb_generate_greedy(lctx._h, p, t.size, predict, temp, repeat_penalty, out.ctypes.data_as(_u32p)))
+    return out.tolist()
+
+
 def ReadLogits(lctx: Context) -> np.ndarray:
     check(lib().lb_context_read_logits(lctx._h, lctx.Logits.ctypes.data_as(_f32p)))
     return lctx.Logits
