@@ -223,13 +223,14 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     LB_CUDA(cudaEventCreate(&ev1));
     use_graph = getenv("LB_NO_GRAPH") == nullptr;  // profiling aid: plain launches instead of graph replay
     // persistent megakernel for N == 1 (FP32 weights, supported shapes); LB_NO_MEGA=1 keeps the per-op kernels
-    use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
+    use_mega = getenv("LB_NO_MEGA") == nullptr && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
     if (use_mega) {
         std::vector<k::MegaLayerHost> ml(nl);
         for (size_t i = 0; i < nl; i++) {
             const Layer &L = m->layers[i];
             ml[i] = {L.attention_norm, L.wqkv, L.wo, L.ffn_norm, L.w1, L.w3, L.w2,
-                     kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d};
+                     kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d,
+                     L.wqkv8.q, L.wo8.q, L.w18.q, L.w38.q, L.w28.q, L.wqkv8.d, L.wo8.d, L.w18.d, L.w38.d, L.w28.d};
         }
         LB_CUDA(cudaMalloc(&mega_layers_dev, nl * sizeof(k::MegaLayerHost)));
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
@@ -304,6 +305,9 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.tokens = tokens_dev; mp.state = state_dev;
         mp.final_norm = model->has_head() ? model->norm : nullptr;
         mp.output = model->has_head() ? model->output : nullptr;
+        mp.q_output = model->has_head() ? model->output8.q : nullptr;
+        mp.d_output = model->has_head() ? model->output8.d : nullptr;
+        mp.q8 = model->q8();
         mp.x = x; mp.y = y; mp.qkv = qkv; mp.attn = attn; mp.act = act; mp.logits = logits;
         const uint32_t hd = hp.head_dim();
         mp.part_o = attn_scratch;
