@@ -223,14 +223,7 @@ int lb_tensor_shape(const lb_tensor *t, uint32_t ne[4], uint32_t nb[4]) {
     LB_TRY_INT(LB_CHECK(t, "nil tensor"); for (int i = 0; i < 4; i++) { if (ne) ne[i] = T(t)->ne[i]; if (nb) nb[i] = T(t)->nb[i]; });
 }
 
-#define LB_OP1(name, fn) \
-    lb_tensor *name(lb_mlctx *c, lb_tensor *a) { LB_TRY_PTR(lb_tensor *, (LB_CHECK(c && a, "nil argument"), W(fn(c->c, T(a))))); }
-#define LB_OP2(name, fn) \
-    lb_tensor *name(lb_mlctx *c, lb_tensor *a, lb_tensor *b) { LB_TRY_PTR(lb_tensor *, (LB_CHECK(c && a && b, "nil argument"), W(fn(c->c, T(a), T(b))))); }
-
 static inline void chk(bool ok, const char *msg) { if (!ok) throw Error(std::string("[HALT] ") + msg); }
-#undef LB_OP1
-#undef LB_OP2
 #define LB_OP1(name, fn) \
     lb_tensor *name(lb_mlctx *c, lb_tensor *a) { try { chk(c && a, "nil argument"); return W(fn(c->c, T(a))); } catch (const std::exception &e) { g_err = e.what(); return nullptr; } }
 #define LB_OP2(name, fn) \

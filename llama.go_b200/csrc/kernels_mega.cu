@@ -14,11 +14,10 @@
 // lives in REGISTERS for the whole phase (no activation re-reads at all) and a weight row is read by
 // 16 warps x 512-byte coalesced requests.  Row partials are combined through shared memory in a fixed
 // order (deterministic).
-// Before a CTA stalls (grid barrier, attention phase, the redundant per-CTA rmsnorm) one warp queues
-// cp.async.bulk.prefetch.L2 requests for the first few hundred KB of the CTA's rows of the NEXT GEMV
-// phase(s): the memory system drains that queue at HBM speed while the SM waits, and the first loads
-// after the stall hit the 126 MB L2.  (A decoupled 17th "prefetch warp" with a progress window was
-// measured slower: 544 threads cap the kernel at 96 registers and the GEMV loop spills.)
+// Measured and rejected (profiles/README.md): cp.async.bulk.prefetch.L2 of the next phase's rows before a
+// barrier (no gain), a decoupled 17th prefetch warp with a progress window (544 threads cap the kernel at
+// 96 registers, the GEMV loop spills: 142 tok/s), loading the next phase's first weight batch into
+// registers across the barrier (no gain), 1-2-row dynamic blocks (too little in flight).
 // Numerics are those of the per-op kernels (see kernels_elementwise.cu / kernels_attn.cu); only the
 // association order of the FP32 dot-product sums differs.
 #include <cooperative_groups.h>
@@ -30,11 +29,11 @@
 namespace lb {
 namespace k {
 
-constexpr int MG_WARPS = 16;                 // consumer warps
-constexpr int MG_THREADS = MG_WARPS * 32;    // consumer threads (named barrier 1)
+constexpr int MG_WARPS = 16;
+constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
-// consumer-only barriers (the prefetch warp never participates)
+// CTA-wide and half-CTA named barriers
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_THREADS) : "memory"); }
 __device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(MG_HALF) : "memory"); }
 
@@ -44,9 +43,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 
 struct MegaShared {
     float part[2][2][MG_ROWBLK][MG_WARPS];  // [buffer][matrix (w1|w3)][row][warp]
@@ -54,7 +50,6 @@ struct MegaShared {
     float fred[2][MG_WARPS / 2];            // per attention half
     float bcast;
     float hbcast[2];
-    unsigned ticket[2];
     unsigned ticket_slot[2];                // dynamic row-block tickets of the current GEMV phase
     float pv[MG_THREADS];
     double rope_cs[64][2];  // cos,sin(past * 10000^(-2j/hd)) for this token, j < hd/2 (once per launch)
@@ -85,23 +80,6 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
 __device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
     r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
     r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
-}
-
-// Queue L2 prefetches for this CTA's rows [skip_bytes, skip_bytes + budget) (in bytes of its row range)
-// of a matrix a later phase will stream (pairs of w1/w3 rows when W3 is given).  Issued by the last warp.
-__device__ __forceinline__ void prefetch_rows(const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t skip_bytes,
-                                              uint32_t budget_bytes) {
-    if ((threadIdx.x >> 5) != MG_WARPS - 1) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
-    const uint32_t row_bytes = K * 4 * (W3 ? 2 : 1);
-    const uint32_t first = skip_bytes / row_bytes;
-    const uint32_t n = (budget_bytes + row_bytes - 1) / row_bytes;
-    for (uint32_t i = first + lane; i < first + n && r0 + i < r1; i += 32) {
-        prefetch_l2_bulk(W + (size_t)(r0 + i) * K, K * 4);
-        if (W3) prefetch_l2_bulk(W3 + (size_t)(r0 + i) * K, K * 4);
-    }
 }
 
 // y = x * f32(1/sqrt(mean_f64(x^2)+1e-5)) * w, only this warp's K-slice, into registers
@@ -352,7 +330,6 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     uint32_t layers_host_q8;  // 1: the layers carry Q8_0 planes (host-side dispatch flag)
-    uint32_t prefetch_bytes;  // bytes of the next phase's rows each CTA queues into L2 before a stall
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
 };
 
@@ -652,8 +629,6 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     const uint32_t hd = h.dim / h.heads;
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
-    static const unsigned long window_kb = getenv("LB_MEGA_WINDOW_KB") ? strtoul(getenv("LB_MEGA_WINDOW_KB"), nullptr, 10) : 0;
-    p.prefetch_bytes = (uint32_t)(window_kb * 1024ul);  // measured: 0 (off) is best; kept as a tunable
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
