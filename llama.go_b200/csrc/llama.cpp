@@ -223,7 +223,10 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     LB_CUDA(cudaEventCreate(&ev1));
     use_graph = getenv("LB_NO_GRAPH") == nullptr;  // profiling aid: plain launches instead of graph replay
     // persistent megakernel for N == 1 (FP32 weights, supported shapes); LB_NO_MEGA=1 keeps the per-op kernels
-    use_mega = getenv("LB_NO_MEGA") == nullptr && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
+    // (Q8_0 models: the megakernel's Q8 phases are implemented but measured slower than the per-op Q8
+    //  kernels — 173 vs 240 tok/s on 7B, too little in flight per warp — so they are opt-in: LB_Q8_MEGA=1)
+    use_mega = getenv("LB_NO_MEGA") == nullptr && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads) &&
+               (!m->q8() || getenv("LB_Q8_MEGA") != nullptr);
     if (use_mega) {
         std::vector<k::MegaLayerHost> ml(nl);
         for (size_t i = 0; i < nl; i++) {

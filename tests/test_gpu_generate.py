@@ -32,7 +32,7 @@ def test_generate_greedy_reproduces_reference_binary_stream(synth, case):
 def test_generate_greedy_argument_checks(synth):
     import llama_go_b200  # noqa: F401
     from llama_go_b200 import llama
-    hp = synth.HParams(64, 32, 32, 2, 1)
+    hp = synth.HParams(64, 64, 32, 2, 1)
     model = llama.Model(hp).load(synth.synth_model(1, hp))
     lctx = llama.NewContext(model, 16)
     with pytest.raises(llama.LlamaB200Error):
