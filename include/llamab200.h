@@ -60,6 +60,11 @@ LB_API uint64_t    lb_kernel_launches(void);       /* kernels launched by this l
 LB_API lb_model *lb_model_create(const lb_hparams *hp, int device, uint32_t layer_begin,
                                  uint32_t layer_end, int weight_type);
 LB_API void      lb_model_free(lb_model *m);
+/* LoadModel (llama.go:712-976): a ggjt v1 file (F32 or F16 tensors) streamed straight into HBM through
+ * pinned staging buffers; same magic/version/name/dtype checks as the reference.  layer_end = 0 means
+ * "all layers"; hp_out (optional) receives the file's hyper-parameters. */
+LB_API lb_model *lb_model_load_ggjt(const char *path, int device, uint32_t layer_begin, uint32_t layer_end,
+                                    int weight_type, lb_hparams *hp_out);
 /* name = ggjt tensor name (llama.go:826-861); dtype LB_TYPE_F32 or LB_TYPE_F16 (widened to FP32
  * like llama.go:938-941); tensors of layers this stage does not own are accepted and ignored. */
 LB_API int       lb_model_set_tensor(lb_model *m, const char *name, int dtype, const void *host, size_t nbytes);

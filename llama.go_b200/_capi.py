@@ -31,6 +31,7 @@ _SIGS = {
     "lb_kernel_launches": (C.c_uint64, []),
     "lb_model_create": (_vp, [C.POINTER(HParamsC), C.c_int, C.c_uint32, C.c_uint32, C.c_int]),
     "lb_model_free": (None, [_vp]),
+    "lb_model_load_ggjt": (_vp, [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(HParamsC)]),
     "lb_model_set_tensor": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, C.c_size_t]),
     "lb_model_get_tensor": (C.c_int, [_vp, C.c_char_p, _f32p, C.c_size_t]),
     "lb_model_init_random": (C.c_int, [_vp, C.c_uint64]),

@@ -87,6 +87,19 @@ lb_model *lb_model_create(const lb_hparams *hp, int device, uint32_t layer_begin
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 void lb_model_free(lb_model *m) { if (m) { delete m->m; delete m; } }
+lb_model *lb_model_load_ggjt(const char *path, int device, uint32_t layer_begin, uint32_t layer_end, int weight_type, lb_hparams *hp_out) {
+    try {
+        LB_CHECK(path != nullptr, "lb_model_load_ggjt: nil path");
+        require_device(device);
+        llama::LoadedModel lm = llama::load_ggjt(path, device, layer_begin, layer_end, weight_type);
+        if (hp_out) {
+            const llama::HParams &h = lm.model->hp;
+            hp_out->vocab = h.vocab; hp_out->dim = h.dim; hp_out->mult = h.mult; hp_out->heads = h.heads; hp_out->layers = h.layers;
+        }
+        auto *m = new lb_model{lm.model.release()};
+        return m;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
 int lb_model_set_tensor(lb_model *m, const char *name, int dtype, const void *host, size_t nbytes) {
     LB_TRY_INT(LB_CHECK(m && name && host, "lb_model_set_tensor: nil argument"); m->m->set_tensor(name, dtype, host, nbytes));
 }

@@ -128,6 +128,14 @@ float pipeline_decode(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tok
 void pipeline_prefill(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past);
 }  // namespace pipe
 namespace llama {
+// ggjt v1 file -> device model (loader.cpp); vocab strings/scores are returned for the tokenizer side
+struct LoadedModel {
+    std::unique_ptr<Model> model;
+    std::vector<std::string> vocab;
+    std::vector<float> scores;
+    uint32_t tensors_loaded = 0;
+};
+LoadedModel load_ggjt(const std::string &path, int device, uint32_t layer_begin, uint32_t layer_end_or_0, int weight_type);
 void synth_fill_host(float *dst, uint64_t count, uint64_t seed, uint64_t tid, uint64_t start, float mean, double sigma);
 
 }  // namespace llama

@@ -68,11 +68,16 @@ class Model:
             pass
 
 
-def LoadModel(fileName: str, device: int = 0):
-    """LoadModel (llama.go:712-976): ggjt v1 file -> (vocab, Model)."""
-    hp, vocab, tensors = synth.read_ggjt(fileName)
-    m = Model(hp, device)
-    m.load(tensors.items())
+def LoadModel(fileName: str, device: int = 0, weight_type: int = LB_TYPE_F32, layer_begin: int = 0, layer_end: int = 0):
+    """LoadModel (llama.go:712-976): ggjt v1 file -> Model, streamed into HBM by the native loader
+    (csrc/loader.cpp).  Returns (vocab, model) like the reference; the vocab is read on the host."""
+    _capi.require_gpu()
+    c = HParamsC()
+    h = check_ptr(lib().lb_model_load_ggjt(fileName.encode(), device, layer_begin, layer_end, weight_type, C.byref(c)))
+    hp = synth.HParams(c.vocab, c.dim, c.mult, c.heads, c.layers)
+    m = Model.__new__(Model)
+    m.hp, m.device, m.layer_begin, m.layer_end, m._h = hp, device, layer_begin, layer_end or hp.layers, h
+    vocab = synth.read_ggjt_vocab(fileName)
     return vocab, m
 
 

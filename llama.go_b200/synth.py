@@ -234,6 +234,21 @@ def write_ggjt(path: str, hp: HParams, tensors, vocab=None, f16: bool = False) -
             arr.astype("<f2" if use_f16 else "<f4").tofile(f)
 
 
+def read_ggjt_vocab(path: str):
+    """Only the vocab section of a ggjt v1 file: list of token byte strings."""
+    with open(path, "rb") as f:
+        magic, ver, V = struct.unpack("<3I", f.read(12))
+        if magic != GGJT_MAGIC or ver != GGJT_VERSION:
+            raise ValueError("not a ggjt v1 file")
+        f.read(24)
+        vocab = []
+        for _ in range(V):
+            (ln,) = struct.unpack("<I", f.read(4))
+            vocab.append(f.read(ln))
+            f.read(4)
+        return vocab
+
+
 def read_ggjt(path: str):
     """Minimal reader (host-side loader for tests): returns (HParams, vocab, {name: ndarray})."""
     with open(path, "rb") as f:
