@@ -48,7 +48,7 @@ struct Reader {
 LoadedModel load_ggjt(const std::string &path, int device, uint32_t layer_begin, uint32_t layer_end_or_0, int weight_type) {
     Mapped mf;
     mf.fd = open(path.c_str(), O_RDONLY);
-    LB_CHECK(mf.fd >= 0, "Failed to load model \\"" + path + "\\"");
+    LB_CHECK(mf.fd >= 0, "Failed to load model '" + path + "'");
     struct stat st;
     LB_CHECK(fstat(mf.fd, &st) == 0 && st.st_size > 36, "Invalid model file '" + path + "'");
     mf.n = (size_t)st.st_size;
