@@ -41,6 +41,7 @@ typedef struct lb_context lb_context;  /* = llama.Context (pkg/llama/llama.go:83
 typedef struct lb_mlctx   lb_mlctx;    /* = ml.Context    (pkg/ml/ml.go:50-57)         */
 typedef struct lb_tensor  lb_tensor;   /* = ml.Tensor     (pkg/ml/ml.go:180-203)       */
 typedef struct lb_graph   lb_graph;    /* = ml.Graph      (pkg/ml/ml.go:31-45)         */
+typedef struct lb_batch   lb_batch;    /* a set of up to 8 lb_contexts ("pods") decoded together */
 
 /* HParams (pkg/llama/llama.go:149-158); ff is derived as in llama.go:761 */
 typedef struct {
@@ -119,6 +120,17 @@ LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint
                          const float *hidden_in_dev, float *hidden_out_dev, float *logits_out);
 LB_API float *lb_context_hidden_buffer(lb_context *c);   /* device [max_batch][dim] scratch for hand-offs */
 LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
+
+/* ---- pod batching: the reference runs --pods concurrent jobs, one llama.Context each, on one
+ * shared Model (pkg/server/server.go:84-106,151-175).  Their single-token Evals are evaluated here as ONE
+ * pass over the weights (B-column MulMat); every pod keeps its own KV cache and position. ---- */
+LB_API lb_batch *lb_batch_create(lb_context **ctxs, uint32_t n);          /* 1..8 contexts of one model, same ctx size */
+LB_API void      lb_batch_free(lb_batch *b);
+/* one token per pod: tokens[n], pasts[n] (position of each pod's new token), logits_out [n][vocab]; synchronous */
+LB_API int       lb_batch_eval(lb_batch *b, const uint32_t *tokens, const uint32_t *pasts, float *logits_out);
+/* `steps` tokens per pod (tokens [n][steps], teacher-forced) enqueued back to back; ms_out = CUDA-event time */
+LB_API int       lb_batch_decode_resident(lb_batch *b, const uint32_t *tokens, uint32_t steps, const uint32_t *pasts, float *ms_out);
+LB_API int       lb_batch_read_logits(lb_batch *b, float *logits_out);    /* [n][vocab] of the last step */
 
 /* ---- multi-GPU layer sharding: one process per GPU, NCCL send/recv of the residual stream ----
  * rank r owns the stage created with lb_model_create(hp, dev, r*L/G, (r+1)*L/G).  NCCL is bound at

@@ -53,6 +53,11 @@ _SIGS = {
     "lb_eval_stage": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, _vp, _vp, _f32p]),
     "lb_context_hidden_buffer": (_vp, [_vp]),
     "lb_context_stream": (_vp, [_vp]),
+    "lb_batch_create": (_vp, [C.POINTER(_vp), C.c_uint32]),
+    "lb_batch_free": (None, [_vp]),
+    "lb_batch_eval": (C.c_int, [_vp, _u32p, _u32p, _f32p]),
+    "lb_batch_decode_resident": (C.c_int, [_vp, _u32p, C.c_uint32, _u32p, _f32p]),
+    "lb_batch_read_logits": (C.c_int, [_vp, _f32p]),
     "lb_comm_unique_id": (C.c_int, [_vp]),
     "lb_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "lb_comm_destroy": (None, []),

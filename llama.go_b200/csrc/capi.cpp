@@ -15,6 +15,7 @@ struct lb_model { llama::Model *m; };
 struct lb_context { llama::Context *c; };
 struct lb_mlctx { ml::Context *c; };
 struct lb_graph { ml::Graph g; };
+struct lb_batch { llama::PodBatch *b; };
 // lb_tensor* is an ml::Tensor* (owned by its lb_mlctx)
 static inline ml::Tensor *T(lb_tensor *t) { return reinterpret_cast<ml::Tensor *>(t); }
 static inline const ml::Tensor *T(const lb_tensor *t) { return reinterpret_cast<const ml::Tensor *>(t); }
@@ -177,6 +178,26 @@ int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t pa
 }
 float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
 void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }
+
+// ---- pod batching ----
+lb_batch *lb_batch_create(lb_context **ctxs, uint32_t n) {
+    try {
+        LB_CHECK(ctxs && n >= 1, "lb_batch_create: nil argument");
+        std::vector<llama::Context *> v(n);
+        for (uint32_t i = 0; i < n; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+        auto *h = new lb_batch{nullptr};
+        try { h->b = new llama::PodBatch(v); } catch (...) { delete h; throw; }
+        return h;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void lb_batch_free(lb_batch *b) { if (b) { delete b->b; delete b; } }
+int lb_batch_eval(lb_batch *b, const uint32_t *tokens, const uint32_t *pasts, float *logits_out) {
+    LB_TRY_INT(LB_CHECK(b, "nil batch"); b->b->eval(tokens, pasts, logits_out));
+}
+int lb_batch_decode_resident(lb_batch *b, const uint32_t *tokens, uint32_t steps, const uint32_t *pasts, float *ms_out) {
+    LB_TRY_INT(LB_CHECK(b, "nil batch"); float ms = b->b->decode_resident(tokens, steps, pasts); if (ms_out) *ms_out = ms);
+}
+int lb_batch_read_logits(lb_batch *b, float *logits_out) { LB_TRY_INT(LB_CHECK(b && logits_out, "nil argument"); b->b->read_logits(logits_out)); }
 
 // ---- multi-GPU pipeline ----
 int lb_comm_unique_id(void *out128) { LB_TRY_INT(LB_CHECK(out128, "nil argument"); pipe::unique_id(out128)); }

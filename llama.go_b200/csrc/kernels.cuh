@@ -14,6 +14,16 @@ struct TView {
     uint32_t nb[4];
 };
 
+// Per-pod pointers of a batched decode step: sequence b has its own KV cache base and
+// position; all pods share the layer offset inside their caches (same ctx size) and the row pitches.
+struct PodPtrs {
+    float *const *K = nullptr;      // device array [B]: base of pod b's K cache
+    float *const *V = nullptr;
+    const uint32_t *pasts = nullptr;  // device array [B]: position of pod b's new token
+    size_t layer_off = 0;           // floats: layer * ctx * dim
+    uint32_t ldq = 0, ldo = 0;      // row pitch of q rows / output rows
+};
+
 namespace k {
 
 // ---- generic op kernels (one per reference ComputeForward*; used by the pkg/ml mirror) ----
@@ -70,7 +80,17 @@ void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, f
 // attention_decode_scratch_floats() must be zero-initialised once (ticket counters).
 void attention_decode(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
                       uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, cudaStream_t st);
-size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd);
+size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd);   // per pod
+// pod batch: B sequences, each with its own cache / position (pods.*), one launch
+void attention_decode_pods(const float *q, float *out, uint32_t B, const PodPtrs &pods, uint32_t max_T, uint32_t dim,
+                           uint32_t heads, float *scratch, cudaStream_t st);
+void rope_qk_store_pods(float *q, const float *k, const float *v, uint32_t ld, uint32_t B, const PodPtrs &pods, uint32_t dim,
+                        uint32_t heads, cudaStream_t st);
+// row b = table[tokens[b * row_stride + *step_dev]]
+void get_rows_pods(const float *table, uint32_t nc, const uint32_t *tokens, uint32_t row_stride, const uint32_t *step_dev,
+                   uint32_t B, float *dst, cudaStream_t st);
+// pasts[b] += 1 for b < B; state[1] (= step) += 1
+void advance_pods(uint32_t *pasts, uint32_t *state, uint32_t B, cudaStream_t st);
 // single-token embedding gather for graph replay: row = table[tokens[*step_dev + n]]
 void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, const uint32_t *step_dev,
                        uint32_t nr, float *dst, cudaStream_t st);

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ Kc, const float *__restrict__ Vc,
                         float *__restrict__ out, const uint32_t *__restrict__ past_dev, uint32_t dim,
                         float scale, float *__restrict__ part_o, float *__restrict__ part_ml,
-                        unsigned int *__restrict__ tickets, uint32_t chunk_cap) {
+                        unsigned int *__restrict__ tickets, uint32_t chunk_cap, PodPtrs pods) {
     extern __shared__ float sm[];  // scores[chunk_cap]
     __shared__ float red[DEC_THREADS / 32];
     __shared__ float s_bcast;
@@ -114,6 +114,13 @@ attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ K
     const uint32_t h = blockIdx.x, sp = blockIdx.y, S = gridDim.y;
     pdl_launch_dependents();
     pdl_wait();
+    if (pods.K) {  // pod batch: sequence b = blockIdx.z has its own cache, position and rows
+        const uint32_t b = blockIdx.z, H = gridDim.x;
+        Kc = pods.K[b] + pods.layer_off; Vc = pods.V[b] + pods.layer_off;
+        past_dev = pods.pasts + b;
+        q += (size_t)b * pods.ldq; out += (size_t)b * pods.ldo;
+        part_o += (size_t)b * H * DEC_MAX_SPLITS * HD; part_ml += (size_t)b * H * DEC_MAX_SPLITS * 2; tickets += (size_t)b * H;
+    }
     const uint32_t Tn = *past_dev + 1;
     const uint32_t chunk = min((Tn + S - 1) / S, chunk_cap);
     const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn);
@@ -235,25 +242,40 @@ size_t attention_decode_scratch_floats(uint32_t heads, uint32_t hd) {
     return (size_t)heads * DEC_MAX_SPLITS * (hd + 2) + heads;
 }
 
+static void attention_decode_launch(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
+                                    uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, uint32_t B, const PodPtrs &pods,
+                                    cudaStream_t st);
+
 void attention_decode(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
                       uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, cudaStream_t st) {
+    attention_decode_launch(q, Kc, Vc, out, past_dev, max_T, dim, heads, scratch, 1, PodPtrs{}, st);
+}
+void attention_decode_pods(const float *q, float *out, uint32_t B, const PodPtrs &pods, uint32_t max_T, uint32_t dim,
+                           uint32_t heads, float *scratch, cudaStream_t st) {
+    attention_decode_launch(q, nullptr, nullptr, out, nullptr, max_T, dim, heads, scratch, B, pods, st);
+}
+
+static void attention_decode_launch(const float *q, const float *Kc, const float *Vc, float *out, const uint32_t *past_dev,
+                                    uint32_t max_T, uint32_t dim, uint32_t heads, float *scratch, uint32_t B, const PodPtrs &pods,
+                                    cudaStream_t st) {
     const uint32_t hd = dim / heads;
     LB_CHECK(hd == 32 || hd == 64 || hd == 128, "attention: head dim must be 32, 64 or 128");
     const uint32_t S = attention_decode_splits(max_T);
     const uint32_t chunk_cap = (max_T + S - 1) / S;
+    // scratch layout (B = number of pods, 1 for a single sequence): part_o [B][H][32][hd] | part_ml [B][H][32][2] | tickets [B][H]
     float *part_o = scratch;
-    float *part_ml = part_o + (size_t)heads * DEC_MAX_SPLITS * hd;
-    unsigned int *tickets = reinterpret_cast<unsigned int *>(part_ml + (size_t)heads * DEC_MAX_SPLITS * 2);
+    float *part_ml = part_o + (size_t)B * heads * DEC_MAX_SPLITS * hd;
+    unsigned int *tickets = reinterpret_cast<unsigned int *>(part_ml + (size_t)B * heads * DEC_MAX_SPLITS * 2);
     float scale = (float)(1.0 / sqrt((double)dim / (double)heads));  // llama.go:306
     size_t smem = (size_t)chunk_cap * sizeof(float);
     LB_CHECK(smem <= 40 * 1024, "attention_decode: context too long");
-    dim3 grid(heads, S);
+    dim3 grid(heads, S, B);
     if (hd == 128)
-        launch_pdl(attention_decode_kernel<128>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+        launch_pdl(attention_decode_kernel<128>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap, pods);
     else if (hd == 64)
-        launch_pdl(attention_decode_kernel<64>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+        launch_pdl(attention_decode_kernel<64>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap, pods);
     else
-        launch_pdl(attention_decode_kernel<32>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap);
+        launch_pdl(attention_decode_kernel<32>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap, pods);
 }
 
 void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,

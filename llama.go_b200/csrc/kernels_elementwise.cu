@@ -340,6 +340,65 @@ void rope_qk_store(float *q, const float *k, const float *v, uint32_t ld, float 
     launch_pdl(rope_qk_store_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, st, q, k, v, ld, Kc, Vc, N, past_dev, dim, dim / heads);
 }
 
+// ---- pod-batch variants: row b belongs to sequence b
+__global__ void rope_qk_store_pods_kernel(float *q, const float *__restrict__ k, const float *__restrict__ v, uint32_t ld,
+                                          uint32_t B, PodPtrs pods, uint32_t dim, uint32_t hd) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t half = dim / 2;
+    const size_t n = (size_t)half * B;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const uint32_t pr = (uint32_t)(idx % half), b = (uint32_t)(idx / half);
+        const uint32_t e = 2 * pr;
+        const int i0 = (int)(e % hd);
+        const uint32_t p = pods.pasts[b];
+        double sn, cs;
+        sincos((double)p * pow(10000.0, ((double)(-i0)) / (double)hd), &sn, &cs);
+        float *qd = q + (size_t)b * ld + e;
+        double x0 = (double)qd[0], x1 = (double)qd[1];
+        qd[0] = (float)(__dsub_rn(__dmul_rn(x0, cs), __dmul_rn(x1, sn)));
+        qd[1] = (float)(__dadd_rn(__dmul_rn(x0, sn), __dmul_rn(x1, cs)));
+        const float *kd = k + (size_t)b * ld + e;
+        x0 = (double)kd[0]; x1 = (double)kd[1];
+        float2 kr;
+        kr.x = (float)(__dsub_rn(__dmul_rn(x0, cs), __dmul_rn(x1, sn)));
+        kr.y = (float)(__dadd_rn(__dmul_rn(x0, sn), __dmul_rn(x1, cs)));
+        *reinterpret_cast<float2 *>(pods.K[b] + pods.layer_off + (size_t)p * dim + e) = kr;
+        *reinterpret_cast<float2 *>(pods.V[b] + pods.layer_off + (size_t)p * dim + e) =
+            *reinterpret_cast<const float2 *>(v + (size_t)b * ld + e);
+    }
+}
+void rope_qk_store_pods(float *q, const float *k, const float *v, uint32_t ld, uint32_t B, const PodPtrs &pods, uint32_t dim,
+                        uint32_t heads, cudaStream_t st) {
+    const size_t n = (size_t)(dim / 2) * B;
+    launch_pdl(rope_qk_store_pods_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, st, q, k, v, ld, B, pods, dim, dim / heads);
+}
+__global__ void get_rows_pods_kernel(const float *__restrict__ table, uint32_t nc, const uint32_t *__restrict__ tokens,
+                                     uint32_t row_stride, const uint32_t *__restrict__ step_dev, float *__restrict__ dst) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t row = blockIdx.x;
+    const size_t r = tokens[(size_t)row * row_stride + *step_dev];
+    const float *src = table + r * nc;
+    float *d = dst + (size_t)row * nc;
+    for (uint32_t i = threadIdx.x * 4; i < nc; i += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(d + i) = *reinterpret_cast<const float4 *>(src + i);
+}
+void get_rows_pods(const float *table, uint32_t nc, const uint32_t *tokens, uint32_t row_stride, const uint32_t *step_dev,
+                   uint32_t B, float *dst, cudaStream_t st) {
+    LB_CHECK((nc & 3) == 0, "get_rows_pods: row length must be a multiple of 4");
+    launch_pdl(get_rows_pods_kernel, dim3(B), dim3(256), 0, st, table, nc, tokens, row_stride, step_dev, dst);
+}
+__global__ void advance_pods_kernel(uint32_t *pasts, uint32_t *state, uint32_t B) {
+    pdl_wait();
+    if (threadIdx.x < B) pasts[threadIdx.x] += 1;
+    if (threadIdx.x == 0) state[1] += 1;
+}
+void advance_pods(uint32_t *pasts, uint32_t *state, uint32_t B, cudaStream_t st) {
+    launch_pdl(advance_pods_kernel, dim3(1), dim3(32), 0, st, pasts, state, B);
+}
+
 __global__ void get_rows_indirect_kernel(const float *__restrict__ table, uint32_t nc, const uint32_t *__restrict__ tokens,
                                          const uint32_t *__restrict__ step_dev, float *__restrict__ dst) {
     uint32_t row = blockIdx.x;

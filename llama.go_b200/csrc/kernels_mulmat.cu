@@ -145,6 +145,76 @@ gemv_swiglu_kernel(const float *__restrict__ W1, const float *__restrict__ W3, u
     }
 }
 
+// Multi-column (pod batch, NC >= 3) variant: a warp owns 4 weight rows so every activation float4 it
+// pulls through L1 is used by 4 rows — with one row per warp the 8 activation columns would need
+// ~190 B/clk of L1 bandwidth per SM to keep up with the weight stream (the L1 limit is 128).
+template <int NC>
+__global__ void __launch_bounds__(128)
+gemv_cols_kernel(const float *__restrict__ W, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
+                 float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
+    constexpr int RPW = 4, U = 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row0 = (blockIdx.x * 4 + warp) * RPW;
+    if (row0 >= M) return;
+    float acc[RPW][NC];
+#pragma unroll
+    for (int r = 0; r < RPW; r++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[r][c] = 0.f;
+    const float *wr[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; r++) wr[r] = W + (size_t)min(row0 + r, M - 1) * K;
+    float4 w[U][RPW];
+    auto load_batch = [&](uint32_t kk) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t kq = kk + u * 128;
+#pragma unroll
+            for (int r = 0; r < RPW; r++) w[u][r] = (kq < K) ? ld_stream_f4(wr[r] + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    pdl_launch_dependents();
+    load_batch(lane * 4);
+    pdl_wait();
+    for (uint32_t kk = lane * 4; kk < K;) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t kq = kk + u * 128;
+            if (kq < K) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx + kq));
+#pragma unroll
+                    for (int r = 0; r < RPW; r++) {
+                        acc[r][c] = fmaf(w[u][r].x, xv.x, acc[r][c]); acc[r][c] = fmaf(w[u][r].y, xv.y, acc[r][c]);
+                        acc[r][c] = fmaf(w[u][r].z, xv.z, acc[r][c]); acc[r][c] = fmaf(w[u][r].w, xv.w, acc[r][c]);
+                    }
+                }
+            }
+        }
+        kk += 128 * U;
+        if (kk < K) load_batch(kk);
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; r++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[r][c] = warp_sum(acc[r][c]);
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RPW; r++) {
+            const uint32_t row = row0 + r;
+            if (row < M) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float v = acc[r][c];
+                    if (res) v = __fadd_rn(v, res[(size_t)c * ldy + row]);
+                    y[(size_t)c * ldy + row] = v;
+                }
+            }
+        }
+    }
+}
+
 template <int NC>
 static void gemv_launch(const float *W, uint32_t M, uint32_t K, const float *x, uint32_t ldx, float *y, uint32_t ldy,
                         const float *res, cudaStream_t st) {
@@ -152,7 +222,9 @@ static void gemv_launch(const float *W, uint32_t M, uint32_t K, const float *x, 
     // and 4-warp blocks so that the grid is >= 6 blocks per SM and every SM holds the same number of
     // warps (256 blocks of 16 rows left 1.7 blocks per SM: measured 51-63 % of HBM peak).
     constexpr bool two = (NC <= 2);
-    if (two && M >= 8192) {
+    if (NC >= 3) {
+        launch_pdl(gemv_cols_kernel<NC>, dim3((M + 15) / 16), dim3(128), 0, st, W, M, K, x, ldx, y, ldy, res);
+    } else if (two && M >= 8192) {
         unsigned grid = (M + 15) / 16;
         launch_pdl(gemv_kernel<NC, 2, 8, 4>, dim3(grid), dim3(256), 0, st, W, M, K, x, ldx, y, ldy, res);
     } else {

@@ -118,6 +118,35 @@ struct Context {
     void build_decode_graph();
 };
 
+// Pod batching (pods.cpp): B contexts ("pods") of one model decode one token each per step
+// in a single pass over the weights.
+struct PodBatch {
+    static constexpr uint32_t kTokensCap = 4096;
+    std::vector<Context *> ctxs;
+    Model *model = nullptr;
+    uint32_t B = 0, ctx_size = 0;
+    cudaStream_t stream = nullptr;
+    float *x = nullptr, *y = nullptr, *cur = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *logits = nullptr;
+    float *attn_scratch = nullptr;
+    float **kb_dev = nullptr, **vb_dev = nullptr;
+    uint32_t *pasts_dev = nullptr, *state_dev = nullptr, *tokens_dev = nullptr;
+    uint32_t *tokens_host = nullptr, *pasts_host = nullptr;
+    float *logits_host = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    explicit PodBatch(const std::vector<Context *> &ctxs);
+    ~PodBatch();
+    void eval(const uint32_t *tokens, const uint32_t *pasts, float *logits_out);          // one token per pod, host buffers
+    float decode_resident(const uint32_t *tokens, uint32_t steps, const uint32_t *pasts);  // teacher-forced, device timed
+    void read_logits(float *out);
+
+   private:
+    void forward();
+    void ensure_graph();
+    void stage_inputs(const uint32_t *tokens, uint32_t steps, const uint32_t *pasts);
+};
+
 }  // namespace llama
 namespace pipe {
 void unique_id(void *out128);

@@ -161,6 +161,48 @@ def GenerateGreedy(lctx: Context, prompt_ids, predict: int, temp: float = 1e-6, 
     return out.tolist()
 
 
+class PodBatch:
+    """Up to 8 llama.Contexts ("pods", pkg/server/server.go:84-106) of one Model decoded together: one
+    pass over the weights per step for all of them."""
+
+    def __init__(self, ctxs):
+        self.ctxs = list(ctxs)
+        self.vocab = self.ctxs[0].model.hp.vocab
+        arr = (C.c_void_p * len(self.ctxs))(*[c._h for c in self.ctxs])
+        self._h = check_ptr(lib().lb_batch_create(arr, len(self.ctxs)))
+
+    def Eval(self, tokens, pasts) -> np.ndarray:
+        """tokens[n], pasts[n] -> logits [n][vocab] (row b = llama.Eval(ctxs[b], [tokens[b]], pasts[b]))."""
+        t, tp = _toks(tokens)
+        p, pp = _toks(pasts)
+        out = np.empty((len(self.ctxs), self.vocab), np.float32)
+        check(lib().lb_batch_eval(self._h, tp, pp, out.ctypes.data_as(_f32p)))
+        return out
+
+    def DecodeResident(self, tokens, pasts) -> float:
+        t = np.ascontiguousarray(tokens, dtype=np.uint32)
+        p, pp = _toks(pasts)
+        ms = C.c_float(0)
+        check(lib().lb_batch_decode_resident(self._h, t.ctypes.data_as(_u32p), t.shape[1], pp, C.byref(ms)))
+        return ms.value
+
+    def ReadLogits(self) -> np.ndarray:
+        out = np.empty((len(self.ctxs), self.vocab), np.float32)
+        check(lib().lb_batch_read_logits(self._h, out.ctypes.data_as(_f32p)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().lb_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def ReadLogits(lctx: Context) -> np.ndarray:
     check(lib().lb_context_read_logits(lctx._h, lctx.Logits.ctypes.data_as(_f32p)))
     return lctx.Logits
