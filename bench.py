@@ -315,6 +315,56 @@ def run_single_gpu(args):
     print(json.dumps(line), flush=True)
 
 
+def run_pods(args):
+    """Extra (non-headline) measurement, SURVEY §8f-1: B pods of LLaMA-7B FP32 decoded in one pass over the weights."""
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import _capi, llama, synth
+    _capi.require_gpu()
+    lib = _capi.lib()
+    hp = getattr(synth, MODELS[args.model])
+    K, W, B = args.steps, args.warmup, args.pods
+    ctx_size = max(args.context or CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
+    model = llama.Model(hp).init_random(0)
+    rs = np.random.RandomState(0)
+    pods = [llama.NewContext(model, ctx_size) for _ in range(B)]
+    for c in pods:
+        llama.Eval(c, rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32), 0)
+    gen = rs.randint(3, hp.vocab, size=(B, 2 * W + 2 * K)).astype(np.uint32)
+    batch = llama.PodBatch(pods)
+    batch.DecodeResident(gen[:, :W], [PROMPT_LEN] * B)
+    sampler = ClockSampler(0); sampler.start()
+    l0 = lib.lb_kernel_launches()
+    ms = batch.DecodeResident(gen[:, W:W + K], [PROMPT_LEN + W] * B)
+    launches = lib.lb_kernel_launches() - l0
+    value = B * K / (ms / 1e3)
+    for i in range(W):
+        batch.Eval(gen[:, W + K + i], [PROMPT_LEN + W + K + i] * B)
+    t0 = time.perf_counter()
+    for i in range(K):
+        batch.Eval(gen[:, 2 * W + K + i], [PROMPT_LEN + 2 * W + K + i] * B)
+    e2e = B * K / (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    T_mid = PROMPT_LEN + W + K / 2.0
+    bytes_per_step = model.weight_bytes_per_token + B * (2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab)
+    gbs = bytes_per_step * (value / B) / 1e9
+    print(json.dumps({
+        "metric": "LLaMA-%s FP32 decode tokens/sec, aggregate over %d pods batched per weight pass" % (args.model.upper(), B),
+        "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LLaMA-%s FP32, %d independent sequences (pods), one token each per step, context %d, %d-token prompts"
+                               % (args.model.upper(), B, ctx_size, PROMPT_LEN), "sequences_in_flight": B, "l2": "inputs>L2",
+                   "decode_path": "per-op kernels, B-column GEMV, CUDA-graph replay"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B + 8, "d2h_bytes_per_step": 4 * hp.vocab * B,
+                "api": "lb_batch_eval (host buffers, synchronous)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "note": "bytes per step = weights once + %d x (KV + logits)" % B},
+        "cpu_baseline": None}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -325,6 +375,7 @@ def main():
     ap.add_argument("--weights", default="f32", choices=["f32", "q8"], help="q8 = BASELINE config 3 (not the headline metric)")
     ap.add_argument("--model", default="7b", choices=sorted(MODELS), help="default 7b = the headline metric; 13b/65b = BASELINE configs 4-5")
     ap.add_argument("--context", type=int, default=0, help="override the context size (BASELINE config 5 uses 2048)")
+    ap.add_argument("--pods", type=int, default=1, help="extra measurement: B pods (1..8) batched per weight pass on one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -333,6 +384,8 @@ def main():
     if world > 1 or args.gpus > 1:
         from bench_pipeline import run_pipeline   # layer-sharded multi-GPU arm
         return run_pipeline(args)
+    if args.pods > 1:
+        return run_pods(args)
     return run_single_gpu(args)
 
 
