@@ -93,9 +93,9 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
 #pragma unroll
     for (int c = 0; c < NC; c++) a1[c] = a3[c] = 0.f;
     const uint32_t K4 = K >> 2;
-    for (uint32_t kk = lane; kk < K4; kk += 32 * Q8_UNROLL) {
-        uint32_t w1[Q8_UNROLL], w3[Q8_UNROLL];
-        float s1[Q8_UNROLL], s3[Q8_UNROLL];
+    uint32_t w1[Q8_UNROLL], w3[Q8_UNROLL];
+    float s1[Q8_UNROLL], s3[Q8_UNROLL];
+    auto load_batch = [&](uint32_t kk) {
 #pragma unroll
         for (int u = 0; u < Q8_UNROLL; u++) {
             uint32_t k4 = kk + u * 32;
@@ -107,6 +107,11 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
                 s3[u] = ok ? __ldg(d3 + (k4 >> 3)) : 0.f;
             }
         }
+    };
+    pdl_launch_dependents();
+    load_batch(lane);  // weights and scales are read-only: issue them before waiting on the predecessor grid (PDL)
+    pdl_wait();
+    for (uint32_t kk = lane; kk < K4;) {
 #pragma unroll
         for (int u = 0; u < Q8_UNROLL; u++) {
             uint32_t k4 = kk + u * 32;
@@ -132,6 +137,8 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
                 }
             }
         }
+        kk += 32 * Q8_UNROLL;
+        if (kk < K4) load_batch(kk);
     }
 #pragma unroll
     for (int c = 0; c < NC; c++) {
@@ -154,10 +161,9 @@ static void gemv_q8_dispatch(const int8_t *Q1, const float *D1, const int8_t *Q3
     LB_CHECK(N >= 1 && N <= 8, "gemv_q8: N must be 1..8");
     LB_CHECK((K & 31) == 0 && (ldx & 3) == 0, "gemv_q8: K must be a multiple of 32");
     unsigned grid = (M + Q8_WARPS - 1) / Q8_WARPS;
-#define LB_Q8_CASE(n) case n: gemv_q8_kernel<n, SWIGLU><<<grid, Q8_WARPS * 32, 0, st>>>(Q1, D1, Q3, D3, M, K, x, ldx, y, ldy, res); break;
+#define LB_Q8_CASE(n) case n: launch_pdl(gemv_q8_kernel<n, SWIGLU>, dim3(grid), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, D3, M, K, x, ldx, y, ldy, res); break;
     switch (N) { LB_Q8_CASE(1) LB_Q8_CASE(2) LB_Q8_CASE(3) LB_Q8_CASE(4) LB_Q8_CASE(5) LB_Q8_CASE(6) LB_Q8_CASE(7) default: LB_Q8_CASE(8) }
 #undef LB_Q8_CASE
-    LB_LAUNCH_CHECK();
 }
 void gemv_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N, float *y,
              uint32_t ldy, const float *residual, cudaStream_t st) {
