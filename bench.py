@@ -107,6 +107,43 @@ def _scratch_dir(need_bytes):
     return tempfile.mkdtemp(prefix="lb_ref_")
 
 
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def reference_cpu_decode_full(steps, warmup, threads=None):
+    """The reference binary on the FULL LLaMA-7B FP32 model (26.9 GB ggjt file in a RAM-backed scratch
+    dir, same synthetic weights as the GPU arm): 8-token prompt, then warmup+steps single-token decodes;
+    tok/s = steps / sum(EVAL_TIME of the timed decodes).  Needs ~60 GB of host RAM; only used when the box has it."""
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import synth
+    from oracle import refbin
+    threads = threads or os.cpu_count() or 1
+    hp = synth.LLAMA_7B
+    predict = warmup + steps + 1
+    context = 8 + predict + 8
+    td = _scratch_dir(28e9)
+    try:
+        path = os.path.join(td, "llama7b.bin")
+        synth.write_ggjt(path, hp, synth.synth_model_fast(0, hp))
+        r = refbin.run(path, "abcde", predict, context, threads, True, port=18097, timeout=3000)
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+    dec = r["eval_ms"][1:][warmup:warmup + steps]
+    if len(dec) < max(1, steps // 2):
+        raise RuntimeError("reference binary produced no timing report:\n" + r["raw"][-2000:].decode("utf-8", "replace"))
+    ms = float(np.mean(dec))
+    return {"tok_s": 1000.0 / ms, "ms_per_token": ms, "kind": "reference", "cores": threads,
+            "sample": (f"reference binary --avx --threads {threads} on the FULL LLaMA-7B FP32 synthetic model: 8-token prompt, "
+                       f"{len(dec)} single-token decodes timed after {warmup} warm-up (mean {ms:.0f} ms/token, past 8..{8 + warmup + steps})")}
+
+
 def reference_cpu_decode(steps, warmup, threads=None):
     """Time the reference's own CPU path on this box's host cores.
 
@@ -174,7 +211,16 @@ def run_reference(args):
     rank, world, _ = rank_world()
     if rank != 0:
         return
-    r = reference_cpu_decode(args.steps, args.warmup)
+    from oracle import refbin
+    full_ok = refbin.available() and _mem_available_gb() > 100 and args.steps <= 160
+    r = None
+    if full_ok:
+        try:
+            r = reference_cpu_decode_full(args.steps, args.warmup)       # measured on the whole model
+        except Exception as e:
+            sys.stderr.write(f"[bench] full-model reference run failed ({e}); falling back to layer slices\n")
+    if r is None:
+        r = reference_cpu_decode(args.steps, args.warmup)                # bounded sample, extrapolated
     line = {
         "impl": "reference", "metric": METRIC, "value": r["tok_s"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_token"], "higher_is_better": True,
