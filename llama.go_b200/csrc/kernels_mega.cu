@@ -215,106 +215,9 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
     }
 }
 
-// int8 -> float without the I2F pipe (see kernels_q8.cu): bias to unsigned, splice into 2^23's mantissa, subtract
-__device__ __forceinline__ void mg_unpack4(uint32_t w, float f[4]) {
-    const uint32_t u = w ^ 0x80808080u;
-    f[0] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650)) - 8388736.0f;
-    f[1] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7651)) - 8388736.0f;
-    f[2] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - 8388736.0f;
-    f[3] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - 8388736.0f;
-}
-__host__ __device__ constexpr int mg_rb_q8(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
-
-// GEMV phase over Q8_0 weights: same scheduling and K-slicing as gemv_phase; a lane's float4 slot
-// of the activation slice meets 4 consecutive int8 (one 32-bit load, 128 B per warp request) and the
-// FP32 scale of their 32-block; products are f32(d*q) * x like the per-op Q8 kernels.
-template <int V, bool SWIGLU>
-__device__ __forceinline__ void gemv_phase_q8(const int8_t *__restrict__ Q1, const float *__restrict__ D1,
-                                              const int8_t *__restrict__ Q3, const float *__restrict__ D3, uint32_t M, uint32_t K,
-                                              const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr) {
-    constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int RB = mg_rb_q8(V, NM);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t KS = K / MG_WARPS, KB = K >> 5;
-    const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
-    const uint32_t pool0 = Q * gridDim.x;
-    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);
-    int buf = 0;
-    auto do_block = [&](uint32_t rb, uint32_t nrb) {
-        for (uint32_t r = 0; r < nrb; r += RB) {
-            uint32_t qa[RB][NM][V];
-            float da[RB][NM][V];
-#pragma unroll
-            for (int i = 0; i < RB; i++) {
-                const bool rok = r + i < nrb;
-                const size_t row = rb + r + i;
-#pragma unroll
-                for (int j = 0; j < V; j++) {
-                    const uint32_t e = (j * 32 + lane) * 4;
-                    const bool ok = rok && e < KS;
-                    const size_t el = (size_t)warp * KS + e;
-                    qa[i][0][j] = ok ? __ldg(reinterpret_cast<const uint32_t *>(Q1 + row * K + el)) : 0x0u;
-                    da[i][0][j] = ok ? __ldg(D1 + row * KB + (el >> 5)) : 0.f;
-                    if (SWIGLU) {
-                        qa[i][NM - 1][j] = ok ? __ldg(reinterpret_cast<const uint32_t *>(Q3 + row * K + el)) : 0x0u;
-                        da[i][NM - 1][j] = ok ? __ldg(D3 + row * KB + (el >> 5)) : 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < RB; i++) {
-#pragma unroll
-                for (int mtx = 0; mtx < NM; mtx++) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < V; j++) {
-                        float f[4];
-                        mg_unpack4(qa[i][mtx][j], f);
-                        const float dd = da[i][mtx][j];
-                        acc = fmaf(__fmul_rn(dd, f[0]), xs[j].x, acc); acc = fmaf(__fmul_rn(dd, f[1]), xs[j].y, acc);
-                        acc = fmaf(__fmul_rn(dd, f[2]), xs[j].z, acc); acc = fmaf(__fmul_rn(dd, f[3]), xs[j].w, acc);
-                    }
-                    acc = warp_sum(acc);
-                    if (lane == 0 && r + i < nrb) sh.part[buf][mtx][r + i][warp] = acc;
-                }
-            }
-        }
-        csync();
-        if (threadIdx.x < nrb) {
-            float s1 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int wv = 0; wv < MG_WARPS; wv++) {
-                s1 += sh.part[buf][0][threadIdx.x][wv];
-                if (SWIGLU) s3 += sh.part[buf][NM - 1][threadIdx.x][wv];
-            }
-            const uint32_t row = rb + threadIdx.x;
-            float v;
-            if (SWIGLU) v = __fmul_rn(silu_ref(s1), s3);
-            else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
-            out[row] = v;
-        }
-        buf ^= 1;
-    };
-    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
-    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) do_block(rb, min((uint32_t)MG_ROWBLK, r1 - rb));
-    int slot = 0;
-    csync();
-    uint32_t t = sh.ticket_slot[0];
-    while ((uint64_t)pool0 + (uint64_t)t * MG_DYN_ROWS < M) {
-        const uint32_t rb = pool0 + t * MG_DYN_ROWS;
-        if (threadIdx.x == 0) sh.ticket_slot[slot ^ 1] = atomicAdd(ctr, 1u);
-        do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));
-        slot ^= 1;
-        t = sh.ticket_slot[slot];
-    }
-}
-
 struct MegaLayer {
     const float *attention_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2;
     float *Kc, *Vc;
-    // Q8_0 planes (kernels_q8.cu) used instead of the float matrices when the model is block-quantised
-    const int8_t *q_wqkv, *q_wo, *q_w1, *q_w3, *q_w2;
-    const float *d_wqkv, *d_wo, *d_w1, *d_w3, *d_w2;
 };
 struct MegaParams {
     const MegaLayer *layers;
@@ -323,13 +226,10 @@ struct MegaParams {
     const uint32_t *tokens;
     const uint32_t *state;        // {past, step}
     const float *final_norm, *output;  // nullptr: no lm_head on this stage
-    const int8_t *q_output;            // Q8_0 lm_head planes
-    const float *d_output;
     float *x, *y, *qkv, *attn, *act, *logits;
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
-    uint32_t layers_host_q8;  // 1: the layers carry Q8_0 planes (host-side dispatch flag)
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
 };
 
@@ -483,7 +383,7 @@ __device__ __forceinline__ void merged_attention_slice(const MegaParams &p, floa
     }
 }
 
-template <int VD, int VF, int HD, bool Q8>
+template <int VD, int VF, int HD>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
     extern __shared__ float scores[];  // [2][chunk_cap]
     __shared__ MegaShared sh;
@@ -521,8 +421,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             stamp(li, 1);
-            if (Q8) gemv_phase_q8<VD, false>(L.q_wqkv, L.d_wqkv, nullptr, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
-            else gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
+            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
         }
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 0));
@@ -535,8 +434,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs);
-            if (Q8) gemv_phase_q8<VD, false>(L.q_wo, L.d_wo, nullptr, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
-            else gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
         }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 2));
@@ -545,8 +443,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             stamp(li, 8);
-            if (Q8) gemv_phase_q8<VD, true>(L.q_w1, L.d_w1, L.q_w3, L.d_w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
-            else gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
+            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
         }
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 3));
@@ -554,8 +451,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
-            if (Q8) gemv_phase_q8<VF, false>(L.q_w2, L.d_w2, nullptr, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
-            else gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
         }
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
@@ -565,8 +461,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
         float4 xs[VD];
         rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
-        if (Q8) gemv_phase_q8<VD, false>(p.q_output, p.d_output, nullptr, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4);
-        else gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4);
+        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4);
     }
 }
 
@@ -583,21 +478,17 @@ static bool pick_variant(uint32_t dim, uint32_t ff, uint32_t hd, int &vd, int &v
     return true;
 }
 
-template <int VD, int VF, bool Q8>
-static cudaError_t launch_hd_q(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
+template <int VD, int VF>
+static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (hd == 128) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 128, Q8>, p);
-    if (hd == 64) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 64, Q8>, p);
-    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 32, Q8>, p);
-}
-template <int VD, int VF>
-static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
-    return p.q_output || (p.n_layers && p.layers_host_q8) ? launch_hd_q<VD, VF, true>(p, hd, smem, st) : launch_hd_q<VD, VF, false>(p, hd, smem, st);
+    if (hd == 128) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 128>, p);
+    if (hd == 64) return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 64>, p);
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<VD, VF, 32>, p);
 }
 
 bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads) {
@@ -618,8 +509,7 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     p.layers = reinterpret_cast<const MegaLayer *>(h.layers_dev);
     p.n_layers = h.n_layers;
     p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
-    p.final_norm = h.final_norm; p.output = h.output; p.q_output = h.q_output; p.d_output = h.d_output;
-    p.layers_host_q8 = h.q8 ? 1u : 0u;
+    p.final_norm = h.final_norm; p.output = h.output;
     p.x = h.x; p.y = h.y; p.qkv = h.qkv; p.attn = h.attn; p.act = h.act; p.logits = h.logits;
     p.part_o = h.part_o; p.part_ml = h.part_ml; p.tickets = h.tickets; p.barrier = h.barrier;
     p.dim = h.dim; p.ff = h.ff; p.heads = h.heads; p.vocab = h.vocab; p.ctx = h.ctx;
