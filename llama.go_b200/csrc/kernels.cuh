@@ -122,8 +122,9 @@ uint32_t decode_mega_splits(uint32_t heads);
 void decode_mega(const MegaParamsHost &p, cudaStream_t st);
 
 // ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
-void quantize_q8(const float *W, int8_t *q, float *d, size_t nelem, cudaStream_t st);
-void dequantize_q8(const int8_t *q, const float *d, float *out, size_t nelem, cudaStream_t st);
+// W / out are plain row-major [rows][K]; q / d are the 4-row-interleaved planes (rows % 4 == 0, K % 32 == 0)
+void quantize_q8(const float *W, int8_t *q, float *d, uint32_t rows, uint32_t K, cudaStream_t st);
+void dequantize_q8(const int8_t *q, const float *d, float *out, uint32_t rows, uint32_t K, cudaStream_t st);
 void gemv_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N,
              float *y, uint32_t ldy, const float *residual, cudaStream_t st);
 void gemv_q8_swiglu(const int8_t *Q1, const float *D1, const int8_t *Q3, const float *D3, uint32_t M, uint32_t K,

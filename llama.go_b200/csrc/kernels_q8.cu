@@ -5,59 +5,89 @@
 // defined here consistently with those constants:
 //   block = 32 consecutive weights of one row (along K);  d = max|w| / 127  (FP32);
 //   q_i = rint(w_i / d) clamped to [-127, 127] (FP32 divide, round-half-even); d == 0 -> q = 0.
-//   36 bytes per 32 weights, stored as two planes: q[M][K] int8 and d[M][K/32] float
-//   (same bytes as the interleaved block, but 16-byte aligned for vector loads).
-// Parity target: the FP32 path on the dequantised weights f32(d * q_i).  The kernels compute
-// f32(d*q_i) explicitly (one rounding) and then FMA, i.e. the same products as the target.
+//   36 bytes per 32 weights.
+// Physical layout in HBM ("4-row interleaved", chosen for the decode GEMV): rows are grouped by 4;
+//   q plane: group g, k4 = k/4  ->  16 bytes at ((g*(K/4) + k4)*16): byte (r%4)*4 + (k%4)
+//   d plane: group g, kb = k/32 ->  4 floats at ((g*(K/32) + kb)*4): float (r%4)
+// so one 128-bit load gives a lane 4 rows x 4 consecutive weights, which all meet the SAME float4 of
+// the activation vector (one fully coalesced 512-byte activation request per warp serves 16 weights
+// per lane), and one more 128-bit load gives the 4 rows' block scales.  A sub-matrix that starts at a
+// row multiple of 4 starts at q + r0*K, d + r0*K/32 like in a plain row-major layout.
+// Parity target: the FP32 path on the dequantised weights f32(d * q_i); the GEMV computes
+// d * sum_4(q_i * x_i) per 4 weights (reassociated scale), the GEMM f32(d*q_i) exactly.
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace lb {
 namespace k {
 
-__global__ void quantize_q8_kernel(const float *__restrict__ W, int8_t *__restrict__ q, float *__restrict__ d, size_t nblocks) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblocks) return;
-    const float4 *src = reinterpret_cast<const float4 *>(W + b * 32);
-    float v[32];
-    float amax = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float4 t = src[i];
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
-    }
-    const float dd = __fdiv_rn(amax, 127.0f);
-    d[b] = dd;
-    int8_t out[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        int r = dd > 0.f ? __float2int_rn(__fdiv_rn(v[i], dd)) : 0;
-        r = max(-127, min(127, r));
-        out[i] = (int8_t)r;
-    }
-    int4 *dst = reinterpret_cast<int4 *>(q + b * 32);
-    dst[0] = *reinterpret_cast<int4 *>(out);
-    dst[1] = *reinterpret_cast<int4 *>(out + 16);
+__device__ __forceinline__ size_t q8_qoff(uint32_t r, uint32_t kcol, uint32_t K) {
+    return ((size_t)(r >> 2) * (K >> 2) + (kcol >> 2)) * 16 + (r & 3) * 4 + (kcol & 3);
 }
-void quantize_q8(const float *W, int8_t *q, float *d, size_t nelem, cudaStream_t st) {
-    LB_CHECK(nelem % 32 == 0, "quantize_q8: element count must be a multiple of 32");
-    size_t nb = nelem / 32;
-    if (!nb) return;
-    quantize_q8_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(W, q, d, nb);
+__device__ __forceinline__ size_t q8_doff(uint32_t r, uint32_t kcol, uint32_t K) {
+    return ((size_t)(r >> 2) * (K >> 5) + (kcol >> 5)) * 4 + (r & 3);
+}
+
+// one thread per (row group, 32-block): 4 rows x 32 weights
+__global__ void quantize_q8_kernel(const float *__restrict__ W, int8_t *__restrict__ q, float *__restrict__ d, uint32_t rows,
+                                   uint32_t K) {
+    const uint32_t KB = K >> 5;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)(rows >> 2) * KB) return;
+    const uint32_t g = (uint32_t)(idx / KB), kb = (uint32_t)(idx % KB);
+    float dd[4];
+    uint32_t packed[4][8];  // [row][k4] 4 int8 each
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const float4 *src = reinterpret_cast<const float4 *>(W + (size_t)(g * 4 + rr) * K + kb * 32);
+        float v[32];
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float4 t = src[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+        }
+        dd[rr] = __fdiv_rn(amax, 127.0f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int r = dd[rr] > 0.f ? __float2int_rn(__fdiv_rn(v[4 * i + j], dd[rr])) : 0;
+                r = max(-127, min(127, r));
+                w |= ((uint32_t)(r & 0xFF)) << (8 * j);
+            }
+            packed[rr][i] = w;
+        }
+    }
+    uint4 *qdst = reinterpret_cast<uint4 *>(q + ((size_t)g * (K >> 2) + kb * 8) * 16);
+#pragma unroll
+    for (int i = 0; i < 8; i++) qdst[i] = make_uint4(packed[0][i], packed[1][i], packed[2][i], packed[3][i]);
+    *reinterpret_cast<float4 *>(d + ((size_t)g * KB + kb) * 4) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+}
+void quantize_q8(const float *W, int8_t *q, float *d, uint32_t rows, uint32_t K, cudaStream_t st) {
+    LB_CHECK(K % 32 == 0 && rows % 4 == 0, "quantize_q8: K must be a multiple of 32 and the row count a multiple of 4");
+    const size_t n = (size_t)(rows / 4) * (K / 32);
+    if (!n) return;
+    quantize_q8_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(W, q, d, rows, K);
     LB_LAUNCH_CHECK();
 }
 
-__global__ void dequantize_q8_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, float *__restrict__ out, size_t n) {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = __fmul_rn(d[i >> 5], (float)q[i]);
+__global__ void dequantize_q8_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, float *__restrict__ out,
+                                     uint32_t rows, uint32_t K) {
+    const size_t n = (size_t)rows * K, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t r = (uint32_t)(i / K), kcol = (uint32_t)(i % K);
+        out[i] = __fmul_rn(d[q8_doff(r, kcol, K)], (float)q[q8_qoff(r, kcol, K)]);
+    }
 }
-void dequantize_q8(const int8_t *q, const float *d, float *out, size_t nelem, cudaStream_t st) {
-    if (!nelem) return;
-    size_t blocks = (nelem + 255) / 256;
+void dequantize_q8(const int8_t *q, const float *d, float *out, uint32_t rows, uint32_t K, cudaStream_t st) {
+    const size_t n = (size_t)rows * K;
+    if (!n) return;
+    size_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    dequantize_q8_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, d, out, nelem);
+    dequantize_q8_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, d, out, rows, K);
     LB_LAUNCH_CHECK();
 }
 
@@ -70,87 +100,130 @@ __device__ __forceinline__ void unpack4(uint32_t w, float f[4]) {
     f[2] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - 8388736.0f;
     f[3] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - 8388736.0f;
 }
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
-// Decode GEMV.  One warp per output row (or per w1/w3 row pair); a lane owns 4 consecutive weights
-// per step (one coalesced 128-byte warp request of int8 against one coalesced 512-byte request of
-// FP32 activations — the activations are the wider stream here), Q8_UNROLL requests in flight.
+// Decode GEMV over the interleaved layout.  A warp owns one row group (4 rows) of W1 (and of W3 for
+// SwiGLU), or — KSPLIT = 4, for matrices with few rows — a quarter of its K range, the four warps of a
+// block then combining through shared memory.  Per step a lane issues one 128-bit weight load (4 rows x
+// 4 weights), one 128-bit scale load and one 128-bit activation load per column; Q8_UNROLL steps in flight.
 constexpr int Q8_WARPS = 4;
-constexpr int Q8_UNROLL = 8;
+constexpr int Q8_UNROLL = 4;
 
-template <int NC, bool SWIGLU>
+template <int NC, bool SWIGLU, int KSPLIT>
 __global__ void __launch_bounds__(Q8_WARPS * 32)
 gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
                const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
                float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
+    constexpr int NM = SWIGLU ? 2 : 1;
+    __shared__ float part[KSPLIT > 1 ? Q8_WARPS : 1][NM][4][NC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t row = blockIdx.x * Q8_WARPS + warp;
-    if (row >= M) return;
-    const uint32_t *q1 = reinterpret_cast<const uint32_t *>(Q1 + (size_t)row * K);
-    const float *d1 = D1 + (size_t)row * (K >> 5);
-    const uint32_t *q3 = SWIGLU ? reinterpret_cast<const uint32_t *>(Q3 + (size_t)row * K) : nullptr;
-    const float *d3 = SWIGLU ? D3 + (size_t)row * (K >> 5) : nullptr;
-    float a1[NC], a3[NC];
+    const uint32_t g = KSPLIT > 1 ? blockIdx.x : blockIdx.x * Q8_WARPS + warp;  // row group
+    const bool active = g < (M >> 2);
+    const uint32_t K4 = K >> 2, KB = K >> 5;
+    // this warp's k4 range
+    const uint32_t per = KSPLIT > 1 ? ((K4 / KSPLIT + 31) & ~31u) : K4;
+    const uint32_t k4_begin = KSPLIT > 1 ? min(warp * per, K4) : 0, k4_end = KSPLIT > 1 ? min(k4_begin + per, K4) : K4;
+    const uint4 *q1 = reinterpret_cast<const uint4 *>(Q1) + (size_t)(active ? g : 0) * K4;
+    const float4 *d1 = reinterpret_cast<const float4 *>(D1) + (size_t)(active ? g : 0) * KB;
+    const uint4 *q3 = SWIGLU ? reinterpret_cast<const uint4 *>(Q3) + (size_t)(active ? g : 0) * K4 : nullptr;
+    const float4 *d3 = SWIGLU ? reinterpret_cast<const float4 *>(D3) + (size_t)(active ? g : 0) * KB : nullptr;
+    float acc[NM][4][NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) a1[c] = a3[c] = 0.f;
-    const uint32_t K4 = K >> 2;
-    uint32_t w1[Q8_UNROLL], w3[Q8_UNROLL];
-    float s1[Q8_UNROLL], s3[Q8_UNROLL];
+    for (int m = 0; m < NM; m++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) acc[m][r][c] = 0.f;
+
+    uint4 w[Q8_UNROLL][NM];
+    float4 s[Q8_UNROLL][NM];
     auto load_batch = [&](uint32_t kk) {
 #pragma unroll
         for (int u = 0; u < Q8_UNROLL; u++) {
-            uint32_t k4 = kk + u * 32;
-            bool ok = k4 < K4;
-            w1[u] = ok ? __ldg(q1 + k4) : 0x0u;
-            s1[u] = ok ? __ldg(d1 + (k4 >> 3)) : 0.f;
+            const uint32_t k4 = kk + u * 32;
+            const bool ok = active && k4 < k4_end;
+            w[u][0] = ok ? ld_stream_u4(q1 + k4) : make_uint4(0x80808080u ^ 0x80808080u, 0, 0, 0);
+            s[u][0] = ok ? __ldg(d1 + (k4 >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (SWIGLU) {
-                w3[u] = ok ? __ldg(q3 + k4) : 0x0u;
-                s3[u] = ok ? __ldg(d3 + (k4 >> 3)) : 0.f;
+                w[u][NM - 1] = ok ? ld_stream_u4(q3 + k4) : make_uint4(0, 0, 0, 0);
+                s[u][NM - 1] = ok ? __ldg(d3 + (k4 >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
     };
     pdl_launch_dependents();
-    load_batch(lane);  // weights and scales are read-only: issue them before waiting on the predecessor grid (PDL)
+    load_batch(k4_begin + lane);  // read-only weights first, then wait for the predecessor grid (PDL)
     pdl_wait();
-    for (uint32_t kk = lane; kk < K4;) {
+    for (uint32_t kk = k4_begin + lane; kk < k4_end;) {
 #pragma unroll
         for (int u = 0; u < Q8_UNROLL; u++) {
-            uint32_t k4 = kk + u * 32;
-            if (k4 < K4) {
-                float f1[4], f3[4];
-                unpack4(w1[u], f1);
+            const uint32_t k4 = kk + u * 32;
+            if (k4 < k4_end) {
+                float4 xv[NC];
 #pragma unroll
-                for (int i = 0; i < 4; i++) f1[i] = __fmul_rn(s1[u], f1[i]);
-                if (SWIGLU) {
-                    unpack4(w3[u], f3);
+                for (int c = 0; c < NC; c++) xv[c] = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) f3[i] = __fmul_rn(s3[u], f3[i]);
-                }
+                for (int m = 0; m < NM; m++) {
+                    const uint32_t wr[4] = {w[u][m].x, w[u][m].y, w[u][m].z, w[u][m].w};
+                    const float sr[4] = {s[u][m].x, s[u][m].y, s[u][m].z, s[u][m].w};
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
-                    a1[c] = fmaf(f1[0], xv.x, a1[c]); a1[c] = fmaf(f1[1], xv.y, a1[c]);
-                    a1[c] = fmaf(f1[2], xv.z, a1[c]); a1[c] = fmaf(f1[3], xv.w, a1[c]);
-                    if (SWIGLU) {
-                        a3[c] = fmaf(f3[0], xv.x, a3[c]); a3[c] = fmaf(f3[1], xv.y, a3[c]);
-                        a3[c] = fmaf(f3[2], xv.z, a3[c]); a3[c] = fmaf(f3[3], xv.w, a3[c]);
+                    for (int r = 0; r < 4; r++) {
+                        float f[4];
+                        unpack4(wr[r], f);
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            float t = f[0] * xv[c].x;
+                            t = fmaf(f[1], xv[c].y, t); t = fmaf(f[2], xv[c].z, t); t = fmaf(f[3], xv[c].w, t);
+                            acc[m][r][c] = fmaf(sr[r], t, acc[m][r][c]);
+                        }
                     }
                 }
             }
         }
         kk += 32 * Q8_UNROLL;
-        if (kk < K4) load_batch(kk);
+        if (kk < k4_end) load_batch(kk);
     }
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        a1[c] = warp_sum(a1[c]);
-        if (SWIGLU) a3[c] = warp_sum(a3[c]);
-    }
-    if (lane == 0) {
+    for (int m = 0; m < NM; m++)
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-            float v = SWIGLU ? __fmul_rn(silu_ref(a1[c]), a3[c]) : a1[c];
-            if (!SWIGLU && res) v = __fadd_rn(v, res[(size_t)c * ldy + row]);
-            y[(size_t)c * ldy + row] = v;
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) acc[m][r][c] = warp_sum(acc[m][r][c]);
+    if (KSPLIT > 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < NC; c++) part[warp][m][r][c] = acc[m][r][c];
+        }
+        __syncthreads();
+        if (warp != 0) return;
+#pragma unroll
+        for (int m = 0; m < NM; m++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float t = part[0][m][r][c];
+                    for (int wv = 1; wv < Q8_WARPS; wv++) t += part[wv][m][r][c];
+                    acc[m][r][c] = t;
+                }
+    }
+    if (lane == 0 && active) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t row = g * 4 + r;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                float v = SWIGLU ? __fmul_rn(silu_ref(acc[0][r][c]), acc[NM - 1][r][c]) : acc[0][r][c];
+                if (!SWIGLU && res) v = __fadd_rn(v, res[(size_t)c * ldy + row]);
+                y[(size_t)c * ldy + row] = v;
+            }
         }
     }
 }
@@ -159,9 +232,14 @@ template <bool SWIGLU>
 static void gemv_q8_dispatch(const int8_t *Q1, const float *D1, const int8_t *Q3, const float *D3, uint32_t M, uint32_t K,
                              const float *x, uint32_t ldx, uint32_t N, float *y, uint32_t ldy, const float *res, cudaStream_t st) {
     LB_CHECK(N >= 1 && N <= 8, "gemv_q8: N must be 1..8");
-    LB_CHECK((K & 31) == 0 && (ldx & 3) == 0, "gemv_q8: K must be a multiple of 32");
-    unsigned grid = (M + Q8_WARPS - 1) / Q8_WARPS;
-#define LB_Q8_CASE(n) case n: launch_pdl(gemv_q8_kernel<n, SWIGLU>, dim3(grid), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, D3, M, K, x, ldx, y, ldy, res); break;
+    LB_CHECK((K & 31) == 0 && (ldx & 3) == 0 && (M & 3) == 0, "gemv_q8: K must be a multiple of 32 and M of 4");
+    const uint32_t groups = M / 4;
+    const bool split = groups < 148u * 16u;  // few row groups (wo, w2): split K over the block's warps to fill the SMs
+#define LB_Q8_CASE(n)                                                                                                                   \
+    case n:                                                                                                                             \
+        if (split) launch_pdl(gemv_q8_kernel<n, SWIGLU, 4>, dim3(groups), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, D3, M, K, x, ldx, y, ldy, res); \
+        else launch_pdl(gemv_q8_kernel<n, SWIGLU, 1>, dim3((groups + Q8_WARPS - 1) / Q8_WARPS), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, D3, M, K, x, ldx, y, ldy, res); \
+        break;
     switch (N) { LB_Q8_CASE(1) LB_Q8_CASE(2) LB_Q8_CASE(3) LB_Q8_CASE(4) LB_Q8_CASE(5) LB_Q8_CASE(6) LB_Q8_CASE(7) default: LB_Q8_CASE(8) }
 #undef LB_Q8_CASE
 }
@@ -192,15 +270,16 @@ gemm_q8_kernel(const int8_t *__restrict__ Q, const float *__restrict__ D, uint32
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    const uint32_t KB = K >> 5;
     for (uint32_t k0 = 0; k0 < K; k0 += GK) {
-        {   // 128 rows x 16 int8: thread t -> row t/2, 8 weights at (t%2)*8
+        {   // 128 rows x 16 int8: thread t -> row t/2, 8 weights at (t%2)*8 (two 4-weight words of the interleaved layout)
             int r = tid >> 1, kq = (tid & 1) * 8;
             float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (m0 + r < M) {
-                const uint2 w = *reinterpret_cast<const uint2 *>(Q + (size_t)(m0 + r) * K + k0 + kq);
-                const float dd = D[(size_t)(m0 + r) * KB + ((k0 + kq) >> 5)];
-                unpack4(w.x, f); unpack4(w.y, f + 4);
+                const uint32_t row = m0 + r;
+                const uint32_t wa = *reinterpret_cast<const uint32_t *>(Q + q8_qoff(row, k0 + kq, K));
+                const uint32_t wb = *reinterpret_cast<const uint32_t *>(Q + q8_qoff(row, k0 + kq + 4, K));
+                const float dd = D[q8_doff(row, k0 + kq, K)];
+                unpack4(wa, f); unpack4(wb, f + 4);
 #pragma unroll
                 for (int i = 0; i < 8; i++) f[i] = __fmul_rn(dd, f[i]);
             }
@@ -244,7 +323,7 @@ gemm_q8_kernel(const int8_t *__restrict__ Q, const float *__restrict__ D, uint32
 }
 void gemm_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,
              uint32_t ldy, const float *residual, cudaStream_t st) {
-    LB_CHECK((K & 31) == 0 && (ldx & 3) == 0, "gemm_q8: K must be a multiple of 32");
+    LB_CHECK((K & 31) == 0 && (ldx & 3) == 0 && (M & 3) == 0, "gemm_q8: K must be a multiple of 32 and M of 4");
     if (!N || !M) return;
     dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN);
     gemm_q8_kernel<<<grid, 256, 0, st>>>(Q, D, M, K, X, ldx, N, Y, ldy, residual);

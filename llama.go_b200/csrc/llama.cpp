@@ -34,7 +34,7 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     LB_CHECK(hp.dim % 4 == 0, "model: dim must be a multiple of 4");
     LB_CHECK(layer_begin < layer_end && layer_end <= hp.layers, "model: bad layer range");
     LB_CHECK(wt == 0 || wt == 16, "model: weight type must be LB_TYPE_F32 or LB_TYPE_Q8_0");
-    if (q8()) LB_CHECK(hp.dim % 32 == 0 && hp.ff() % 32 == 0, "model: Q8_0 needs dim and ff to be multiples of 32");
+    if (q8()) LB_CHECK(hp.dim % 32 == 0 && hp.ff() % 32 == 0 && hp.vocab % 4 == 0, "model: Q8_0 needs dim and ff to be multiples of 32 and vocab of 4");
     LB_CUDA(cudaSetDevice(device));
     const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
     const size_t A = 64;  // floats: 256-byte alignment of every tensor
@@ -81,7 +81,7 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     if (has_head()) {
         norm = slab + o_norm; output = fptr(o_out); output8 = qmat(o_out);
         tensors["norm.weight"] = {norm, d, 2, 1.f, 0.1f, Q8Mat()};
-        tensors["output.weight"] = {output, V * d, 3, 0.f, sdd, output8};
+        tensors["output.weight"] = {output, V * d, 3, 0.f, sdd, output8, (uint32_t)d};
     }
     layers.resize(lo.size());
     for (size_t i = 0; i < lo.size(); i++) {
@@ -94,14 +94,14 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
         uint64_t base = 16ull * (il + 1);
         auto fq = [&](size_t rows_off) { return q8() ? nullptr : L.wqkv + rows_off; };
         tensors[p + "attention_norm.weight"] = {L.attention_norm, d, base + 0, 1.f, 0.1f, Q8Mat()};
-        tensors[p + "attention.wq.weight"] = {fq(0), d * d, base + 1, 0.f, sdd, qmat(lo[i].qkv, 0)};
-        tensors[p + "attention.wk.weight"] = {fq(d * d), d * d, base + 2, 0.f, sdd, qmat(lo[i].qkv, d * d)};
-        tensors[p + "attention.wv.weight"] = {fq(2 * d * d), d * d, base + 3, 0.f, sdd, qmat(lo[i].qkv, 2 * d * d)};
-        tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd, L.wo8};
+        tensors[p + "attention.wq.weight"] = {fq(0), d * d, base + 1, 0.f, sdd, qmat(lo[i].qkv, 0), (uint32_t)d};
+        tensors[p + "attention.wk.weight"] = {fq(d * d), d * d, base + 2, 0.f, sdd, qmat(lo[i].qkv, d * d), (uint32_t)d};
+        tensors[p + "attention.wv.weight"] = {fq(2 * d * d), d * d, base + 3, 0.f, sdd, qmat(lo[i].qkv, 2 * d * d), (uint32_t)d};
+        tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd, L.wo8, (uint32_t)d};
         tensors[p + "ffn_norm.weight"] = {L.ffn_norm, d, base + 5, 1.f, 0.1f, Q8Mat()};
-        tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd, L.w18};
-        tensors[p + "feed_forward.w2.weight"] = {L.w2, d * ff, base + 7, 0.f, sf, L.w28};
-        tensors[p + "feed_forward.w3.weight"] = {L.w3, ff * d, base + 8, 0.f, sdd, L.w38};
+        tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd, L.w18, (uint32_t)d};
+        tensors[p + "feed_forward.w2.weight"] = {L.w2, d * ff, base + 7, 0.f, sf, L.w28, (uint32_t)ff};
+        tensors[p + "feed_forward.w3.weight"] = {L.w3, ff * d, base + 8, 0.f, sdd, L.w38, (uint32_t)d};
     }
 }
 
@@ -135,7 +135,7 @@ void Model::set_tensor(const std::string &name, int dtype, const void *host, siz
         LB_CUDA(cudaMemcpy(tmp16, host, nbytes, cudaMemcpyHostToDevice));
         k::f16_to_f32(static_cast<const uint16_t *>(tmp16), dst, e.nelem, 0);
     }
-    if (quant) k::quantize_q8(dst, e.q8.q, e.q8.d, e.nelem, 0);
+    if (quant) k::quantize_q8(dst, e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
     LB_CUDA(cudaDeviceSynchronize());
     if (tmp16) cudaFree(tmp16);
     if (tmp32) cudaFree(tmp32);
@@ -150,7 +150,7 @@ void Model::get_tensor(const std::string &name, float *host, size_t nelem) {
     if (e.q8.q) {
         void *tmp = nullptr;
         LB_CUDA(cudaMalloc(&tmp, nelem * sizeof(float)));
-        k::dequantize_q8(e.q8.q, e.q8.d, static_cast<float *>(tmp), nelem, 0);
+        k::dequantize_q8(e.q8.q, e.q8.d, static_cast<float *>(tmp), (uint32_t)(nelem / e.cols), e.cols, 0);
         LB_CUDA(cudaMemcpy(host, tmp, nelem * sizeof(float), cudaMemcpyDeviceToHost));
         cudaFree(tmp);
     } else {
@@ -171,7 +171,7 @@ void Model::init_random(uint64_t seed) {
         float sscale = (float)((double)e.sigma / IH_STD);
         if (e.q8.q) {
             k::init_random(static_cast<float *>(tmp), e.nelem, seed, e.tid, e.mean, sscale, 0);
-            k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, e.nelem, 0);
+            k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
         } else {
             k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
         }

@@ -51,7 +51,7 @@ struct Model {
     std::vector<Layer> layers;  // index = global layer - layer_begin
     bool q8() const { return weight_type == 16; }
 
-    struct Entry { float *ptr; size_t nelem; uint64_t tid; float mean, sigma; Q8Mat q8; };
+    struct Entry { float *ptr; size_t nelem; uint64_t tid; float mean, sigma; Q8Mat q8; uint32_t cols = 0; };
     std::map<std::string, Entry> tensors;  // ggjt names (llama.go:826-861) owned by this stage
 
     Model(const HParams &hp, int device, uint32_t lb, uint32_t le, int weight_type);

@@ -147,7 +147,7 @@ LoadedModel load_ggjt(const std::string &path, int device, uint32_t layer_begin,
                 const float *quant_src = f32;
                 if (dtype == 1) k::f16_to_f32(static_cast<const uint16_t *>(dev_tmp), f32, nelem, cs);
                 else quant_src = static_cast<const float *>(dev_tmp);
-                if (e.q8.q) k::quantize_q8(quant_src, e.q8.q, e.q8.d, nelem, cs);
+                if (e.q8.q) k::quantize_q8(quant_src, e.q8.q, e.q8.d, (uint32_t)(nelem / e.cols), e.cols, cs);
                 LB_CUDA(cudaStreamSynchronize(cs));  // dev_tmp is reused by the next tensor
             }
             out.tensors_loaded++;
