@@ -109,9 +109,9 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
 // Decode GEMV over the interleaved layout.  A warp owns one row group (4 rows) of W1 (and of W3 for
 // SwiGLU), or — KSPLIT = 4, for matrices with few rows — a quarter of its K range, the four warps of a
 // block then combining through shared memory.  Per step a lane issues one 128-bit weight load (4 rows x
-// 4 weights), one 128-bit scale load and one 128-bit activation load per column; 4-8 steps in flight.
+// 4 weights), one 128-bit scale load and one 128-bit activation load per column; Q8_UNROLL steps in flight.
 constexpr int Q8_WARPS = 4;
-constexpr int Q8_UNROLL_MAX = 8;
+constexpr int Q8_UNROLL = 4;
 
 template <int NC, bool SWIGLU, int KSPLIT>
 __global__ void __launch_bounds__(Q8_WARPS * 32)
@@ -119,7 +119,6 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
                const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
                float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
     constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int Q8_UNROLL = (SWIGLU || NC > 2) ? 4 : Q8_UNROLL_MAX;  // 128-bit requests in flight per lane and matrix
     __shared__ float part[KSPLIT > 1 ? Q8_WARPS : 1][NM][4][NC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = KSPLIT > 1 ? blockIdx.x : blockIdx.x * Q8_WARPS + warp;  // row group
