@@ -51,7 +51,9 @@ def run_pipeline(args):
         return float(t.item())
 
     # ---- value: K pipelined steps, device timed, max over ranks
-    stage.decode(gen[:, :W], PROMPT_LEN)
+    stage.decode(gen[:, :W], PROMPT_LEN)      # warm-up: graphs captured, NCCL p2p channels connected
+    sync_all()
+    stage.decode(gen[:, :W], PROMPT_LEN)      # second warm-up pass (one run was seen 2x slow on a cold pair of GPUs)
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
