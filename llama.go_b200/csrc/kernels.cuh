@@ -131,6 +131,11 @@ void gemv_q8_swiglu(const int8_t *Q1, const float *D1, const int8_t *Q3, const f
                     const float *x, uint32_t ldx, uint32_t N, float *act, uint32_t ldy, cudaStream_t st);
 void gemm_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
              float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
+// prefill GEMM on tcgen05 with the Q8_0 dequantisation fused into the shared-memory stage (kernels_tc.cu)
+void gemm_q8_tc(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+                float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
+void gemm_q8_auto(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N,
+                  float *Y, uint32_t ldy, const float *residual, cudaStream_t st);
 
 }  // namespace k
 }  // namespace lb

@@ -16,6 +16,11 @@
 // (K = 256), then an accumulate warp-group adds that partial tile into FP32 registers (round to
 // nearest) while the MMA warp fills the other TMEM buffer.
 //
+// Q8_0 weights (template Q8 = true): the weight operand arrives as the int8 tile (4 KB) + its block
+// scales (512 B) by TMA from the 4-row-interleaved planes of kernels_q8.cu, and the transform warp-group
+// DEQUANTISES IN THE SHARED-MEMORY STAGE: v = f32(d*q) is written as the hi operand and v - trunc(v)
+// as the lo operand, both at the 128-byte-swizzled K-major positions the MMA descriptors expect.
+//
 // Warp roles (320 threads, 1 CTA per SM, one 128x128 output tile per CTA):
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
@@ -43,7 +48,9 @@ constexpr int TC_THREADS = 320;
 constexpr int TC_CHUNK_KB = 8;  // k-blocks (of 32) summed inside TMEM before promotion to registers
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
-constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // raw + lo for A and B
+constexpr uint32_t TC_Q_BYTES = TC_BM * TC_BK;              // int8 weight tile (Q8 mode): 32 row groups x 128 B
+constexpr uint32_t TC_D_BYTES = (TC_BM / 4) * 16;           // its scales: one float4 per row group
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_Q_BYTES + 1024;  // raw + lo for A and B, q tile, scales (padded)
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -131,8 +138,19 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// unpack 4 int8 (see kernels_q8.cu): exact, avoids the I2F pipe
+__device__ __forceinline__ void tc_unpack4(uint32_t w, float f[4]) {
+    const uint32_t u = w ^ 0x80808080u;
+    f[0] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7650)) - 8388736.0f;
+    f[1] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7651)) - 8388736.0f;
+    f[2] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7652)) - 8388736.0f;
+    f[3] = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7653)) - 8388736.0f;
+}
+
+template <bool Q8>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, float *__restrict__ Y,
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD,
+                   const __grid_constant__ CUtensorMap tmX, float *__restrict__ Y,
                    uint32_t ldy, const float *__restrict__ res, uint32_t M, uint32_t N, uint32_t K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B atoms need 1024-byte alignment
@@ -149,6 +167,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     auto a_lo = [&](int s) { return base + s * TC_STAGE_BYTES + TC_A_BYTES; };
     auto b_raw = [&](int s) { return base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES; };
     auto b_lo = [&](int s) { return base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + TC_B_BYTES; };
+    auto q_tile = [&](int s) { return base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES; };
+    auto d_tile = [&](int s) { return base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_Q_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
@@ -179,8 +199,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1;
                 mbar_wait(empty(s), ph ^ 1);
-                mbar_expect_tx(full_raw(s), TC_A_BYTES + TC_B_BYTES);
-                tma_load_2d(a_raw(s), &tmW, full_raw(s), (int)(kb * TC_BK), (int)m0);
+                if (Q8) {
+                    mbar_expect_tx(full_raw(s), TC_Q_BYTES + TC_D_BYTES + TC_B_BYTES);
+                    tma_load_2d(q_tile(s), &tmW, full_raw(s), (int)(kb * TC_BK * 4), (int)(m0 / 4));  // 128 B per row group
+                    tma_load_2d(d_tile(s), &tmD, full_raw(s), (int)(kb * 4), (int)(m0 / 4));           // one float4 per row group
+                } else {
+                    mbar_expect_tx(full_raw(s), TC_A_BYTES + TC_B_BYTES);
+                    tma_load_2d(a_raw(s), &tmW, full_raw(s), (int)(kb * TC_BK), (int)m0);
+                }
                 tma_load_2d(b_raw(s), &tmX, full_raw(s), (int)(kb * TC_BK), (int)n0);
             }
         }
@@ -226,10 +252,35 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             const float4 *br = reinterpret_cast<const float4 *>(base_ptr + s * TC_STAGE_BYTES + 2 * TC_A_BYTES);
             float4 *bl = reinterpret_cast<float4 *>(base_ptr + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + TC_B_BYTES);
             auto lo = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+            if (Q8) {
+                // dequantise in the shared-memory stage: 256 vectors (row group g, k4) of 4 rows x 4 int8
+                const uint4 *qt = reinterpret_cast<const uint4 *>(base_ptr + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES);
+                const float4 *dt = reinterpret_cast<const float4 *>(base_ptr + s * TC_STAGE_BYTES + 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_Q_BYTES);
+                float4 *ah = reinterpret_cast<float4 *>(base_ptr + s * TC_STAGE_BYTES);
 #pragma unroll
-            for (int i = 0; i < (int)(TC_A_BYTES / 16 / 128); i++) {
-                float4 v = ar[t + i * 128];
-                al[t + i * 128] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+                for (int i = 0; i < 2; i++) {
+                    const int vec = t + i * 128, g = vec >> 3, k4 = vec & 7;
+                    const uint4 w = qt[vec];
+                    const float4 sc = dt[g];
+                    const uint32_t wr[4] = {w.x, w.y, w.z, w.w};
+                    const float sr[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++) {
+                        float f[4];
+                        tc_unpack4(wr[rr], f);
+                        const float4 v = make_float4(__fmul_rn(sr[rr], f[0]), __fmul_rn(sr[rr], f[1]), __fmul_rn(sr[rr], f[2]), __fmul_rn(sr[rr], f[3]));
+                        const int row = g * 4 + rr;
+                        const int off = row * 8 + (k4 ^ (row & 7));  // float4 index inside the 128-byte-swizzled K-major tile
+                        ah[off] = v;
+                        al[off] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < (int)(TC_A_BYTES / 16 / 128); i++) {
+                    float4 v = ar[t + i * 128];
+                    al[t + i * 128] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+                }
             }
 #pragma unroll
             for (int i = 0; i < (int)(TC_B_BYTES / 16 / 128); i++) {
@@ -310,24 +361,61 @@ static CUtensorMap make_map(const float *ptr, uint32_t rows, uint32_t cols, uint
     return m;
 }
 
+// generic 2-D tensor map: `cols` elements of `esz` bytes per row, row pitch `pitch_bytes`
+static CUtensorMap make_map_raw(const void *ptr, CUtensorMapDataType dt, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                                uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&m, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
 bool gemm_tf32x3_supported(uint32_t M, uint32_t K, uint32_t ldx, const float *W, const float *X) {
     (void)M;
     return K >= TC_BK && (K % TC_BK) == 0 && (ldx % 4) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)X % 16) == 0;
+}
+
+template <bool Q8>
+static void set_attr_once() {
+    static bool attr = false;
+    if (!attr) {
+        LB_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr = true;
+    }
 }
 
 void gemm_tf32x3(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y, uint32_t ldy,
                  const float *residual, cudaStream_t st) {
     LB_CHECK(gemm_tf32x3_supported(M, K, ldx, W, X), "gemm_tf32x3: unsupported shape (K must be a multiple of 32)");
     if (!M || !N) return;
-    static bool attr = false;
-    if (!attr) {
-        LB_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr = true;
-    }
+    set_attr_once<false>();
     CUtensorMap tmW = make_map(W, M, K, K, TC_BM);
     CUtensorMap tmX = make_map(X, N, K, ldx, TC_BN);
     dim3 grid((M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN);
-    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmW, tmX, Y, ldy, residual, M, N, K);
+    gemm_tf32x3_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmW, tmW, tmX, Y, ldy, residual, M, N, K);
+    LB_LAUNCH_CHECK();
+}
+
+// Q8_0 weights (4-row-interleaved planes of kernels_q8.cu): q plane = [M/4 row groups][K*4 bytes],
+// d plane = [M/4][K/32 float4]
+void gemm_q8_tc(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,
+                uint32_t ldy, const float *residual, cudaStream_t st) {
+    LB_CHECK(K >= TC_BK && K % TC_BK == 0 && M % 4 == 0 && ldx % 4 == 0 && (uintptr_t)Q % 16 == 0 && (uintptr_t)D % 16 == 0 &&
+                 (uintptr_t)X % 16 == 0, "gemm_q8_tc: unsupported shape");
+    if (!M || !N) return;
+    set_attr_once<true>();
+    CUtensorMap tmQ = make_map_raw(Q, CU_TENSOR_MAP_DATA_TYPE_UINT8, M / 4, (uint64_t)K * 4, (uint64_t)K * 4, TC_BK * 4, TC_BM / 4,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE);
+    CUtensorMap tmD = make_map_raw(D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M / 4, (uint64_t)(K / 32) * 4, (uint64_t)(K / 32) * 16, 4, TC_BM / 4,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE);
+    CUtensorMap tmX = make_map(X, N, K, ldx, TC_BN);
+    dim3 grid((M + TC_BM - 1) / TC_BM, (N + TC_BN - 1) / TC_BN);
+    gemm_tf32x3_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmD, tmX, Y, ldy, residual, M, N, K);
     LB_LAUNCH_CHECK();
 }
 
@@ -336,6 +424,12 @@ void gemm_auto(const float *W, uint32_t M, uint32_t K, const float *X, uint32_t 
     static const bool no_tc = getenv("LB_NO_TC") != nullptr;
     if (!no_tc && gemm_tf32x3_supported(M, K, ldx, W, X)) gemm_tf32x3(W, M, K, X, ldx, N, Y, ldy, residual, st);
     else gemm_f32(W, M, K, X, ldx, N, Y, ldy, residual, st);
+}
+void gemm_q8_auto(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,
+                  uint32_t ldy, const float *residual, cudaStream_t st) {
+    static const bool no_tc = getenv("LB_NO_TC") != nullptr;
+    if (!no_tc && K >= TC_BK && K % TC_BK == 0) gemm_q8_tc(Q, D, M, K, X, ldx, N, Y, ldy, residual, st);
+    else gemm_q8(Q, D, M, K, X, ldx, N, Y, ldy, residual, st);
 }
 
 }  // namespace k

@@ -272,7 +272,7 @@ static void matmul(const float *W, const Q8Mat &W8, uint32_t M, uint32_t K, cons
                    float *Y, uint32_t ldy, const float *res, cudaStream_t st) {
     if (W8.q) {
         if (N <= 8) k::gemv_q8(W8.q, W8.d, M, K, X, ldx, N, Y, ldy, res, st);
-        else k::gemm_q8(W8.q, W8.d, M, K, X, ldx, N, Y, ldy, res, st);
+        else k::gemm_q8_auto(W8.q, W8.d, M, K, X, ldx, N, Y, ldy, res, st);
     } else {
         if (N <= 8) k::gemv_f32(W, M, K, X, ldx, N, Y, ldy, res, st);
         else k::gemm_auto(W, M, K, X, ldx, N, Y, ldy, res, st);
