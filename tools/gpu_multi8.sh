@@ -24,8 +24,5 @@ except Exception as e: print('   parse failed', e); print(open('${f%.json}.err')
 }
 run 8 7b 512 100
 run 4 7b 512 100
-run 2 7b 512 100
 run 8 65b 2048 40
 run 4 13b 512 60
-run 2 13b 512 60
-run 1 13b 512 60
