@@ -121,6 +121,14 @@ LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint
 LB_API float *lb_context_hidden_buffer(lb_context *c);   /* device [max_batch][dim] scratch for hand-offs */
 LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
 
+/* ---- tokenizer: ml.Tokenize (pkg/ml/ml.go:2761-2848) on the host; works without a GPU ---- */
+typedef struct lb_vocab lb_vocab;                                  /* = ml.Vocab (ml.go:2653-2657) */
+LB_API lb_vocab *lb_vocab_create(uint32_t size);
+LB_API void      lb_vocab_free(lb_vocab *v);
+LB_API int       lb_vocab_set(lb_vocab *v, uint32_t id, const char *bytes, uint32_t len, float score);
+/* returns the number of ids (may exceed cap; only min(count, cap) are written), or -1 on bad arguments */
+LB_API int64_t   lb_tokenize(const lb_vocab *v, const char *text, uint32_t len, int bos, uint32_t *out, uint32_t cap);
+
 /* ---- pod batching: the reference runs --pods concurrent jobs, one llama.Context each, on one
  * shared Model (pkg/server/server.go:84-106,151-175).  Their single-token Evals are evaluated here as ONE
  * pass over the weights (B-column MulMat); every pod keeps its own KV cache and position. ---- */

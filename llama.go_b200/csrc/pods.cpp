@@ -15,7 +15,6 @@ PodBatch::PodBatch(const std::vector<Context *> &cs) : ctxs(cs) {
     model = cs[0]->model;
     ctx_size = cs[0]->ctx_size;
     LB_CHECK(model->has_embedding() && model->has_head(), "pod batch: needs a single-stage model");
-    LB_CHECK(!model->q8() || true, "");
     for (Context *c : cs) {
         LB_CHECK(c->model == model, "pod batch: contexts must share one model");
         LB_CHECK(c->ctx_size == ctx_size, "pod batch: contexts must have the same context size");

@@ -131,6 +131,33 @@ def SoftMax(ctx, a): return _t(ctx, lib().lb_soft_max(ctx._h, a._h))
 def Silu(ctx, a): return _t(ctx, lib().lb_silu(ctx._h, a._h))
 
 
+class Vocab:
+    """ml.Vocab (ml.go:2653-2657): tokens as bytes, with scores.  Host only (no GPU needed)."""
+
+    def __init__(self, tokens, scores=None):
+        self.tokens = [bytes(t) for t in tokens]
+        self._h = check_ptr(lib().lb_vocab_create(len(self.tokens)))
+        for i, t in enumerate(self.tokens):
+            check(lib().lb_vocab_set(self._h, i, t, len(t), float(scores[i]) if scores is not None else 0.0))
+
+    def __del__(self):
+        try:
+            lib().lb_vocab_free(self._h)
+        except Exception:
+            pass
+
+
+def Tokenize(vocab: Vocab, text, bos: bool = True):
+    """ml.Tokenize (ml.go:2761-2848)."""
+    raw = text.encode() if isinstance(text, str) else bytes(text)
+    cap = len(raw) + 2
+    out = (C.c_uint32 * cap)()
+    n = lib().lb_tokenize(vocab._h, raw, len(raw), 1 if bos else 0, out, cap)
+    if n < 0:
+        raise LlamaB200Error("lb_tokenize: bad arguments")
+    return list(out[:n])
+
+
 class Graph:
     """ml.Graph (ml.go:31-45)."""
 

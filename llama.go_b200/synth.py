@@ -204,6 +204,20 @@ def byte_vocab(vocab_size: int):
     return toks
 
 
+def merge_vocab(vocab_size: int):
+    """A vocab WITH merges, to exercise ml.Tokenize's bigram queue (ml.go:2739-2821): ids 3.. hold
+    pieces and their scores (ties included); the rest is filled like byte_vocab().  No piece contains a
+    space, newline or '%', so the CLI's printed stream stays intact (see byte_vocab)."""
+    pieces = [(b"he", -1.0), (b"ll", -2.0), (b"hell", -3.0), (b"hello", -2.5), (b"lo", -2.0), (b"wo", -4.0), (b"rl", -4.0),
+              (b"wor", -5.0), (b"ld", -3.5), (b"world", -1.5), (b"th", -0.5), (b"the", -0.75), (b"el", -2.0), (b"or", -4.0),
+              (b"h", -9.0), (b"e", -9.0), (b"l", -9.0), (b"o", -9.0), (b"helloworld", -0.1), (b"ow", -6.0)]
+    toks, scores = byte_vocab(vocab_size), [0.0] * vocab_size
+    for i, (p, sc) in enumerate(pieces):
+        toks[3 + i] = p
+        scores[3 + i] = sc
+    return toks, scores
+
+
 def prompt_token_ids(prompt: bytes):
     """Token ids the reference produces for `--prompt <prompt>` with byte_vocab():
     main.go:129 prepends one space, server.go:120 another, Tokenize adds BOS."""
@@ -211,16 +225,16 @@ def prompt_token_ids(prompt: bytes):
 
 
 # --------------------------------------------------------------------------- ggjt writer
-def write_ggjt(path: str, hp: HParams, tensors, vocab=None, f16: bool = False) -> None:
+def write_ggjt(path: str, hp: HParams, tensors, vocab=None, f16: bool = False, scores=None) -> None:
     """Write a ggjt v1 file.  `tensors` = iterable of (name, ndarray[out,in] or [n])."""
     vocab = vocab if vocab is not None else byte_vocab(hp.vocab)
     with open(path, "wb") as f:
         f.write(struct.pack("<9I", GGJT_MAGIC, GGJT_VERSION, hp.vocab, hp.dim, hp.mult, hp.heads,
                             hp.layers, hp.dim // hp.heads, 1 if f16 else 0))
-        for tok in vocab:
+        for i, tok in enumerate(vocab):
             f.write(struct.pack("<I", len(tok)))
             f.write(tok)
-            f.write(struct.pack("<f", 0.0))
+            f.write(struct.pack("<f", 0.0 if scores is None else float(scores[i])))
         for name, arr in tensors:
             arr = np.ascontiguousarray(arr)
             nb = name.encode()

@@ -31,6 +31,8 @@ CASES = [
     ("hd128", (1024, 256, 64, 2, 3), 11, "The quick brown fox jumps over", 128, 24),
     ("wide3h", (768, 384, 128, 3, 2), 23, "abcde", 64, 16),  # 8-token prompt: the --avx edge (T>=8)
     ("long", (512, 128, 32, 4, 2), 5, "x" * 61, 160, 40),    # 64-token prompt, T up to 104
+    # vocab WITH merges: pins ml.Tokenize (csrc/tokenizer.cpp) to the reference through the generated stream
+    ("merges", (512, 64, 32, 2, 2), 13, "hello world the hell helloworld lower", 128, 16),
 ]
 
 
@@ -38,13 +40,23 @@ def main():
     O.build()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, hpt, seed, prompt, context, predict in CASES:
+        if only and name not in only:
+            continue
         hp = synth.HParams(*hpt)
-        vocab = synth.byte_vocab(hp.vocab)
-        ids = synth.prompt_token_ids(prompt.encode())
+        scores = None
+        if name == "merges":
+            from llama_go_b200 import ml
+            vocab, scores = synth.merge_vocab(hp.vocab)
+            # main.go:129 and server.go:120 each prepend one space; Tokenize adds BOS
+            ids = ml.Tokenize(ml.Vocab(vocab, scores), b"  " + prompt.encode(), True)
+        else:
+            vocab = synth.byte_vocab(hp.vocab)
+            ids = synth.prompt_token_ids(prompt.encode())
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, "m.bin")
-            synth.write_ggjt(path, hp, synth.synth_model(seed, hp), vocab)
+            synth.write_ggjt(path, hp, synth.synth_model(seed, hp), vocab, scores=scores)
             rec = {"hparams": list(hpt), "seed": seed, "prompt": prompt, "prompt_ids": ids,
                    "context": context, "predict": predict, "runs": {}}
             for mode, threads, avx in (("scalar", 1, False), ("avx", 4, True)):
