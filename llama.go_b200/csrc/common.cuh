@@ -5,6 +5,7 @@
 #include <atomic>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace lb {
 
@@ -36,6 +37,54 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
     } while (0)
 
 constexpr int kNumSMs = 148;
+
+// Owns device / pinned-host allocations, events and streams of one object and releases them in its
+// destructor — declared as the FIRST member, so an exception half-way through a constructor (e.g. an
+// out-of-memory cudaMalloc) does not leak what was already allocated.
+struct DeviceOwner {
+    int device = 0;
+    std::vector<void *> dev, pinned;
+    std::vector<cudaEvent_t> events;
+    std::vector<cudaStream_t> streams;
+    DeviceOwner() = default;
+    DeviceOwner(const DeviceOwner &) = delete;
+    DeviceOwner &operator=(const DeviceOwner &) = delete;
+    ~DeviceOwner() {
+        cudaSetDevice(device);
+        for (cudaStream_t s : streams) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        for (void *p : dev) cudaFree(p);
+        for (void *p : pinned) cudaFreeHost(p);
+    }
+    template <typename T>
+    T *dmalloc(size_t n, bool zero = true) {
+        void *p = nullptr;
+        const size_t bytes = (n ? n : 1) * sizeof(T);
+        LB_CUDA(cudaMalloc(&p, bytes));
+        dev.push_back(p);
+        if (zero) LB_CUDA(cudaMemset(p, 0, bytes));
+        return static_cast<T *>(p);
+    }
+    template <typename T>
+    T *hmalloc(size_t n) {
+        void *p = nullptr;
+        LB_CUDA(cudaMallocHost(&p, (n ? n : 1) * sizeof(T)));
+        pinned.push_back(p);
+        return static_cast<T *>(p);
+    }
+    cudaEvent_t event() {
+        cudaEvent_t e = nullptr;
+        LB_CUDA(cudaEventCreate(&e));
+        events.push_back(e);
+        return e;
+    }
+    cudaStream_t stream() {
+        cudaStream_t s = nullptr;
+        LB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        streams.push_back(s);
+        return s;
+    }
+};
 
 // Programmatic dependent launch (PDL): decode kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization so that kernel k+1's CTAs are scheduled into the

@@ -59,13 +59,11 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
         l.w1 = reserve_mat(ff * d); l.w3 = reserve_mat(ff * d); l.w2 = reserve_mat(d * ff);
     }
     slab_floats = total;
-    LB_CUDA(cudaMalloc(&slab, (total ? total : 1) * sizeof(float)));
-    LB_CUDA(cudaMemset(slab, 0, (total ? total : 1) * sizeof(float)));
+    mem.device = device;
+    slab = mem.dmalloc<float>(total);
     if (q8()) {
-        LB_CUDA(cudaMalloc(&qslab, qtotal ? qtotal : 1));
-        LB_CUDA(cudaMemset(qslab, 0, qtotal ? qtotal : 1));
-        LB_CUDA(cudaMalloc(&dslab, (dtotal ? dtotal : 1) * sizeof(float)));
-        LB_CUDA(cudaMemset(dslab, 0, (dtotal ? dtotal : 1) * sizeof(float)));
+        qslab = mem.dmalloc<int8_t>(qtotal);
+        dslab = mem.dmalloc<float>(dtotal);
     }
     auto fptr = [&](const MOff &o) { return q8() ? nullptr : slab + o.f; };
     auto qmat = [&](const MOff &o, size_t row_off_elems = 0) {
@@ -105,12 +103,7 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     }
 }
 
-Model::~Model() {
-    cudaSetDevice(device);
-    if (slab) cudaFree(slab);
-    if (qslab) cudaFree(qslab);
-    if (dslab) cudaFree(dslab);
-}
+Model::~Model() {}  // `mem` releases the slabs
 
 void Model::set_tensor(const std::string &name, int dtype, const void *host, size_t nbytes) {
     // LoadModel's tensor loop, llama.go:889-959: unknown names abort (:906-910); only F32 and F16
@@ -194,16 +187,12 @@ uint64_t Model::weight_bytes_per_token() const {
 Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     LB_CHECK(cs > 0, "context: ctx_size must be > 0");
     LB_CUDA(cudaSetDevice(m->device));
-    LB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    mem.device = m->device;
+    stream = mem.stream();
     const HParams &hp = m->hp;
     const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab, nl = m->layers.size();
     max_batch = cs;
-    auto dalloc = [&](size_t floats) {
-        void *p = nullptr;
-        LB_CUDA(cudaMalloc(&p, (floats ? floats : 1) * sizeof(float)));
-        LB_CUDA(cudaMemset(p, 0, (floats ? floats : 1) * sizeof(float)));
-        return static_cast<float *>(p);
-    };
+    auto dalloc = [&](size_t floats) { return mem.dmalloc<float>(floats); };
     kv_k = dalloc(nl * cs * d);
     kv_v = dalloc(nl * cs * d);
     x = dalloc((size_t)max_batch * d); y = dalloc((size_t)max_batch * d); cur = dalloc((size_t)max_batch * d);
@@ -212,15 +201,13 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     logits = dalloc(V);
     attn_scratch = dalloc(k::attention_decode_scratch_floats(hp.heads, hp.head_dim()));
     tokens_cap = max_batch + 4096;
-    LB_CUDA(cudaMalloc(&tokens_dev, tokens_cap * sizeof(uint32_t)));
-    LB_CUDA(cudaMemset(tokens_dev, 0, tokens_cap * sizeof(uint32_t)));
-    LB_CUDA(cudaMalloc(&state_dev, 2 * sizeof(uint32_t)));
-    LB_CUDA(cudaMemset(state_dev, 0, 2 * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&state_host, 2 * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&tokens_host, tokens_cap * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&logits_host, V * sizeof(float)));
-    LB_CUDA(cudaEventCreate(&ev0));
-    LB_CUDA(cudaEventCreate(&ev1));
+    tokens_dev = mem.dmalloc<uint32_t>(tokens_cap);
+    state_dev = mem.dmalloc<uint32_t>(2);
+    state_host = mem.hmalloc<uint32_t>(2);
+    tokens_host = mem.hmalloc<uint32_t>(tokens_cap);
+    logits_host = mem.hmalloc<float>(V);
+    ev0 = mem.event();
+    ev1 = mem.event();
     use_graph = getenv("LB_NO_GRAPH") == nullptr;  // profiling aid: plain launches instead of graph replay
     // persistent megakernel for N == 1 (FP32 weights, supported shapes); LB_NO_MEGA=1 keeps the per-op kernels
     // (Q8_0 models keep the per-op kernels: a Q8 variant of the megakernel's K-sliced phases was measured
@@ -233,14 +220,10 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
             ml[i] = {L.attention_norm, L.wqkv, L.wo, L.ffn_norm, L.w1, L.w3, L.w2,
                      kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d};
         }
-        LB_CUDA(cudaMalloc(&mega_layers_dev, nl * sizeof(k::MegaLayerHost)));
+        mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
-        LB_CUDA(cudaMalloc(&mega_barrier, (2 + 4 * nl) * sizeof(unsigned)));  // grid barrier + per-phase ticket counters
-        LB_CUDA(cudaMemset(mega_barrier, 0, (2 + 4 * nl) * sizeof(unsigned)));
-        if (getenv("LB_MEGA_TRACE")) {
-            LB_CUDA(cudaMalloc(&mega_trace, (nl * 13 + 5 * 148) * sizeof(unsigned long long)));
-            LB_CUDA(cudaMemset(mega_trace, 0, (nl * 13 + 5 * 148) * sizeof(unsigned long long)));
-        }
+        mega_barrier = mem.dmalloc<unsigned>(2 + 4 * nl);  // grid barrier + per-phase ticket counters
+        if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13 + 5 * 148);
     }
 }
 
@@ -249,22 +232,7 @@ Context::~Context() {
     if (stream) cudaStreamSynchronize(stream);
     if (decode_graph) cudaGraphExecDestroy(decode_graph);
     if (stage_graph) cudaGraphExecDestroy(stage_graph);
-    for (float *p : {kv_k, kv_v, x, y, cur, qkv, attn, act, up, logits, all_logits, attn_scratch})
-        if (p) cudaFree(p);
-    if (mega_layers_dev) cudaFree(mega_layers_dev);
-    if (mega_barrier) cudaFree(mega_barrier);
-    if (mega_trace) cudaFree(mega_trace);
-    if (tokens_dev) cudaFree(tokens_dev);
-    if (state_dev) cudaFree(state_dev);
-    if (ring_dev) cudaFree(ring_dev);
-    if (present_dev) cudaFree(present_dev);
-    if (ring_pos_dev) cudaFree(ring_pos_dev);
-    if (state_host) cudaFreeHost(state_host);
-    if (tokens_host) cudaFreeHost(tokens_host);
-    if (logits_host) cudaFreeHost(logits_host);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    // buffers, events and the stream are released by `mem`
 }
 
 // MulMat of a weight matrix: F32 or Q8_0 planes, GEMV (N <= 8) or GEMM
@@ -350,9 +318,7 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (model->has_head()) {
         if (all_rows) {
-            if (!all_logits) {
-                LB_CUDA(cudaMalloc(&all_logits, (size_t)max_batch * V * sizeof(float)));
-            }
+            if (!all_logits) all_logits = mem.dmalloc<float>((size_t)max_batch * V, false);
             k::rms_norm(x, model->norm, cur, d, n, st);
             matmul(model->output, model->output8, V, d, cur, d, n, all_logits, V, nullptr, st);
         } else {
@@ -509,9 +475,9 @@ void Context::generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_
     LB_CHECK(temp > 0.f, "generate_greedy : temp must be > 0 (the reference replaces 0 by 0.5, main.go:379-381)");
     LB_CUDA(cudaSetDevice(model->device));
     if (!ring_dev) {
-        LB_CUDA(cudaMalloc(&ring_dev, ctx_size * sizeof(uint32_t)));
-        LB_CUDA(cudaMalloc(&present_dev, hp.vocab * sizeof(uint32_t)));
-        LB_CUDA(cudaMalloc(&ring_pos_dev, sizeof(uint32_t)));
+        ring_dev = mem.dmalloc<uint32_t>(ctx_size);
+        present_dev = mem.dmalloc<uint32_t>(hp.vocab);
+        ring_pos_dev = mem.dmalloc<uint32_t>(1);
     }
     // ring of the last ctx_size ids: zeros, then the prompt (server.go:127-138, 190)
     std::vector<uint32_t> ring(ctx_size, 0u), present(hp.vocab, 0u);

@@ -35,6 +35,7 @@ struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] mat
 
 // llama.Model (llama.go:181-193) for one pipeline stage: layers [layer_begin, layer_end).
 struct Model {
+    DeviceOwner mem;  // first member: owns the weight slabs
     HParams hp;
     int device = 0;
     uint32_t layer_begin = 0, layer_end = 0;
@@ -66,6 +67,7 @@ struct Model {
 
 // llama.Context (llama.go:83-113): FP32 KV cache in HBM + activations + stream + decode graph.
 struct Context {
+    DeviceOwner mem;  // first member: owns every buffer, event and the stream below
     Model *model;
     uint32_t ctx_size;
     cudaStream_t stream = nullptr;
@@ -121,6 +123,7 @@ struct Context {
 // Pod batching (pods.cpp): B contexts ("pods") of one model decode one token each per step
 // in a single pass over the weights.
 struct PodBatch {
+    DeviceOwner mem;  // first member: owns every buffer, event and the stream below
     static constexpr uint32_t kTokensCap = 4096;
     std::vector<Context *> ctxs;
     Model *model = nullptr;

@@ -24,49 +24,33 @@ PodBatch::PodBatch(const std::vector<Context *> &cs) : ctxs(cs) {
     const HParams &hp = model->hp;
     const size_t d = hp.dim, ff = hp.ff(), V = hp.vocab;
     LB_CUDA(cudaSetDevice(model->device));
-    LB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    auto dalloc = [&](size_t floats) {
-        void *p = nullptr;
-        LB_CUDA(cudaMalloc(&p, floats * sizeof(float)));
-        LB_CUDA(cudaMemset(p, 0, floats * sizeof(float)));
-        return static_cast<float *>(p);
-    };
+    mem.device = model->device;
+    stream = mem.stream();
+    auto dalloc = [&](size_t floats) { return mem.dmalloc<float>(floats); };
     x = dalloc(B * d); y = dalloc(B * d); cur = dalloc(B * d); qkv = dalloc(B * 3 * d); attn = dalloc(B * d);
     act = dalloc(B * ff); logits = dalloc(B * V);
     attn_scratch = dalloc(B * k::attention_decode_scratch_floats(hp.heads, hp.head_dim()));
     std::vector<float *> kb(B), vb(B);
     for (uint32_t b = 0; b < B; b++) { kb[b] = cs[b]->kv_k; vb[b] = cs[b]->kv_v; }
-    LB_CUDA(cudaMalloc(&kb_dev, B * sizeof(float *)));
-    LB_CUDA(cudaMalloc(&vb_dev, B * sizeof(float *)));
+    kb_dev = mem.dmalloc<float *>(B, false);
+    vb_dev = mem.dmalloc<float *>(B, false);
     LB_CUDA(cudaMemcpy(kb_dev, kb.data(), B * sizeof(float *), cudaMemcpyHostToDevice));
     LB_CUDA(cudaMemcpy(vb_dev, vb.data(), B * sizeof(float *), cudaMemcpyHostToDevice));
-    LB_CUDA(cudaMalloc(&pasts_dev, 8 * sizeof(uint32_t)));
-    LB_CUDA(cudaMalloc(&state_dev, 2 * sizeof(uint32_t)));
-    LB_CUDA(cudaMalloc(&tokens_dev, (size_t)B * kTokensCap * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&tokens_host, (size_t)B * kTokensCap * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&pasts_host, 10 * sizeof(uint32_t)));
-    LB_CUDA(cudaMallocHost(&logits_host, B * V * sizeof(float)));
-    LB_CUDA(cudaEventCreate(&ev0));
-    LB_CUDA(cudaEventCreate(&ev1));
+    pasts_dev = mem.dmalloc<uint32_t>(8);
+    state_dev = mem.dmalloc<uint32_t>(2);
+    tokens_dev = mem.dmalloc<uint32_t>((size_t)B * kTokensCap);
+    tokens_host = mem.hmalloc<uint32_t>((size_t)B * kTokensCap);
+    pasts_host = mem.hmalloc<uint32_t>(10);
+    logits_host = mem.hmalloc<float>(B * V);
+    ev0 = mem.event();
+    ev1 = mem.event();
 }
 
 PodBatch::~PodBatch() {
     cudaSetDevice(model->device);
     if (stream) cudaStreamSynchronize(stream);
     if (graph) cudaGraphExecDestroy(graph);
-    for (float *p : {x, y, cur, qkv, attn, act, logits, attn_scratch})
-        if (p) cudaFree(p);
-    if (kb_dev) cudaFree(kb_dev);
-    if (vb_dev) cudaFree(vb_dev);
-    if (pasts_dev) cudaFree(pasts_dev);
-    if (state_dev) cudaFree(state_dev);
-    if (tokens_dev) cudaFree(tokens_dev);
-    if (tokens_host) cudaFreeHost(tokens_host);
-    if (pasts_host) cudaFreeHost(pasts_host);
-    if (logits_host) cudaFreeHost(logits_host);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    // buffers, events and the stream are released by `mem`
 }
 
 static void mm(const float *W, const Q8Mat &W8, uint32_t M, uint32_t K, const float *X, uint32_t ldx, uint32_t N, float *Y,

@@ -29,6 +29,26 @@ def test_generate_greedy_reproduces_reference_binary_stream(synth, case):
     assert llama.GenerateGreedy(lctx, rec["prompt_ids"], rec["predict"]) == toks
 
 
+def test_tokenize_then_generate_reproduces_reference_binary_with_a_merge_vocab(synth):
+    """prompt TEXT -> lb_tokenize -> GPU generate: the whole server.Do job (server.go:113-176) for a vocab
+    with merges, against the stream the reference binary printed for the same prompt."""
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import llama, ml
+    from oracle import refbin
+    rec, _ = load_case("merges")
+    hp = synth.HParams(*rec["hparams"])
+    vocab, scores = synth.merge_vocab(hp.vocab)
+    ids = ml.Tokenize(ml.Vocab(vocab, scores), b"  " + rec["prompt"].encode(), True)
+    assert ids == rec["prompt_ids"]
+    model = llama.Model(hp).load(synth.synth_model(rec["seed"], hp))
+    lctx = llama.NewContext(model, rec["context"])
+    toks = llama.GenerateGreedy(lctx, ids, rec["predict"])
+    assert toks == rec["oracle_tokens"]
+    expected = refbin.expected_text(vocab, ids, toks)
+    for mode in ("scalar", "avx"):
+        assert refbin.same_stream(bytes.fromhex(rec["runs"][mode]["text_hex"]), expected)
+
+
 def test_generate_greedy_argument_checks(synth):
     import llama_go_b200  # noqa: F401
     from llama_go_b200 import llama
