@@ -174,7 +174,7 @@ int lb_context_synchronize(lb_context *c) {
 }
 int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t past, const float *hidden_in_dev,
                   float *hidden_out_dev, float *logits_out) {
-    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->use_graph = false; c->c->eval(tokens, n, past, logits_out, false, hidden_in_dev, hidden_out_dev));
+    LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->eval(tokens, n, past, logits_out, false, hidden_in_dev, hidden_out_dev));
 }
 float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
 void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }

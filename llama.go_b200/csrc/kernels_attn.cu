@@ -132,24 +132,35 @@ attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ K
 
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < LANES) qv = *reinterpret_cast<const float4 *>(qh + lane * 4);
-    // ---- scores: warp w takes keys t0 + w, t0 + w + 4, ...; 4 keys in flight per warp
+    // ---- scores: warp w takes keys t0 + w, t0 + w + NW, ...; AU keys in flight per warp
     constexpr int NW = DEC_THREADS / 32;
-    for (uint32_t i = warp; i < nk; i += NW * 4) {
-        float4 kv[4];
+    constexpr int AU = 8;
+    for (uint32_t i = warp; i < nk; i += NW * AU) {
+        float4 kv[AU];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < AU; u++) {
             uint32_t ii = i + u * NW;
             kv[u] = (ii < nk && lane < LANES) ? ld_stream_f4(kbase + (size_t)(t0 + ii) * dim + lane * 4)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < AU; u++) {
             uint32_t ii = i + u * NW;
             float d = kv[u].x * qv.x;
             d = fmaf(kv[u].y, qv.y, d); d = fmaf(kv[u].z, qv.z, d); d = fmaf(kv[u].w, qv.w, d);
             d = warp_sum(d);
             if (lane == 0 && ii < nk) sm[ii] = __fmul_rn(d, scale);
         }
+    }
+    // ---- the first AU V rows of this thread do not depend on the scores: fetch them now, under the softmax.
+    // Thread (kg, dl) takes keys kg, kg + KG, ... for the 4 dims of float4 lane dl.
+    constexpr int KG = DEC_THREADS / LANES;
+    const uint32_t kg = threadIdx.x / LANES, dl = threadIdx.x % LANES;
+    float4 vf[AU];
+#pragma unroll
+    for (int u = 0; u < AU; u++) {
+        const uint32_t key = kg + u * KG;
+        vf[u] = key < nk ? ld_stream_f4(vbase + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     // ---- local softmax statistics
@@ -181,31 +192,37 @@ attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ K
         part_ml[((size_t)h * S + sp) * 2 + 0] = m;
         part_ml[((size_t)h * S + sp) * 2 + 1] = t;
     }
-    // ---- partial P·V: DEC_THREADS/HD groups, thread (g, d) takes keys g, g+G, ... (8 loads in flight)
-    constexpr int G = DEC_THREADS / HD;
-    const uint32_t g = threadIdx.x / HD, d = threadIdx.x % HD;
-    float acc = 0.f;
-    {
-        const float *vp = vbase + d;
-        uint32_t i = g;
-        for (; i + 7 * G < nk; i += 8 * G) {
-            float v[8];
+    // ---- partial P·V: sequential over this thread's keys, then over the key groups (fixed order)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t base = 0; base < nk; base += KG * AU) {
+        if (base) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldg(vp + (size_t)(t0 + i + u * G) * dim);
-#pragma unroll
-            for (int u = 0; u < 8; u++) acc = fmaf(v[u], sm[i + u * G], acc);
+            for (int u = 0; u < AU; u++) {
+                const uint32_t key = base + kg + u * KG;
+                vf[u] = key < nk ? ld_stream_f4(vbase + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        for (; i < nk; i += G) acc = fmaf(__ldg(vp + (size_t)(t0 + i) * dim), sm[i], acc);
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const uint32_t key = base + kg + u * KG;
+            if (key < nk) {
+                const float sc = sm[key];
+                acc.x = fmaf(vf[u].x, sc, acc.x); acc.y = fmaf(vf[u].y, sc, acc.y);
+                acc.z = fmaf(vf[u].z, sc, acc.z); acc.w = fmaf(vf[u].w, sc, acc.w);
+            }
+        }
     }
-    if (G > 1) {
-        __shared__ float pv[DEC_THREADS];
+    {
+        __shared__ float4 pv[DEC_THREADS];  // [kg][dl]
         pv[threadIdx.x] = acc;
         __syncthreads();
         if (threadIdx.x < HD) {
-            for (int i = 1; i < G; i++) acc += pv[i * HD + threadIdx.x];
+            const float *pvf = reinterpret_cast<const float *>(pv);
+            float r = 0.f;
+            for (int i = 0; i < KG; i++) r += pvf[i * HD + threadIdx.x];
+            part_o[((size_t)h * S + sp) * HD + threadIdx.x] = r;
         }
     }
-    if (threadIdx.x < HD) part_o[((size_t)h * S + sp) * HD + threadIdx.x] = acc;
     // ---- ticket: the last CTA of this head merges
     __threadfence();
     __syncthreads();
@@ -213,17 +230,35 @@ attention_decode_kernel(const float *__restrict__ q, const float *__restrict__ K
     __syncthreads();
     if (s_ticket != S - 1) return;
     __threadfence();
-    float M = -INFINITY;
-    for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&part_ml[((size_t)h * S + s2) * 2]));
-    float L = 0.f, o = 0.f;
+    // Merge of the S <= 32 partials.  The statistics are fetched by S lanes at once and every thread's S partial
+    // outputs 8 at a time: a loop of dependent L2 reads (3 per split) cost ~0.4 us per split, more than the
+    // attention itself.  The accumulation order over the splits stays sequential, so the bits do not change.
+    __shared__ float s_w[DEC_MAX_SPLITS], s_l[DEC_MAX_SPLITS];
+    if (warp == 0) {
+        float ms = -INFINITY, ls = 0.f;
+        if ((uint32_t)lane < S) {
+            ms = __ldcg(&part_ml[((size_t)h * S + lane) * 2]);
+            ls = __ldcg(&part_ml[((size_t)h * S + lane) * 2 + 1]);
+        }
+        const float M = warp_max(ms);
+        // an empty split has m = -inf, l = 0, o = 0: its weight is exp(-inf) = 0 and it adds exact zeros
+        s_w[lane] = ls > 0.f ? (float)exp((double)__fsub_rn(ms, M)) : 0.f;
+        s_l[lane] = ls;
+    }
+    __syncthreads();
     if (threadIdx.x < HD) {
-        for (uint32_t s2 = 0; s2 < S; s2++) {
-            float ms = __ldcg(&part_ml[((size_t)h * S + s2) * 2]);
-            float ls = __ldcg(&part_ml[((size_t)h * S + s2) * 2 + 1]);
-            if (ls > 0.f) {
-                float w = (float)exp((double)__fsub_rn(ms, M));
-                L = fmaf(ls, w, L);
-                o = fmaf(__ldcg(&part_o[((size_t)h * S + s2) * HD + threadIdx.x]), w, o);
+        float L = 0.f, o = 0.f;
+        const float *po = part_o + (size_t)h * S * HD + threadIdx.x;
+        for (uint32_t s0 = 0; s0 < S; s0 += 8) {
+            float pv8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) pv8[u] = s0 + u < S ? __ldcg(po + (size_t)(s0 + u) * HD) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (s0 + u < S && s_l[s0 + u] > 0.f) {
+                    L = fmaf(s_l[s0 + u], s_w[s0 + u], L);
+                    o = fmaf(pv8[u], s_w[s0 + u], o);
+                }
             }
         }
         out[(size_t)h * HD + threadIdx.x] = __fmul_rn(o, __fdiv_rn(1.0f, L));

@@ -33,6 +33,8 @@ constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
+constexpr int MG_MAX_ITEMS = 2 * kNumSMs;  // attention items (head, split) per layer: <= 2 per CTA (decode_mega_splits)
+constexpr int MG_MAX_HEADS = 256;          // dim <= 8192 (largest K-slice variant), head dim >= 32
 // CTA-wide and half-CTA named barriers
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_THREADS) : "memory"); }
 __device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(MG_HALF) : "memory"); }
@@ -51,8 +53,10 @@ struct MegaShared {
     float bcast;
     float hbcast[2];
     unsigned ticket_slot[2];                // dynamic row-block tickets of the current GEMV phase
-    float pv[MG_THREADS];
+    float4 pv[MG_THREADS];                  // P·V partials: per half [key group][float4 lane of the head]
     double rope_cs[64][2];  // cos,sin(past * 10000^(-2j/hd)) for this token, j < hd/2 (once per launch)
+    // merge of the attention splits (P3 prologue): per (head, split) m, l, weight; per head 1/L
+    float mrg_m[MG_MAX_ITEMS], mrg_l[MG_MAX_ITEMS], mrg_w[MG_MAX_ITEMS], mrg_inv[MG_MAX_HEADS];
 };
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
@@ -239,7 +243,8 @@ template <int HD>
 __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaLayer &L, uint32_t past, MegaShared &sh, float *scores_all) {
     constexpr int LANES = HD / 4;
     constexpr int HW = MG_WARPS / 2;     // warps per half
-    constexpr int G = MG_HALF / HD;      // P·V groups per half
+    constexpr int KG = MG_HALF / LANES;  // P·V key groups per half: thread (kg, dl) takes keys kg, kg + KG, ... for 4 dims
+    constexpr int AU = 8;                // K rows per warp / V rows per thread in flight
     const int half = threadIdx.x / MG_HALF, ht = threadIdx.x % MG_HALF;
     const int hwarp = ht >> 5, lane = threadIdx.x & 31;
     const uint32_t dim = p.dim, S = p.splits, Tn = past + 1;
@@ -247,7 +252,8 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
     const uint32_t chunk = min((Tn + S - 1) / S, p.chunk_cap);
     const uint32_t items = p.heads * S;
     float *scores = scores_all + (size_t)half * p.chunk_cap;
-    float *pv = sh.pv + half * MG_HALF;
+    float4 *pv = sh.pv + half * MG_HALF;
+    const uint32_t kg = ht / LANES, dl = ht % LANES;
     for (uint32_t item = blockIdx.x * 2 + half; item < items; item += gridDim.x * 2) {
         const uint32_t h = item / S, sp = item % S;
         const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn), nk = t1 - t0;
@@ -276,22 +282,30 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
             }
         }
         hsync(half);  // the freshly stored K/V row is visible to this half (read back through L2)
-        // scores (MulMat K·Q, Scale): warp w takes keys w, w+HW, ... (4 keys in flight)
-        for (uint32_t i = hwarp; i < nk; i += HW * 4) {
-            float4 kk[4];
+        // scores (MulMat K·Q, Scale): warp w takes keys w, w+HW, ... (AU keys in flight: one HBM round trip for
+        // the 7B chunk of <= 57 keys)
+        for (uint32_t i = hwarp; i < nk; i += HW * AU) {
+            float4 kk[AU];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < AU; u++) {
                 const uint32_t ii = i + u * HW;
                 kk[u] = (ii < nk && lane < LANES) ? ldcg4(Kh + (size_t)(t0 + ii) * dim + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < AU; u++) {
                 const uint32_t ii = i + u * HW;
                 float dd = kk[u].x * qv.x;
                 dd = fmaf(kk[u].y, qv.y, dd); dd = fmaf(kk[u].z, qv.z, dd); dd = fmaf(kk[u].w, qv.w, dd);
                 dd = warp_sum(dd);
                 if (lane == 0 && ii < nk) scores[ii] = __fmul_rn(dd, scale);
             }
+        }
+        // the first AU V rows of this thread do not depend on the scores: fetch them now, under the softmax
+        float4 vf[AU];
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const uint32_t key = kg + u * KG;
+            vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         hsync(half);
         // local softmax statistics (SoftMax, ml.go:2472-2499, per split)
@@ -323,26 +337,32 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
             p.part_ml[((size_t)h * S + sp) * 2 + 0] = m;
             p.part_ml[((size_t)h * S + sp) * 2 + 1] = t;
         }
-        // partial P·V
-        const uint32_t g = ht / HD, d = ht % HD;
-        float acc = 0.f;
-        {
-            const float *vp = Vh + d;
-            uint32_t i = g;
-            for (; i + 7 * G < nk; i += 8 * G) {
-                float v[8];
+        // partial P·V: sequential over this thread's keys, then over the key groups (fixed order)
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t base = 0; base < nk; base += KG * AU) {
+            if (base) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = __ldcg(vp + (size_t)(t0 + i + u * G) * dim);
-#pragma unroll
-                for (int u = 0; u < 8; u++) acc = fmaf(v[u], scores[i + u * G], acc);
+                for (int u = 0; u < AU; u++) {
+                    const uint32_t key = base + kg + u * KG;
+                    vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-            for (; i < nk; i += G) acc = fmaf(__ldcg(vp + (size_t)(t0 + i) * dim), scores[i], acc);
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t key = base + kg + u * KG;
+                if (key < nk) {
+                    const float sc = scores[key];
+                    acc.x = fmaf(vf[u].x, sc, acc.x); acc.y = fmaf(vf[u].y, sc, acc.y);
+                    acc.z = fmaf(vf[u].z, sc, acc.z); acc.w = fmaf(vf[u].w, sc, acc.w);
+                }
+            }
         }
-        pv[ht] = acc;
+        pv[ht] = acc;  // [kg][dl]
         hsync(half);
         if (ht < HD) {
+            const float *pvf = reinterpret_cast<const float *>(pv);
             float r = 0.f;
-            for (int i = 0; i < G; i++) r += pv[i * HD + ht];
+            for (int i = 0; i < KG; i++) r += pvf[i * HD + ht];
             p.part_o[((size_t)h * S + sp) * HD + ht] = r;
         }
         hsync(half);  // scores / pv buffers are reused by the next item of this half
@@ -355,28 +375,57 @@ __device__ __forceinline__ void attention_phase(const MegaParams &p, const MegaL
 // reference's single-pass softmax; the merge weights use the FP32 expf — an f64 exp per lane and split
 // measured 8 us per layer here — while the softmax terms themselves keep the reference's f64 exp.)
 template <int V, int HD>
-__device__ __forceinline__ void merged_attention_slice(const MegaParams &p, float4 (&xs)[V]) {
+__device__ __forceinline__ void merged_attention_slice(const MegaParams &p, float4 (&xs)[V], MegaShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t KS = p.dim / MG_WARPS, S = p.splits;
+    const uint32_t KS = p.dim / MG_WARPS, S = p.splits, items = p.heads * S;
+    // Statistics first, by one thread per (head, split) and then per head, through shared memory; the partial
+    // outputs are then fetched 12 splits at a time.  (A per-lane loop "read m,l -> if l > 0 read O_s"
+    // is a chain of 2 dependent L2 round trips per split: 9 splits cost ~5 us per layer.)  The accumulation
+    // order over the splits is unchanged, so are the bits.
+    for (uint32_t i = threadIdx.x; i < items; i += MG_THREADS) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
+        sh.mrg_m[i] = ml.x;
+        sh.mrg_l[i] = ml.y;
+    }
+    csync();
+    for (uint32_t h = threadIdx.x; h < p.heads; h += MG_THREADS) {
+        float M = -INFINITY;
+        for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, sh.mrg_m[h * S + s2]);
+        float Lsum = 0.f;
+        for (uint32_t s2 = 0; s2 < S; s2++) {
+            const float l = sh.mrg_l[h * S + s2];
+            float wgt = 0.f;
+            if (l > 0.f) {
+                wgt = expf(__fsub_rn(sh.mrg_m[h * S + s2], M));
+                Lsum = fmaf(l, wgt, Lsum);
+            }
+            sh.mrg_w[h * S + s2] = wgt;
+        }
+        sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
+    }
+    csync();
+    constexpr int MB = 12;  // splits per batch of loads: 7B has 9 splits, 13B 7, 30B 5, 65B 4
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const uint32_t e = (j * 32 + lane) * 4;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < KS) {
             const uint32_t g = warp * KS + e, h = g / HD, d = g % HD;
-            float M = -INFINITY;
-            for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, __ldcg(&p.part_ml[((size_t)h * S + s2) * 2]));
-            float Lsum = 0.f;
-            for (uint32_t s2 = 0; s2 < S; s2++) {
-                const float2 ml = __ldcg(reinterpret_cast<const float2 *>(&p.part_ml[((size_t)h * S + s2) * 2]));
-                if (ml.y > 0.f) {
-                    const float wgt = expf(__fsub_rn(ml.x, M));
-                    const float4 po = ldcg4(&p.part_o[((size_t)h * S + s2) * HD + d]);
-                    Lsum = fmaf(ml.y, wgt, Lsum);
-                    o.x = fmaf(po.x, wgt, o.x); o.y = fmaf(po.y, wgt, o.y); o.z = fmaf(po.z, wgt, o.z); o.w = fmaf(po.w, wgt, o.w);
+            const float *po = p.part_o + (size_t)h * S * HD + d;
+            for (uint32_t s0 = 0; s0 < S; s0 += MB) {
+                float4 pv[MB];
+#pragma unroll
+                for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < MB; u++) {
+                    if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
+                        const float wgt = sh.mrg_w[h * S + s0 + u];
+                        o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
+                        o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+                    }
                 }
             }
-            const float inv = __fdiv_rn(1.0f, Lsum);
+            const float inv = sh.mrg_inv[h];
             o.x = __fmul_rn(o.x, inv); o.y = __fmul_rn(o.y, inv); o.z = __fmul_rn(o.z, inv); o.w = __fmul_rn(o.w, inv);
         }
         xs[j] = o;
@@ -433,7 +482,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         stamp(li, 5);
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
-            merged_attention_slice<VD, HD>(p, xs);
+            merged_attention_slice<VD, HD>(p, xs, sh);
             gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
         }
         stamp(li, 6);

@@ -405,7 +405,7 @@ void Context::eval(const uint32_t *tokens, uint32_t n, uint32_t past, float *log
     state_host[0] = past; state_host[1] = 0;
     LB_CUDA(cudaMemcpyAsync(state_dev, state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     const bool single_stage = model->has_embedding() && model->has_head();
-    if (n == 1 && !all_rows && single_stage && use_graph) {
+    if (n == 1 && !all_rows && single_stage && use_graph && !hidden_in && !hidden_out) {
         if (!decode_graph) {
             // first single-token eval runs eagerly (also sets kernel attributes), then capture
             forward(1, true, false, nullptr, nullptr);
