@@ -92,34 +92,37 @@ __device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1)
 template <int V>
 __device__ __forceinline__ void rms_slice(const float *x, const float *w, uint32_t K, float4 (&xs)[V], MegaShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double acc = 0.0;
-    for (uint32_t i = threadIdx.x * 4; i < K; i += MG_THREADS * 4) {
-        float4 v = ldcg4(x + i);
-        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
-        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) sh.red[warp] = acc;
-    csync();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < MG_WARPS; i++) t += sh.red[i];
-        sh.bcast = (float)(1.0 / sqrt(t / (double)K + 1e-5));
-    }
-    csync();
-    const float sc = sh.bcast;
     const uint32_t KS = K / MG_WARPS;
+    // The 16 warps' K-slices tile x exactly once, so the slice this thread keeps is also its share of the sum
+    // of squares: one L2 round trip instead of two.  f64 accumulation: per thread, per warp, then warps 0..15.
+    float4 v[V], ww[V];
 #pragma unroll
     for (int j = 0; j < V; j++) {
         const uint32_t e = (j * 32 + lane) * 4;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ww[j] = v[j];
         if (e < KS) {
-            float4 v = ldcg4(x + (size_t)warp * KS + e);
-            float4 ww = __ldg(reinterpret_cast<const float4 *>(w + (size_t)warp * KS + e));
-            xs[j].x = __fmul_rn(ww.x, __fmul_rn(v.x, sc)); xs[j].y = __fmul_rn(ww.y, __fmul_rn(v.y, sc));
-            xs[j].z = __fmul_rn(ww.z, __fmul_rn(v.z, sc)); xs[j].w = __fmul_rn(ww.w, __fmul_rn(v.w, sc));
-        } else {
-            xs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = ldcg4(x + (size_t)warp * KS + e);
+            ww[j] = __ldg(reinterpret_cast<const float4 *>(w + (size_t)warp * KS + e));
         }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        acc += (double)__fmul_rn(v[j].x, v[j].x); acc += (double)__fmul_rn(v[j].y, v[j].y);
+        acc += (double)__fmul_rn(v[j].z, v[j].z); acc += (double)__fmul_rn(v[j].w, v[j].w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.red[warp] = acc;  // (a grid barrier separates this from the previous use of sh.red)
+    csync();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < MG_WARPS; i++) t += sh.red[i];
+    const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        xs[j].x = __fmul_rn(ww[j].x, __fmul_rn(v[j].x, sc)); xs[j].y = __fmul_rn(ww[j].y, __fmul_rn(v[j].y, sc));
+        xs[j].z = __fmul_rn(ww[j].z, __fmul_rn(v[j].z, sc)); xs[j].w = __fmul_rn(ww[j].w, __fmul_rn(v[j].w, sc));
     }
 }
 
