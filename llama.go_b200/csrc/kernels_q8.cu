@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace lb {
 namespace k {
@@ -230,32 +231,21 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
     }
 }
 
-// The same GEMV with the weight / scale stream staged through a per-warp cp.async ring in shared memory.
-// Why: a Q8 matrix is 4x smaller than its FP32 twin, so every warp of the grid is resident at once and the
-// register-buffered loop above degenerates into (HBM latency + arithmetic) paid serially once per batch —
-// ~13 us of fixed cost on [12288 x 4096], which streams in 9 us.  Here a lane keeps S-1 steps (16 B of
-// weights + 16 B of scales each) in flight WITHOUT holding registers for them, the arithmetic of step i
-// overlaps the loads of steps i+1 .. i+S-1, and 70 KB per SM stay in flight with ~24 resident warps.
-// A lane only ever reads back the bytes it copied itself, so cp.async.wait_group is the only
-// synchronisation; k order and per-lane arithmetic are those of gemv_q8_kernel (bit-identical results).
-__device__ __forceinline__ void cp_async_cg16(void *smem, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_ca16(void *smem, const void *g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+// Double-buffered variant for 1-2 columns.  Every warp of these grids is resident at once and they start in
+// phase, so the loop above pays (HBM latency + its share of the issue slots) serially once per batch: ~13 us
+// of fixed cost on [12288 x 4096], which streams in 9 us.  Here the loads of batch i+1 are issued BEFORE the
+// arithmetic of batch i.  To afford two batches in registers the 4 rows' block scales are not loaded by every
+// lane (8 lanes share a block): lane j of each group of 8 loads the float4 of step j % U and the others
+// fetch it with 4 shuffles.  k order and per-lane arithmetic are those of gemv_q8_kernel: same bits.
+// (Rejected, profiles/README.md: a per-warp cp.async ring in shared memory — 1.5-2.5x slower.)
 template <int NC, bool SWIGLU, int KSPLIT>
 __global__ void __launch_bounds__(Q8_WARPS * 32)
-gemv_q8_async_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
-                     const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
-                     float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
+gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
+                  const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
+                  float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
     constexpr int NM = SWIGLU ? 2 : 1;
-    constexpr int S = (SWIGLU || KSPLIT > 1) ? 4 : 8;                     // ring stages (power of two); 16-32 KB per block
-    __shared__ __align__(16) uint4 ring[Q8_WARPS][S][2 * NM][32];         // [m] weights, [NM + m] scales; a lane's own column
+    constexpr int U = Q8_UNROLL / NM;  // steps per batch (same register budget for W1 and W1 + W3)
+    constexpr uint32_t STEP = 32 * U;
     __shared__ float part[KSPLIT > 1 ? Q8_WARPS : 1][NM][4][NC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = KSPLIT > 1 ? blockIdx.x : blockIdx.x * Q8_WARPS + warp;  // row group
@@ -263,11 +253,12 @@ gemv_q8_async_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1
     const uint32_t K4 = K >> 2, KB = K >> 5;
     const uint32_t per = KSPLIT > 1 ? ((K4 / KSPLIT + 31) & ~31u) : K4;
     const uint32_t k4_begin = KSPLIT > 1 ? min(warp * per, K4) : 0, k4_end = KSPLIT > 1 ? min(k4_begin + per, K4) : K4;
-    const uint32_t nsteps = active ? (k4_end - k4_begin + 31) >> 5 : 0;
     const uint4 *q1 = reinterpret_cast<const uint4 *>(Q1) + (size_t)(active ? g : 0) * K4;
     const float4 *d1 = reinterpret_cast<const float4 *>(D1) + (size_t)(active ? g : 0) * KB;
     const uint4 *q3 = SWIGLU ? reinterpret_cast<const uint4 *>(Q3) + (size_t)(active ? g : 0) * K4 : nullptr;
     const float4 *d3 = SWIGLU ? reinterpret_cast<const float4 *>(D3) + (size_t)(active ? g : 0) * KB : nullptr;
+    const uint32_t su = (lane & 7) % U;              // the step whose scales this lane loads
+    const uint32_t sq = (lane >> 3) * 8 + su * 32;   // k4 offset (within a batch) of that block's first lane
     float acc[NM][4][NC];
 #pragma unroll
     for (int m = 0; m < NM; m++)
@@ -276,53 +267,72 @@ gemv_q8_async_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1
 #pragma unroll
             for (int c = 0; c < NC; c++) acc[m][r][c] = 0.f;
 
-    auto issue = [&](uint32_t step) {  // exactly one commit group per call, possibly empty
-        const uint32_t k4 = k4_begin + step * 32 + lane;
-        if (step < nsteps && k4 < k4_end) {
-            uint4(*slot)[32] = ring[warp][step & (S - 1)];
-            cp_async_cg16(&slot[0][lane], q1 + k4);
-            cp_async_ca16(&slot[NM][lane], d1 + (k4 >> 3));
-            if (SWIGLU) {
-                cp_async_cg16(&slot[NM - 1][lane], q3 + k4);
-                cp_async_ca16(&slot[2 * NM - 1][lane], d3 + (k4 >> 3));
-            }
+    uint4 w[2][U][NM];
+    float4 s[2][NM];
+    auto load_batch = [&](auto bc, uint32_t kb0) {  // kb0 = k4 of lane 0 at step 0 of the batch (multiple of 32)
+        constexpr int b = decltype(bc)::value;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k4 = kb0 + u * 32 + lane;
+            const bool ok = active && k4 < k4_end;
+            w[b][u][0] = ok ? ld_stream_u4(q1 + k4) : make_uint4(0, 0, 0, 0);
+            if (SWIGLU) w[b][u][NM - 1] = ok ? ld_stream_u4(q3 + k4) : make_uint4(0, 0, 0, 0);
         }
-        cp_async_commit();
+        const uint32_t ks = kb0 + sq;  // first k4 of the block this lane fetches the scales of
+        const bool oks = active && ks < k4_end;
+        s[b][0] = oks ? __ldg(d1 + (ks >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SWIGLU) s[b][NM - 1] = oks ? __ldg(d3 + (ks >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    pdl_launch_dependents();
+    auto compute_batch = [&](auto bc, uint32_t kb0) {
+        constexpr int b = decltype(bc)::value;
 #pragma unroll
-    for (int st = 0; st < S - 1; st++) issue(st);  // read-only weights first, then wait for the predecessor grid (PDL)
-    pdl_wait();
-    for (uint32_t step = 0; step < nsteps; step++) {
-        issue(step + S - 1);   // refills the slot consumed in the previous iteration
-        cp_async_wait<S - 1>();  // this lane's copies of `step` have landed
-        const uint32_t k4 = k4_begin + step * 32 + lane;
-        if (k4 < k4_end) {
-            const uint4(*slot)[32] = ring[warp][step & (S - 1)];
-            float4 xv[NC];
+        for (int u = 0; u < U; u++) {
+            const uint32_t k4 = kb0 + u * 32 + lane;
+            const int src = (lane & ~7) | u;  // the lane of this group of 8 that holds step u's scales
+            float sr[NM][4];
 #pragma unroll
-            for (int c = 0; c < NC; c++) xv[c] = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
+            for (int m = 0; m < NM; m++) {  // shuffles outside the k4 predicate: all 32 lanes take part
+                sr[m][0] = __shfl_sync(0xffffffffu, s[b][m].x, src); sr[m][1] = __shfl_sync(0xffffffffu, s[b][m].y, src);
+                sr[m][2] = __shfl_sync(0xffffffffu, s[b][m].z, src); sr[m][3] = __shfl_sync(0xffffffffu, s[b][m].w, src);
+            }
+            if (k4 < k4_end) {
+                float4 xv[NC];
 #pragma unroll
-            for (int m = 0; m < NM; m++) {
-                const uint4 wv = slot[m][lane];
-                const uint4 sv = slot[NM + m][lane];
-                const uint32_t wr[4] = {wv.x, wv.y, wv.z, wv.w};
-                const float sr[4] = {__uint_as_float(sv.x), __uint_as_float(sv.y), __uint_as_float(sv.z), __uint_as_float(sv.w)};
+                for (int c = 0; c < NC; c++) xv[c] = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    float f[4];
-                    unpack4(wr[r], f);
+                for (int m = 0; m < NM; m++) {
+                    const uint32_t wr[4] = {w[b][u][m].x, w[b][u][m].y, w[b][u][m].z, w[b][u][m].w};
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        float t = f[0] * xv[c].x;
-                        t = fmaf(f[1], xv[c].y, t); t = fmaf(f[2], xv[c].z, t); t = fmaf(f[3], xv[c].w, t);
-                        acc[m][r][c] = fmaf(sr[r], t, acc[m][r][c]);
+                    for (int r = 0; r < 4; r++) {
+                        float f[4];
+                        unpack4(wr[r], f);
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            float t = f[0] * xv[c].x;
+                            t = fmaf(f[1], xv[c].y, t); t = fmaf(f[2], xv[c].z, t); t = fmaf(f[3], xv[c].w, t);
+                            acc[m][r][c] = fmaf(sr[m][r], t, acc[m][r][c]);
+                        }
                     }
                 }
             }
         }
+    };
+    using B0 = std::integral_constant<int, 0>;
+    using B1 = std::integral_constant<int, 1>;
+    pdl_launch_dependents();
+    uint32_t kb0 = k4_begin;  // warp-uniform
+    load_batch(B0{}, kb0);    // read-only weights first, then wait for the predecessor grid (PDL)
+    if (kb0 + STEP < k4_end) load_batch(B1{}, kb0 + STEP);
+    pdl_wait();
+    while (kb0 < k4_end) {
+        compute_batch(B0{}, kb0);
+        if (kb0 + 2 * STEP < k4_end) load_batch(B0{}, kb0 + 2 * STEP);
+        kb0 += STEP;
+        if (kb0 >= k4_end) break;
+        compute_batch(B1{}, kb0);
+        if (kb0 + 2 * STEP < k4_end) load_batch(B1{}, kb0 + 2 * STEP);
+        kb0 += STEP;
     }
-    cp_async_wait<0>();
 #pragma unroll
     for (int m = 0; m < NM; m++)
 #pragma unroll
@@ -365,18 +375,6 @@ gemv_q8_async_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1
     }
 }
 
-// the ring needs 6 blocks x 32 KB of shared memory per SM to keep [12288 x 4096] in one wave
-template <auto Kern>
-static void prefer_max_shared() {
-    static thread_local int done_for_device = -1;
-    int dev = 0;
-    LB_CUDA(cudaGetDevice(&dev));
-    if (done_for_device == dev) return;
-    LB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(Kern), cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared));
-    done_for_device = dev;
-}
-
 template <bool SWIGLU>
 static void gemv_q8_dispatch(const int8_t *Q1, const float *D1, const int8_t *Q3, const float *D3, uint32_t M, uint32_t K,
                              const float *x, uint32_t ldx, uint32_t N, float *y, uint32_t ldy, const float *res, cudaStream_t st) {
@@ -384,18 +382,23 @@ static void gemv_q8_dispatch(const int8_t *Q1, const float *D1, const int8_t *Q3
     LB_CHECK((K & 31) == 0 && (ldx & 3) == 0 && (M & 3) == 0, "gemv_q8: K must be a multiple of 32 and M of 4");
     const uint32_t groups = M / 4;
     const bool split = groups < 148u * 16u;  // few row groups (wo, w2): split K over the block's warps to fill the SMs
-    static const bool sync_loop = getenv("LB_Q8_SYNC") != nullptr;  // A/B aid: the register-buffered loop
+    static const bool sync_loop = getenv("LB_Q8_SYNC") != nullptr;  // A/B aid: the single-buffered loop for every N
 #define LB_Q8_LAUNCH(kern, n, ks)                                                                                                       \
     launch_pdl(kern<n, SWIGLU, ks>, dim3(ks > 1 ? groups : (groups + Q8_WARPS - 1) / Q8_WARPS), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, \
                D3, M, K, x, ldx, y, ldy, res)
-#define LB_Q8_CASE(n)                                                                                                                   \
+#define LB_Q8_CASE_DB(n)                                                                                                                \
     case n:                                                                                                                             \
         if (sync_loop) { if (split) LB_Q8_LAUNCH(gemv_q8_kernel, n, 4); else LB_Q8_LAUNCH(gemv_q8_kernel, n, 1); }                     \
-        else if (split) { prefer_max_shared<gemv_q8_async_kernel<n, SWIGLU, 4>>(); LB_Q8_LAUNCH(gemv_q8_async_kernel, n, 4); }         \
-        else { prefer_max_shared<gemv_q8_async_kernel<n, SWIGLU, 1>>(); LB_Q8_LAUNCH(gemv_q8_async_kernel, n, 1); }                    \
+        else { if (split) LB_Q8_LAUNCH(gemv_q8_db_kernel, n, 4); else LB_Q8_LAUNCH(gemv_q8_db_kernel, n, 1); }                         \
         break;
-    switch (N) { LB_Q8_CASE(1) LB_Q8_CASE(2) LB_Q8_CASE(3) LB_Q8_CASE(4) LB_Q8_CASE(5) LB_Q8_CASE(6) LB_Q8_CASE(7) default: LB_Q8_CASE(8) }
+#define LB_Q8_CASE(n)                                                                                                                   \
+    case n:                                                                                                                             \
+        if (split) LB_Q8_LAUNCH(gemv_q8_kernel, n, 4); else LB_Q8_LAUNCH(gemv_q8_kernel, n, 1);                                        \
+        break;
+    // 1-2 columns (single-sequence decode): double-buffered; 3-8 columns (pods) keep the registers for accumulators
+    switch (N) { LB_Q8_CASE_DB(1) LB_Q8_CASE_DB(2) LB_Q8_CASE(3) LB_Q8_CASE(4) LB_Q8_CASE(5) LB_Q8_CASE(6) LB_Q8_CASE(7) default: LB_Q8_CASE(8) }
 #undef LB_Q8_CASE
+#undef LB_Q8_CASE_DB
 #undef LB_Q8_LAUNCH
 }
 void gemv_q8(const int8_t *Q, const float *D, uint32_t M, uint32_t K, const float *x, uint32_t ldx, uint32_t N, float *y,
