@@ -335,7 +335,7 @@ def run_single_gpu(args):
         "config": {"workload": "LLaMA-%s %s single-sequence decode, context %d, %d-token prompt prefilled, past %d..%d"
                                % (args.model.upper(), "Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
                    "weights": "random-init (device RNG, seed 0) %.1f GB" % (model.weight_bytes_per_token / 1e9), "kv_cache": "fp32 in HBM",
-                   "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (26.4 GB weights per step)",
+                   "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (%.1f GB weights per step)" % (model.weight_bytes_per_token / 1e9),
                    "decode_path": "persistent cooperative megakernel, CUDA-graph replay" if mega else "per-op kernels + PDL, CUDA-graph replay",
                    "setup_s": round(t_setup, 1)},
         "clocks": clocks,
@@ -349,8 +349,10 @@ def run_single_gpu(args):
                       "note": "algorithmic bytes of one token (SURVEY 8d: weights + KV read/write + logits) / CUDA-event time per graph replay "
                               "(memset + megakernel + 1-thread state advance)"}
                      if mega else
-                     {"bound": "hbm", "kernel": "gemv_swiglu_kernel (w1,w3)", "achieved": dom["GB/s"], "peak": peak,
-                      "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4), "traffic": kernel_traffic("gemv_swiglu_kernel"),
+                     {"bound": "hbm", "kernel": ("gemv_q8_db_kernel<1, swiglu> (w1,w3)" if q8 else "gemv_swiglu_kernel (w1,w3)"),
+                      "achieved": dom["GB/s"], "peak": peak,
+                      "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4),
+                      "traffic": kernel_traffic("gemv_q8_db_kernel_swiglu" if q8 else "gemv_swiglu_kernel"),
                       "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]}),
         "step_roofline": {"bytes_per_token": int(bytes_per_token), "achieved_GBs": round(step_gbs, 1),
                           "frac": round(step_gbs / peak, 4), "roofline_tok_s": round(peak * 1e9 / bytes_per_token, 1)},

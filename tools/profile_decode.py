@@ -23,10 +23,11 @@ def main():
     ap.add_argument("--past", type=int, default=448, help="position the decode steps start at (KV beyond the prompt is zero)")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--ctx", type=int, default=512)
+    ap.add_argument("--weights", default="f32", choices=["f32", "q8"])
     a = ap.parse_args()
     hp = synth.HParams(32000, 4096, 256, 32, a.layers)
     lib = _capi.lib()
-    model = llama.Model(hp).init_random(0)
+    model = llama.Model(hp, weight_type=llama.LB_TYPE_Q8_0 if a.weights == "q8" else llama.LB_TYPE_F32).init_random(0)
     lctx = llama.NewContext(model, a.ctx)
     print("launches after init:", lib.lb_kernel_launches(), flush=True)
     rs = np.random.RandomState(0)
