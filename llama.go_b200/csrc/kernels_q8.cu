@@ -239,7 +239,7 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
 // fetch it with 4 shuffles.  k order and per-lane arithmetic are those of gemv_q8_kernel: same bits.
 // (Rejected, profiles/README.md: a per-warp cp.async ring in shared memory — 1.5-2.5x slower.)
 template <int NC, bool SWIGLU, int KSPLIT>
-__global__ void __launch_bounds__(Q8_WARPS * 32)
+__global__ void __launch_bounds__(Q8_WARPS * 32, (NC == 1 && !SWIGLU) ? 6 : 1)  // 6 blocks/SM: [12288 x 4096] is one wave
 gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
                   const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
                   float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
@@ -285,6 +285,16 @@ gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, c
     };
     auto compute_batch = [&](auto bc, uint32_t kb0) {
         constexpr int b = decltype(bc)::value;
+        // the batch's activation float4s first, back to back: loaded one step at a time, each step stalled on
+        // its own L1 round trip (48 % of the stall samples of the first capture, profiles/README.md)
+        float4 xv[U][NC];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k4 = kb0 + u * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                xv[u][c] = k4 < k4_end ? __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t k4 = kb0 + u * 32 + lane;
@@ -296,9 +306,6 @@ gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, c
                 sr[m][2] = __shfl_sync(0xffffffffu, s[b][m].z, src); sr[m][3] = __shfl_sync(0xffffffffu, s[b][m].w, src);
             }
             if (k4 < k4_end) {
-                float4 xv[NC];
-#pragma unroll
-                for (int c = 0; c < NC; c++) xv[c] = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
                     const uint32_t wr[4] = {w[b][u][m].x, w[b][u][m].y, w[b][u][m].z, w[b][u][m].w};
@@ -308,8 +315,8 @@ gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, c
                         unpack4(wr[r], f);
 #pragma unroll
                         for (int c = 0; c < NC; c++) {
-                            float t = f[0] * xv[c].x;
-                            t = fmaf(f[1], xv[c].y, t); t = fmaf(f[2], xv[c].z, t); t = fmaf(f[3], xv[c].w, t);
+                            float t = f[0] * xv[u][c].x;
+                            t = fmaf(f[1], xv[u][c].y, t); t = fmaf(f[2], xv[u][c].z, t); t = fmaf(f[3], xv[u][c].w, t);
                             acc[m][r][c] = fmaf(sr[m][r], t, acc[m][r][c]);
                         }
                     }
