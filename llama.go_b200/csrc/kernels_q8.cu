@@ -231,6 +231,13 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
     }
 }
 
+// Resident blocks per SM the double-buffered kernel is compiled for: its grids must fit in ONE wave
+// ([12288 x 4096] = 768 blocks -> 6 per SM; w1|w3 = 688 blocks -> 5; the K-split grids of 1024 blocks -> 7).
+// (A bare minimum of 1 makes ptxas spend registers freely: 128 instead of 96 and a second wave for w1|w3.)
+constexpr int q8_db_min_blocks(int nc, bool swiglu, int ksplit) {
+    return nc == 1 ? (swiglu ? 5 : (ksplit == 1 ? 6 : 7)) : ((nc == 2 && !swiglu) ? 5 : 4);
+}
+
 // Double-buffered variant for 1-2 columns.  Every warp of these grids is resident at once and they start in
 // phase, so the loop above pays (HBM latency + its share of the issue slots) serially once per batch: ~13 us
 // of fixed cost on [12288 x 4096], which streams in 9 us.  Here the loads of batch i+1 are issued BEFORE the
@@ -239,7 +246,7 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
 // fetch it with 4 shuffles.  k order and per-lane arithmetic are those of gemv_q8_kernel: same bits.
 // (Rejected, profiles/README.md: a per-warp cp.async ring in shared memory — 1.5-2.5x slower.)
 template <int NC, bool SWIGLU, int KSPLIT>
-__global__ void __launch_bounds__(Q8_WARPS * 32, (NC == 1 && !SWIGLU) ? 6 : 1)  // 6 blocks/SM: [12288 x 4096] is one wave
+__global__ void __launch_bounds__(Q8_WARPS * 32, q8_db_min_blocks(NC, SWIGLU, KSPLIT))
 gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
                   const float *__restrict__ D3, uint32_t M, uint32_t K, const float *__restrict__ x, uint32_t ldx,
                   float *__restrict__ y, uint32_t ldy, const float *__restrict__ res) {
@@ -283,10 +290,44 @@ gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, c
         s[b][0] = oks ? __ldg(d1 + (ks >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (SWIGLU) s[b][NM - 1] = oks ? __ldg(d3 + (ks >> 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto compute_batch = [&](auto bc, uint32_t kb0) {
+    auto compute_batch_stepwise = [&](auto bc, uint32_t kb0) {
         constexpr int b = decltype(bc)::value;
-        // the batch's activation float4s first, back to back: loaded one step at a time, each step stalled on
-        // its own L1 round trip (48 % of the stall samples of the first capture, profiles/README.md)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t k4 = kb0 + u * 32 + lane;
+            const int src = (lane & ~7) | u;  // the lane of this group of 8 that holds step u's scales
+            float sr[NM][4];
+#pragma unroll
+            for (int m = 0; m < NM; m++) {  // shuffles outside the k4 predicate: all 32 lanes take part
+                sr[m][0] = __shfl_sync(0xffffffffu, s[b][m].x, src); sr[m][1] = __shfl_sync(0xffffffffu, s[b][m].y, src);
+                sr[m][2] = __shfl_sync(0xffffffffu, s[b][m].z, src); sr[m][3] = __shfl_sync(0xffffffffu, s[b][m].w, src);
+            }
+            if (k4 < k4_end) {
+                float4 xv[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) xv[c] = __ldg(reinterpret_cast<const float4 *>(x + (size_t)c * ldx) + k4);
+#pragma unroll
+                for (int m = 0; m < NM; m++) {
+                    const uint32_t wr[4] = {w[b][u][m].x, w[b][u][m].y, w[b][u][m].z, w[b][u][m].w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        float f[4];
+                        unpack4(wr[r], f);
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            float t = f[0] * xv[c].x;
+                            t = fmaf(f[1], xv[c].y, t); t = fmaf(f[2], xv[c].z, t); t = fmaf(f[3], xv[c].w, t);
+                            acc[m][r][c] = fmaf(sr[m][r], t, acc[m][r][c]);
+                        }
+                    }
+                }
+            }
+        }
+    };
+    auto compute_batch_hoisted = [&](auto bc, uint32_t kb0) {
+        constexpr int b = decltype(bc)::value;
+        // the batch's activation float4s first, back to back: loaded one step at a time, each step stalled on its
+        // own L1 round trip (48 % of the stall samples in the ncu source view): 16.6 -> 14.2 us on [12288 x 4096]
         float4 xv[U][NC];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -323,6 +364,13 @@ gemv_q8_db_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, c
                 }
             }
         }
+    };
+    // Whole-row single-column GEMV (qkv, lm_head) takes the hoisted form; the K-split and SwiGLU variants measured
+    // slower with it (register pressure -> fewer resident blocks) and keep the per-step activation load.
+    constexpr bool HOIST = NC == 1 && !SWIGLU && KSPLIT == 1;
+    auto compute_batch = [&](auto bc, uint32_t kb0) {
+        if constexpr (HOIST) compute_batch_hoisted(bc, kb0);
+        else compute_batch_stepwise(bc, kb0);
     };
     using B0 = std::integral_constant<int, 0>;
     using B1 = std::integral_constant<int, 1>;
