@@ -20,6 +20,9 @@ def run_pipeline(args):
     from llama_go_b200 import _capi, pipeline, synth
 
     rank, world, local = rank_world()
+    # stdout carries exactly one JSON line: NCCL prints "NCCL version ..." there when NCCL_DEBUG=VERSION is inherited
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     dist.init_process_group("gloo", rank=rank, world_size=world)
