@@ -10,7 +10,9 @@ A "step" = one decoded token per in-flight sequence (N sequences at N GPUs, see 
           with CUDA events on the engine's stream (lb_decode_resident).
   e2e   : the same K steps through the public API lb_eval() with HOST buffers: token id H2D and
           128 KB logits D2H inside the timed region, one synchronous call per token.
-  roofline    : dominant kernel (w1/w3 SwiGLU GEMV) algorithmic bytes / CUDA-event time vs measured HBM peak.
+  roofline    : dominant kernel = the decode megakernel (one launch per token): algorithmic bytes of a token
+                 / CUDA-event time per replay vs the measured HBM peak; on the per-op paths
+                (Q8 weights, LB_NO_MEGA=1) the w1/w3 SwiGLU GEMV.
   cpu_baseline: the reference's own binary (--avx, all host threads) on a bounded sample.
 --impl reference times the reference's own CPU implementation (oracle/_ref/llama-go-linux).
 Weights (26.4 GB/token) are far larger than L2 (126 MB): no flush needed between iterations.
