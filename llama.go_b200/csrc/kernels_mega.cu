@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace lb {
 namespace k {
 
@@ -33,6 +35,7 @@ constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
+constexpr int MG_DYN_ROWS = 4;          // rows per dynamically scheduled block of a GEMV phase
 constexpr int MG_MAX_ITEMS = 2 * kNumSMs;  // attention items (head, split) per layer: <= 2 per CTA (decode_mega_splits)
 constexpr int MG_MAX_HEADS = 256;          // dim <= 8192 (largest K-slice variant), head dim >= 32
 // CTA-wide and half-CTA named barriers
@@ -59,8 +62,36 @@ struct MegaShared {
     float mrg_m[MG_MAX_ITEMS], mrg_l[MG_MAX_ITEMS], mrg_w[MG_MAX_ITEMS], mrg_inv[MG_MAX_HEADS];
 };
 
+// ---- L2 prefetch of the rows this CTA will stream first in an upcoming GEMV phase (its static block starts at
+// row blockIdx.x * Q, see gemv_phase).  Issued by warp 1 BETWEEN the arrival and the wait of a grid barrier: HBM is
+// idle while the grid synchronises, and the prefetch must come after the arrival — thread 0's __threadfence()
+// before the arrival atomic waits for its warp's outstanding memory operations, so anything issued earlier delays
+// the arrival of this CTA and with it every other CTA (why the round-1 attempts showed no gain).
+struct MegaPrefetch {
+    const float *W = nullptr, *W3 = nullptr;
+    uint32_t M = 0, K = 0, bytes = 0;  // bytes: budget per matrix and CTA
+};
+__device__ __forceinline__ void l2_prefetch_rows(const MegaPrefetch &pf) {
+    if (!pf.W || threadIdx.x < 32 || threadIdx.x >= 64) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t Q = ((uint32_t)(((uint64_t)pf.M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
+    const uint32_t row_bytes = pf.K * 4;
+    uint32_t rows = pf.bytes / row_bytes;
+    if (rows > Q) rows = Q;
+    const size_t total = (size_t)rows * row_bytes;  // contiguous: rows are row-major and adjacent
+    constexpr uint32_t CH = 8192;                    // bytes per prefetch instruction
+    const char *b1 = reinterpret_cast<const char *>(pf.W + (size_t)blockIdx.x * Q * pf.K);
+    const char *b3 = pf.W3 ? reinterpret_cast<const char *>(pf.W3 + (size_t)blockIdx.x * Q * pf.K) : nullptr;
+    for (size_t off = (size_t)lane * CH; off < total; off += 32 * CH) {
+        const uint32_t n = (uint32_t)(total - off < CH ? total - off : CH);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b1 + off), "r"(n) : "memory");
+        if (b3) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b3 + off), "r"(n) : "memory");
+    }
+}
+
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr,
+                                             const MegaPrefetch &pf = MegaPrefetch()) {
     target += nctas;
     csync();
     if (threadIdx.x == 0) {
@@ -71,6 +102,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
         }
         __threadfence();
         atomicAdd(bar, 1u);
+    }
+    l2_prefetch_rows(pf);  // warp 1; warp 0 polls
+    if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_u32(bar) < target) {
             if (clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a scheduling bug
@@ -139,7 +173,6 @@ __device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&
 
 // rows per load batch of a phase with V float4 per lane and NM matrices
 __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
-constexpr int MG_DYN_ROWS = 4;  // rows per dynamically scheduled block
 
 // One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
 // Scheduling: ~80 % of the rows are assigned statically (CTA c owns a contiguous block, processed
@@ -238,6 +271,7 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
+    uint32_t prefetch;          // LB_MEGA_PF: L2 prefetch across grid barriers (A/B switch)
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -466,6 +500,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     }
     csync();
     unsigned *sched = p.barrier + 1;  // [n_layers * 4 + 1] ticket counters, zeroed with the barrier
+    auto pf = [&](const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t bytes) {
+        MegaPrefetch f;
+        if (p.prefetch && W) { f.W = W; f.W3 = W3; f.M = M; f.K = K; f.bytes = bytes; }
+        return f;
+    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
         stamp(li, 0);
@@ -476,7 +515,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
         }
         stamp(li, 2);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0), pf(L.wo, nullptr, dim, dim, 512u << 10));  // all of wo's static rows, under the attention phase
         stamp(li, 3);
         // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
@@ -489,7 +528,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
         }
         stamp(li, 6);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2), pf(L.w1, L.w3, ff, dim, 64u << 10));
         stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
@@ -498,7 +537,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
         }
         stamp(li, 9);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3), pf(L.w2, nullptr, dim, ff, 136u << 10));
         stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
@@ -506,7 +545,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
         }
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4),
+                     li + 1 < p.n_layers ? pf(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 128u << 10)
+                                         : pf(p.output, nullptr, p.vocab, dim, 128u << 10));
         stamp(li, 12);
         xin = p.x;
     }
@@ -572,6 +613,8 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    static const bool mega_pf = getenv("LB_MEGA_PF") != nullptr;  // round-2 experiment: A/B in one run
+    p.prefetch = mega_pf ? 1u : 0u;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
