@@ -70,18 +70,24 @@ struct MegaShared {
 struct MegaPrefetch {
     const float *W = nullptr, *W3 = nullptr;
     uint32_t M = 0, K = 0, bytes = 0;  // bytes: budget per matrix and CTA
+    bool all_static = false;           // the phase uses the contiguous M/grid split (gemv_phase all_static)
 };
 __device__ __forceinline__ void l2_prefetch_rows(const MegaPrefetch &pf) {
     if (!pf.W || threadIdx.x < 32 || threadIdx.x >= 64) return;
     const int lane = threadIdx.x & 31;
-    const uint32_t Q = ((uint32_t)(((uint64_t)pf.M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
+    uint32_t Q = ((uint32_t)(((uint64_t)pf.M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
+    uint32_t first = blockIdx.x * Q;
+    if (pf.all_static) {
+        first = (uint32_t)(((uint64_t)pf.M * blockIdx.x) / gridDim.x);
+        Q = (uint32_t)(((uint64_t)pf.M * (blockIdx.x + 1)) / gridDim.x) - first;
+    }
     const uint32_t row_bytes = pf.K * 4;
     uint32_t rows = pf.bytes / row_bytes;
     if (rows > Q) rows = Q;
     const size_t total = (size_t)rows * row_bytes;  // contiguous: rows are row-major and adjacent
     constexpr uint32_t CH = 8192;                    // bytes per prefetch instruction
-    const char *b1 = reinterpret_cast<const char *>(pf.W + (size_t)blockIdx.x * Q * pf.K);
-    const char *b3 = pf.W3 ? reinterpret_cast<const char *>(pf.W3 + (size_t)blockIdx.x * Q * pf.K) : nullptr;
+    const char *b1 = reinterpret_cast<const char *>(pf.W + (size_t)first * pf.K);
+    const char *b3 = pf.W3 ? reinterpret_cast<const char *>(pf.W3 + (size_t)first * pf.K) : nullptr;
     for (size_t off = (size_t)lane * CH; off < total; off += 32 * CH) {
         const uint32_t n = (uint32_t)(total - off < CH ? total - off : CH);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b1 + off), "r"(n) : "memory");
@@ -182,16 +188,20 @@ __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ?
 // static split: 3-4 us per phase).  The next ticket is fetched while the current block streams.
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
-                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr) {
+                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr,
+                                           bool all_static = false) {
     constexpr int NM = SWIGLU ? 2 : 1;
     constexpr int RB = mg_rb(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KS = K / MG_WARPS;
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
+    // all_static (experiment LB_MEGA_WO_STATIC, short phases): contiguous M/grid rows per CTA, no ticket pool — a
+    // 4-row ticket block is load -> wait -> compute -> sync with only 64 KB in flight (~56 % of the SM's HBM share),
+    // which costs a 10 us phase more than the ~7 % arrival skew of a static split.
     const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;  // static rows per CTA
-    const uint32_t pool0 = Q * gridDim.x;
-    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);  // latency hidden behind the static part
+    const uint32_t pool0 = all_static ? M : Q * gridDim.x;
+    if (threadIdx.x == 0) sh.ticket_slot[0] = all_static ? 0u : atomicAdd(ctr, 1u);  // latency hidden behind the static part
     int buf = 0;
     // rows [rb, rb+nrb) -> partials -> combine -> out
     auto do_block = [&](uint32_t rb, uint32_t nrb) {
@@ -240,7 +250,8 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
         buf ^= 1;  // the other partial buffer is used next; this one is reused only after the next csync
     };
     // static part
-    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    if (all_static) cta_rows(M, r0, r1);
     for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) do_block(rb, min((uint32_t)MG_ROWBLK, r1 - rb));
     // dynamic pool
     int slot = 0;
@@ -272,6 +283,7 @@ struct MegaParams {
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
     uint32_t prefetch;          // LB_MEGA_PF: L2 prefetch across grid barriers (A/B switch)
+    uint32_t wo_static;         // LB_MEGA_WO_STATIC: the wo phase uses the contiguous static split (A/B switch)
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -500,13 +512,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     }
     csync();
     unsigned *sched = p.barrier + 1;  // [n_layers * 4 + 1] ticket counters, zeroed with the barrier
+    const float *L_wo = nullptr;  // the current layer's wo (for the prefetch of an all-static wo phase)
     auto pf = [&](const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t bytes) {
         MegaPrefetch f;
-        if (p.prefetch && W) { f.W = W; f.W3 = W3; f.M = M; f.K = K; f.bytes = bytes; }
+        if (p.prefetch && W) { f.W = W; f.W3 = W3; f.M = M; f.K = K; f.bytes = bytes; f.all_static = p.wo_static && W == L_wo; }
         return f;
     };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
+        L_wo = L.wo;
         stamp(li, 0);
         {   // ---- P1: rmsnorm * attention_norm, then [wq;wk;wv] (llama.go:255-265)
             float4 xs[VD];
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs, sh);
-            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, p.wo_static != 0);
         }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 2), pf(L.w1, L.w3, ff, dim, 64u << 10));
@@ -615,6 +629,8 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     static const bool mega_pf = getenv("LB_MEGA_PF") != nullptr;  // round-2 experiment: A/B in one run
     p.prefetch = mega_pf ? 1u : 0u;
+    static const bool mega_wo_static = getenv("LB_MEGA_WO_STATIC") != nullptr;
+    p.wo_static = mega_wo_static ? 1u : 0u;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
