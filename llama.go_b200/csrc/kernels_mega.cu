@@ -27,6 +27,7 @@
 #include "kernels.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace lb {
 namespace k {
@@ -263,6 +264,72 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
         do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
         slot ^= 1;
         t = sh.ticket_slot[slot];
+    }
+}
+
+// EXPERIMENT (LB_MEGA_WO_STATIC=2): a short single-matrix phase with the contiguous static split, software-pipelined:
+// two half-batches of rows live in registers, the loads of half-batch i+1 are issued before the arithmetic of
+// half-batch i, so 64-128 KB per SM are in flight at all times instead of a 128 KB burst followed by a bubble.
+// Same K-slices, same per-row arithmetic and the same combine as gemv_phase: identical results.
+template <int V>
+__device__ __forceinline__ void gemv_phase_static_pipelined(const float *__restrict__ W, uint32_t M, uint32_t K,
+                                                            const float4 (&xs)[V], float *out, const float *res, MegaShared &sh) {
+    constexpr int RBH = mg_rb(V, 1) >= 8 ? 3 : (mg_rb(V, 1) >= 2 ? mg_rb(V, 1) / 2 : 1);  // 4 rows x 2 buffers spill at the 128-register cap
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+    const float *w1 = W + (size_t)warp * KS + lane * 4;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    float4 a[2][RBH][V];
+    auto issue = [&](auto bc, uint32_t row, uint32_t n) {
+        constexpr int b = decltype(bc)::value;
+#pragma unroll
+        for (int i = 0; i < RBH; i++) {
+            const bool rok = (uint32_t)i < n;
+            const size_t off = (size_t)(row + i) * K;
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
+                a[b][i][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto consume = [&](auto bc, uint32_t rel, uint32_t n, int buf) {
+        constexpr int b = decltype(bc)::value;
+#pragma unroll
+        for (int i = 0; i < RBH; i++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                acc = fmaf(a[b][i][j].x, xs[j].x, acc); acc = fmaf(a[b][i][j].y, xs[j].y, acc);
+                acc = fmaf(a[b][i][j].z, xs[j].z, acc); acc = fmaf(a[b][i][j].w, xs[j].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && (uint32_t)i < n) sh.part[buf][0][rel + i][warp] = acc;
+        }
+    };
+    using B0 = std::integral_constant<int, 0>;
+    using B1 = std::integral_constant<int, 1>;
+    auto cnt = [](uint32_t total, uint32_t at) { return total > at ? (total - at < (uint32_t)RBH ? total - at : (uint32_t)RBH) : 0u; };
+    int buf = 0;
+    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) {
+        const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
+        issue(B0{}, rb, cnt(nrb, 0));
+        for (uint32_t r = 0; r < nrb; r += 2 * RBH) {
+            if (r + RBH < nrb) issue(B1{}, rb + r + RBH, cnt(nrb, r + RBH));
+            consume(B0{}, r, cnt(nrb, r), buf);
+            if (r + 2 * RBH < nrb) issue(B0{}, rb + r + 2 * RBH, cnt(nrb, r + 2 * RBH));
+            if (r + RBH < nrb) consume(B1{}, r + RBH, cnt(nrb, r + RBH), buf);
+        }
+        csync();
+        if (threadIdx.x < nrb) {
+            float s1 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < MG_WARPS; wv++) s1 += sh.part[buf][0][threadIdx.x][wv];
+            const uint32_t row = rb + threadIdx.x;
+            out[row] = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
+        }
+        buf ^= 1;
     }
 }
 
@@ -539,7 +606,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs, sh);
-            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, p.wo_static != 0);
+            if (p.wo_static == 2) gemv_phase_static_pipelined<VD>(L.wo, dim, dim, xs, p.y, xin, sh);
+            else gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, p.wo_static != 0);
         }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x, arr(li, 2), pf(L.w1, L.w3, ff, dim, 64u << 10));
@@ -629,8 +697,8 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     static const bool mega_pf = getenv("LB_MEGA_PF") != nullptr;  // round-2 experiment: A/B in one run
     p.prefetch = mega_pf ? 1u : 0u;
-    static const bool mega_wo_static = getenv("LB_MEGA_WO_STATIC") != nullptr;
-    p.wo_static = mega_wo_static ? 1u : 0u;
+    static const uint32_t mega_wo_static = getenv("LB_MEGA_WO_STATIC") ? (uint32_t)atoi(getenv("LB_MEGA_WO_STATIC")) : 0u;
+    p.wo_static = mega_wo_static;  // 1: contiguous static split, 2: + software-pipelined half-batches
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);

@@ -1,14 +1,14 @@
 #!/bin/bash
 # Round-2 first measurement of the prepared megakernel experiments (this branch only):
 #   LB_MEGA_PF=1         L2 prefetch of the next GEMV phase's first rows between barrier arrival and wait
-#   LB_MEGA_WO_STATIC=1  contiguous static row split for the wo phase
+#   LB_MEGA_WO_STATIC=1  contiguous static row split for the wo phase (=2: + software-pipelined half-batches)
 # Parity first (golden logits are tolerance-based; the prefetch does not change results, the static split only the
 # order in which rows are produced), then A/B of the four combinations: bench value + CTA-0 phase trace.
 set -u
 TAG=${1:-r02a}
 OUT=gpurun_out
 mkdir -p $OUT
-for combo in "" "LB_MEGA_PF=1" "LB_MEGA_WO_STATIC=1" "LB_MEGA_PF=1 LB_MEGA_WO_STATIC=1"; do
+for combo in "" "LB_MEGA_PF=1" "LB_MEGA_WO_STATIC=1" "LB_MEGA_WO_STATIC=2" "LB_MEGA_PF=1 LB_MEGA_WO_STATIC=1" "LB_MEGA_PF=1 LB_MEGA_WO_STATIC=2"; do
   name=$(echo "base $combo" | tr ' =' '__')
   echo "=== [$combo] parity (eval + generate tests)"
   env $combo timeout 600 python -m pytest tests/test_gpu_eval.py tests/test_gpu_generate.py -x -q -m gpu > $OUT/pytest_${name}_$TAG.log 2>&1; echo "rc=$?"; tail -2 $OUT/pytest_${name}_$TAG.log
