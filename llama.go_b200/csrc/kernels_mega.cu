@@ -26,6 +26,9 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace lb {
 namespace k {
 
@@ -33,6 +36,7 @@ constexpr int MG_WARPS = 16;
 constexpr int MG_THREADS = MG_WARPS * 32;
 constexpr int MG_HALF = MG_THREADS / 2;      // attention runs two items at a time, 8 warps each
 constexpr int MG_ROWBLK = 32;          // rows whose partials are combined per __syncthreads
+constexpr int MG_DYN_ROWS = 4;          // rows per dynamically scheduled block of a GEMV phase
 constexpr int MG_MAX_ITEMS = 2 * kNumSMs;  // attention items (head, split) per layer: <= 2 per CTA (decode_mega_splits)
 constexpr int MG_MAX_HEADS = 256;          // dim <= 8192 (largest K-slice variant), head dim >= 32
 // CTA-wide and half-CTA named barriers
@@ -59,8 +63,42 @@ struct MegaShared {
     float mrg_m[MG_MAX_ITEMS], mrg_l[MG_MAX_ITEMS], mrg_w[MG_MAX_ITEMS], mrg_inv[MG_MAX_HEADS];
 };
 
+// ---- L2 prefetch of the rows this CTA will stream first in an upcoming GEMV phase (its static block starts at
+// row blockIdx.x * Q, see gemv_phase).  Issued by warp 1 BETWEEN the arrival and the wait of a grid barrier: HBM is
+// idle while the grid synchronises, and the prefetch must come after the arrival — thread 0's __threadfence()
+// before the arrival atomic waits for its warp's outstanding memory operations, so anything issued earlier delays
+// the arrival of this CTA and with it every other CTA (why the round-1 attempts showed no gain).
+struct MegaPrefetch {
+    const float *W = nullptr, *W3 = nullptr;
+    uint32_t M = 0, K = 0, bytes = 0;  // bytes: budget per matrix and CTA
+    bool all_static = false;           // the phase uses the contiguous M/grid split (gemv_phase all_static)
+};
+__device__ __forceinline__ void l2_prefetch_rows(const MegaPrefetch &pf) {
+    if (!pf.W || threadIdx.x < 32 || threadIdx.x >= 64) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t Q = ((uint32_t)(((uint64_t)pf.M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
+    uint32_t first = blockIdx.x * Q;
+    if (pf.all_static) {
+        first = (uint32_t)(((uint64_t)pf.M * blockIdx.x) / gridDim.x);
+        Q = (uint32_t)(((uint64_t)pf.M * (blockIdx.x + 1)) / gridDim.x) - first;
+    }
+    const uint32_t row_bytes = pf.K * 4;
+    uint32_t rows = pf.bytes / row_bytes;
+    if (rows > Q) rows = Q;
+    const size_t total = (size_t)rows * row_bytes;  // contiguous: rows are row-major and adjacent
+    constexpr uint32_t CH = 8192;                    // bytes per prefetch instruction
+    const char *b1 = reinterpret_cast<const char *>(pf.W + (size_t)first * pf.K);
+    const char *b3 = pf.W3 ? reinterpret_cast<const char *>(pf.W3 + (size_t)first * pf.K) : nullptr;
+    for (size_t off = (size_t)lane * CH; off < total; off += 32 * CH) {
+        const uint32_t n = (uint32_t)(total - off < CH ? total - off : CH);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b1 + off), "r"(n) : "memory");
+        if (b3) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b3 + off), "r"(n) : "memory");
+    }
+}
+
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr,
+                                             const MegaPrefetch &pf = MegaPrefetch()) {
     target += nctas;
     csync();
     if (threadIdx.x == 0) {
@@ -71,6 +109,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
         }
         __threadfence();
         atomicAdd(bar, 1u);
+    }
+    l2_prefetch_rows(pf);  // warp 1; warp 0 polls
+    if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_u32(bar) < target) {
             if (clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU on a scheduling bug
@@ -139,7 +180,6 @@ __device__ __forceinline__ void load_slice(const float *x, uint32_t K, float4 (&
 
 // rows per load batch of a phase with V float4 per lane and NM matrices
 __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ? 1 : (V * NM >= 6) ? 2 : (V * NM >= 3) ? 4 : 8; }
-constexpr int MG_DYN_ROWS = 4;  // rows per dynamically scheduled block
 
 // One GEMV phase.  SWIGLU = false: out[r] = W[r]·xs (+ res[r]).  SWIGLU = true: out[r] = silu(W[r]·xs) * (W3[r]·xs).
 // Scheduling: ~80 % of the rows are assigned statically (CTA c owns a contiguous block, processed
@@ -149,16 +189,20 @@ constexpr int MG_DYN_ROWS = 4;  // rows per dynamically scheduled block
 // static split: 3-4 us per phase).  The next ticket is fetched while the current block streams.
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
-                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr) {
+                                           const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr,
+                                           bool all_static = false) {
     constexpr int NM = SWIGLU ? 2 : 1;
     constexpr int RB = mg_rb(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KS = K / MG_WARPS;
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
+    // all_static (experiment LB_MEGA_WO_STATIC, short phases): contiguous M/grid rows per CTA, no ticket pool — a
+    // 4-row ticket block is load -> wait -> compute -> sync with only 64 KB in flight (~56 % of the SM's HBM share),
+    // which costs a 10 us phase more than the ~7 % arrival skew of a static split.
     const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;  // static rows per CTA
-    const uint32_t pool0 = Q * gridDim.x;
-    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);  // latency hidden behind the static part
+    const uint32_t pool0 = all_static ? M : Q * gridDim.x;
+    if (threadIdx.x == 0) sh.ticket_slot[0] = all_static ? 0u : atomicAdd(ctr, 1u);  // latency hidden behind the static part
     int buf = 0;
     // rows [rb, rb+nrb) -> partials -> combine -> out
     auto do_block = [&](uint32_t rb, uint32_t nrb) {
@@ -207,7 +251,8 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
         buf ^= 1;  // the other partial buffer is used next; this one is reused only after the next csync
     };
     // static part
-    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    if (all_static) cta_rows(M, r0, r1);
     for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) do_block(rb, min((uint32_t)MG_ROWBLK, r1 - rb));
     // dynamic pool
     int slot = 0;
@@ -219,6 +264,72 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
         do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
         slot ^= 1;
         t = sh.ticket_slot[slot];
+    }
+}
+
+// EXPERIMENT (LB_MEGA_WO_STATIC=2): a short single-matrix phase with the contiguous static split, software-pipelined:
+// two half-batches of rows live in registers, the loads of half-batch i+1 are issued before the arithmetic of
+// half-batch i, so 64-128 KB per SM are in flight at all times instead of a 128 KB burst followed by a bubble.
+// Same K-slices, same per-row arithmetic and the same combine as gemv_phase: identical results.
+template <int V>
+__device__ __forceinline__ void gemv_phase_static_pipelined(const float *__restrict__ W, uint32_t M, uint32_t K,
+                                                            const float4 (&xs)[V], float *out, const float *res, MegaShared &sh) {
+    constexpr int RBH = mg_rb(V, 1) >= 8 ? 3 : (mg_rb(V, 1) >= 2 ? mg_rb(V, 1) / 2 : 1);  // 4 rows x 2 buffers spill at the 128-register cap
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+    const float *w1 = W + (size_t)warp * KS + lane * 4;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    float4 a[2][RBH][V];
+    auto issue = [&](auto bc, uint32_t row, uint32_t n) {
+        constexpr int b = decltype(bc)::value;
+#pragma unroll
+        for (int i = 0; i < RBH; i++) {
+            const bool rok = (uint32_t)i < n;
+            const size_t off = (size_t)(row + i) * K;
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
+                a[b][i][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    auto consume = [&](auto bc, uint32_t rel, uint32_t n, int buf) {
+        constexpr int b = decltype(bc)::value;
+#pragma unroll
+        for (int i = 0; i < RBH; i++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                acc = fmaf(a[b][i][j].x, xs[j].x, acc); acc = fmaf(a[b][i][j].y, xs[j].y, acc);
+                acc = fmaf(a[b][i][j].z, xs[j].z, acc); acc = fmaf(a[b][i][j].w, xs[j].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && (uint32_t)i < n) sh.part[buf][0][rel + i][warp] = acc;
+        }
+    };
+    using B0 = std::integral_constant<int, 0>;
+    using B1 = std::integral_constant<int, 1>;
+    auto cnt = [](uint32_t total, uint32_t at) { return total > at ? (total - at < (uint32_t)RBH ? total - at : (uint32_t)RBH) : 0u; };
+    int buf = 0;
+    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) {
+        const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
+        issue(B0{}, rb, cnt(nrb, 0));
+        for (uint32_t r = 0; r < nrb; r += 2 * RBH) {
+            if (r + RBH < nrb) issue(B1{}, rb + r + RBH, cnt(nrb, r + RBH));
+            consume(B0{}, r, cnt(nrb, r), buf);
+            if (r + 2 * RBH < nrb) issue(B0{}, rb + r + 2 * RBH, cnt(nrb, r + 2 * RBH));
+            if (r + RBH < nrb) consume(B1{}, r + RBH, cnt(nrb, r + RBH), buf);
+        }
+        csync();
+        if (threadIdx.x < nrb) {
+            float s1 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < MG_WARPS; wv++) s1 += sh.part[buf][0][threadIdx.x][wv];
+            const uint32_t row = rb + threadIdx.x;
+            out[row] = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
+        }
+        buf ^= 1;
     }
 }
 
@@ -238,6 +349,8 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
+    uint32_t prefetch;          // LB_MEGA_PF: L2 prefetch across grid barriers (A/B switch)
+    uint32_t wo_static;         // LB_MEGA_WO_STATIC: the wo phase uses the contiguous static split (A/B switch)
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -466,8 +579,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     }
     csync();
     unsigned *sched = p.barrier + 1;  // [n_layers * 4 + 1] ticket counters, zeroed with the barrier
+    const float *L_wo = nullptr;  // the current layer's wo (for the prefetch of an all-static wo phase)
+    auto pf = [&](const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t bytes) {
+        MegaPrefetch f;
+        if (p.prefetch && W) { f.W = W; f.W3 = W3; f.M = M; f.K = K; f.bytes = bytes; f.all_static = p.wo_static && W == L_wo; }
+        return f;
+    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
+        L_wo = L.wo;
         stamp(li, 0);
         {   // ---- P1: rmsnorm * attention_norm, then [wq;wk;wv] (llama.go:255-265)
             float4 xs[VD];
@@ -476,7 +596,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
         }
         stamp(li, 2);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0), pf(L.wo, nullptr, dim, dim, 512u << 10));  // all of wo's static rows, under the attention phase
         stamp(li, 3);
         // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
@@ -486,10 +606,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs, sh);
-            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1);
+            if (p.wo_static == 2) gemv_phase_static_pipelined<VD>(L.wo, dim, dim, xs, p.y, xin, sh);
+            else gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, p.wo_static != 0);
         }
         stamp(li, 6);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2), pf(L.w1, L.w3, ff, dim, 64u << 10));
         stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
@@ -498,7 +619,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
         }
         stamp(li, 9);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3), pf(L.w2, nullptr, dim, ff, 136u << 10));
         stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
@@ -506,7 +627,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
         }
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4),
+                     li + 1 < p.n_layers ? pf(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 128u << 10)
+                                         : pf(p.output, nullptr, p.vocab, dim, 128u << 10));
         stamp(li, 12);
         xin = p.x;
     }
@@ -572,6 +695,10 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    static const bool mega_pf = getenv("LB_MEGA_PF") != nullptr;  // round-2 experiment: A/B in one run
+    p.prefetch = mega_pf ? 1u : 0u;
+    static const uint32_t mega_wo_static = getenv("LB_MEGA_WO_STATIC") ? (uint32_t)atoi(getenv("LB_MEGA_WO_STATIC")) : 0u;
+    p.wo_static = mega_wo_static;  // 1: contiguous static split, 2: + software-pipelined half-batches
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
