@@ -320,7 +320,7 @@ def run_single_gpu(args):
     bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
     step_gbs = bytes_per_token * value / 1e9
 
-    mega = (not q8) and os.environ.get("LB_NO_MEGA") is None
+    mega = ((not q8) and os.environ.get("LB_NO_MEGA") is None) or (q8 and os.environ.get("LB_Q8_MEGA") is not None)
     cpu = None
     if not args.no_cpu_baseline:
         try:

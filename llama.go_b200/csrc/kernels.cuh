@@ -104,6 +104,8 @@ void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
 struct MegaLayerHost {  // one per layer, array lives in device memory
     const float *attention_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2;
     float *Kc, *Vc;
+    const int8_t *q_wqkv, *q_wo, *q_w1, *q_w3, *q_w2;  // Q8_0 planes (nullptr for F32 models)
+    const float *d_wqkv, *d_wo, *d_w1, *d_w3, *d_w2;
 };
 struct MegaParamsHost {
     const MegaLayerHost *layers_dev;
@@ -111,6 +113,9 @@ struct MegaParamsHost {
     const float *tok_embeddings;      // nullptr: residual comes in through x (pipeline stage > 0)
     const uint32_t *tokens, *state;   // device: token ids, {past, step}
     const float *final_norm, *output; // final_norm == nullptr: no lm_head on this stage
+    const int8_t *q_output = nullptr; // Q8_0 lm_head planes (experiment: Q8 megakernel)
+    const float *d_output = nullptr;
+    bool q8 = false;
     float *x, *y, *qkv, *attn, *act, *logits;
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
@@ -118,6 +123,7 @@ struct MegaParamsHost {
     void *trace = nullptr;            // optional uint64[n_layers*13] phase time stamps (profiling aid)
 };
 bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads);
+bool decode_mega_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab);
 uint32_t decode_mega_splits(uint32_t heads);
 void decode_mega(const MegaParamsHost &p, cudaStream_t st);
 

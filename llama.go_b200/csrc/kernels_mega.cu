@@ -336,6 +336,8 @@ __device__ __forceinline__ void gemv_phase_static_pipelined(const float *__restr
 struct MegaLayer {
     const float *attention_norm, *wqkv, *wo, *ffn_norm, *w1, *w3, *w2;
     float *Kc, *Vc;
+    const int8_t *q_wqkv, *q_wo, *q_w1, *q_w3, *q_w2;  // Q8_0 planes (Q8 megakernel)
+    const float *d_wqkv, *d_wo, *d_w1, *d_w3, *d_w2;
 };
 struct MegaParams {
     const MegaLayer *layers;
@@ -344,6 +346,8 @@ struct MegaParams {
     const uint32_t *tokens;
     const uint32_t *state;        // {past, step}
     const float *final_norm, *output;  // nullptr: no lm_head on this stage
+    const int8_t *q_output;            // Q8 megakernel: lm_head planes
+    const float *d_output;
     float *x, *y, *qkv, *attn, *act, *logits;
     float *part_o, *part_ml;
     unsigned *tickets, *barrier;
@@ -640,6 +644,255 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     }
 }
 
+
+// =================================================================================================================
+// EXPERIMENT (LB_Q8_MEGA=1, unmeasured): the decode megakernel for Q8_0 weights on the int8 tensor cores.
+// Same phases, barriers, attention and merge as decode_mega_kernel.  A GEMV phase differs:
+//  * the phase's activation vector (RMSNorm output / merged attention / SwiGLU output) is written to shared memory
+//    and turned, one warp per Q8 block, into 4 balanced base-128 digits per element relative to the block's power
+//    of two (exact to 2^-28 of the block maximum) stored as B fragments of mma.sync.m16n8k32.s8 (digit j = column j);
+//  * work unit = a tile of 16 rows; the 16 warps of the CTA split the tile's K blocks, every warp feeds its
+//    (16 rows x 32 k) sub-tiles from HBM straight into the A fragment (in the 4-row interleaved planes one 32-bit
+//    word = 4 consecutive k of one row = one A register), one IMMA per sub-tile, s32 results exact, then
+//    acc[row] += d_w[row][blk] * 2^e[blk] * sum_j 128^-(j+1) c_j;
+//  * row partials of the 16 warps are combined through shared memory exactly as in gemv_phase.
+// Fragment/index math: tools/studies/q8_mma_layout_emulation.py.  Numerics: tools/studies/q8_int8_digits.py.
+constexpr int MGQ_U = 8;  // K blocks in flight per warp
+
+__device__ __forceinline__ uint32_t ldq_stream_u32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+struct MegaQ8Smem {       // carved out of dynamic shared memory after the attention scores
+    float *vec;           // [Kmax]   the phase's activation vector
+    uint32_t *bfrag;      // [Kmax/32][32] words: B fragments of the 16 lanes with gid < 4 (2 words each)
+    float *xsc;           // [Kmax/32] 2^e per block
+};
+
+template <int V>
+__device__ __forceinline__ void slice_to_smem(const float4 (&xs)[V], uint32_t K, float *vec) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t KS = K / MG_WARPS;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+        const uint32_t e = (j * 32 + lane) * 4;
+        if (e < KS) *reinterpret_cast<float4 *>(vec + (size_t)warp * KS + e) = xs[j];
+    }
+}
+
+// vec (shared or global, K floats) -> B fragments + block scales; one warp per block of 32
+__device__ __forceinline__ void q8_digits_phase(const float *vec, uint32_t K, const MegaQ8Smem &q, bool vec_global) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t NB = K >> 5;
+    const int tig = (lane & 15) >> 2, reg = lane >> 4;   // where element `lane` of a block sits in the B fragment
+    for (uint32_t b = warp; b < NB; b += MG_WARPS) {
+        const float v = vec_global ? __ldcg(vec + (size_t)b * 32 + lane) : vec[(size_t)b * 32 + lane];
+        const float mx = warp_max(fabsf(v));
+        uint32_t pack = 0;
+        float scale = 0.f;
+        if (mx >= 1e-30f && mx <= 1e30f) {
+            const int e = ilogbf(mx) + 2;  // |v| / 2^e < 0.5
+            scale = ldexpf(1.0f, e);
+            float r = v * ldexpf(1.0f, -e);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                r *= 128.0f;
+                const float dj = rintf(r);
+                r -= dj;
+                pack |= ((uint32_t)(int)dj & 0xffu) << (8 * j);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t w = ((pack >> (8 * j)) & 0xffu) << (8 * (lane & 3));
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            if ((lane & 3) == 0) q.bfrag[(size_t)b * 32 + (j * 4 + tig) * 2 + reg] = w;  // column j, rows tig*4.. (+16)
+        }
+        if (lane == 0) q.xsc[b] = scale;
+    }
+}
+
+// this warp's share (K blocks [b_begin, b_end)) of one 16-row tile of a Q8 matrix -> per-lane partial sums of rows
+// R0 + gid (lo) and R0 + gid + 8 (hi), already reduced over the digit columns (valid in every lane of the quad)
+__device__ __forceinline__ void q8_tile_partial(const int8_t *__restrict__ Q, const float *__restrict__ D, uint32_t R0, uint32_t K,
+                                                uint32_t b_begin, uint32_t b_end, const MegaQ8Smem &q, float &out_lo, float &out_hi) {
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const uint32_t NB = K >> 5, K4 = K >> 2;
+    const uint32_t r_lo = R0 + gid, r_hi = r_lo + 8;
+    const uint32_t *qa = reinterpret_cast<const uint32_t *>(Q) + ((size_t)(r_lo >> 2) * K4 + tig) * 4 + (r_lo & 3);
+    const uint32_t *qb = reinterpret_cast<const uint32_t *>(Q) + ((size_t)(r_hi >> 2) * K4 + tig) * 4 + (r_hi & 3);
+    const float *da = D + (size_t)(r_lo >> 2) * NB * 4 + (r_lo & 3);
+    const float *db = D + (size_t)(r_hi >> 2) * NB * 4 + (r_hi & 3);
+    const float w0 = tig == 0 ? 0x1p-7f : 0x1p-21f, w1 = w0 * 0x1p-7f;  // tig 0: digits 0,1; tig 1: digits 2,3
+    float acc_lo = 0.f, acc_hi = 0.f;
+    for (uint32_t bb = b_begin; bb < b_end; bb += MGQ_U) {
+        uint32_t a[MGQ_U][4];
+        float s_lo[MGQ_U], s_hi[MGQ_U];
+#pragma unroll
+        for (int u = 0; u < MGQ_U; u++) {
+            const uint32_t b = bb + u;
+            const bool ok = b < b_end;
+            const size_t w = (size_t)b * 32;
+            a[u][0] = ok ? ldq_stream_u32(qa + w) : 0u;
+            a[u][1] = ok ? ldq_stream_u32(qb + w) : 0u;
+            a[u][2] = ok ? ldq_stream_u32(qa + w + 16) : 0u;
+            a[u][3] = ok ? ldq_stream_u32(qb + w + 16) : 0u;
+            s_lo[u] = ok ? __ldg(da + (size_t)b * 4) : 0.f;
+            s_hi[u] = ok ? __ldg(db + (size_t)b * 4) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < MGQ_U; u++) {
+            const uint32_t b = bb + u;
+            if (b < b_end) {  // warp-uniform
+                uint2 bf = make_uint2(0u, 0u);
+                if (gid < 4) bf = *reinterpret_cast<const uint2 *>(q.bfrag + (size_t)b * 32 + (gid * 4 + tig) * 2);
+                const float xs = q.xsc[b];
+                int c0, c1, c2, c3;
+                asm volatile(
+                    "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                    : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3)
+                    : "r"(a[u][0]), "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]), "r"(bf.x), "r"(bf.y), "r"(0));
+                const float v_lo = fmaf((float)c0, w0, (float)c1 * w1), v_hi = fmaf((float)c2, w0, (float)c3 * w1);
+                acc_lo = fmaf(s_lo[u] * xs, v_lo, acc_lo);
+                acc_hi = fmaf(s_hi[u] * xs, v_hi, acc_hi);
+            }
+        }
+    }
+    // digit columns live in tig 0 and 1; tig 2 and 3 hold the zero columns
+    acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 1); acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 2);
+    acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 1); acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 2);
+    out_lo = acc_lo; out_hi = acc_hi;
+}
+
+constexpr int MGQ_TILE = 16;  // rows per work unit (one IMMA tile)
+
+template <bool SWIGLU>
+__device__ __forceinline__ void gemv_phase_q8(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
+                                              const float *__restrict__ D3, uint32_t M, uint32_t K, const MegaQ8Smem &q, float *out,
+                                              const float *res, MegaShared &sh, unsigned *ctr) {
+    constexpr int NM = SWIGLU ? 2 : 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const uint32_t NB = K >> 5;
+    const uint32_t per = (NB + MG_WARPS - 1) / MG_WARPS, b_begin = min((uint32_t)warp * per, NB), b_end = min(b_begin + per, NB);
+    const uint32_t tiles = M / MGQ_TILE;
+    const uint32_t Qt = (uint32_t)(((uint64_t)tiles * 4) / (5 * gridDim.x));  // static tiles per CTA
+    const uint32_t pool0 = Qt * gridDim.x;
+    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);
+    int buf = 0;
+    auto do_tiles = [&](uint32_t t0, uint32_t nt) {  // nt = 1 or 2 tiles (MG_ROWBLK = 32 rows per combine)
+        for (uint32_t ti = 0; ti < nt; ti++) {
+#pragma unroll
+            for (int mtx = 0; mtx < NM; mtx++) {
+                float lo, hi;
+                q8_tile_partial(mtx ? Q3 : Q1, mtx ? D3 : D1, (t0 + ti) * MGQ_TILE, K, b_begin, b_end, q, lo, hi);
+                if (tig == 0) {
+                    sh.part[buf][mtx][ti * MGQ_TILE + gid][warp] = lo;
+                    sh.part[buf][mtx][ti * MGQ_TILE + gid + 8][warp] = hi;
+                }
+            }
+        }
+        csync();
+        if (threadIdx.x < nt * MGQ_TILE) {
+            float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < MG_WARPS; wv++) {
+                s1 += sh.part[buf][0][threadIdx.x][wv];
+                if (SWIGLU) s3 += sh.part[buf][NM - 1][threadIdx.x][wv];
+            }
+            const uint32_t row = t0 * MGQ_TILE + threadIdx.x;
+            float v;
+            if (SWIGLU) v = __fmul_rn(silu_ref(s1), s3);
+            else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
+            out[row] = v;
+        }
+        buf ^= 1;
+    };
+    const uint32_t t0 = blockIdx.x * Qt, t1 = t0 + Qt;
+    for (uint32_t t = t0; t < t1; t += 2) do_tiles(t, min(2u, t1 - t));
+    int slot = 0;
+    csync();
+    uint32_t tk = sh.ticket_slot[0];
+    while ((uint64_t)pool0 + tk < tiles) {
+        const uint32_t t = pool0 + tk;
+        if (threadIdx.x == 0) sh.ticket_slot[slot ^ 1] = atomicAdd(ctr, 1u);
+        do_tiles(t, 1);
+        slot ^= 1;
+        tk = sh.ticket_slot[slot];
+    }
+}
+
+template <int VD, int HD>
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_q8_kernel(const MegaParams p, uint32_t kmax) {
+    extern __shared__ float scores[];  // [2][chunk_cap] | vec [kmax] | bfrag [kmax/32][32] | xsc [kmax/32]
+    __shared__ MegaShared sh;
+    MegaQ8Smem q;
+    q.vec = scores + ((2 * (size_t)p.chunk_cap + 3) & ~(size_t)3);  // 16-byte aligned (float4 stores)
+    q.bfrag = reinterpret_cast<uint32_t *>(q.vec + kmax);
+    q.xsc = reinterpret_cast<float *>(q.bfrag + (size_t)(kmax >> 5) * 32);
+    const uint32_t dim = p.dim, ff = p.ff;
+    unsigned target = 0;
+    const uint32_t past = p.state[0];
+    const float *xin = p.x;
+    if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;
+    if (threadIdx.x < HD / 2) {
+        double sn, cs;
+        sincos((double)past * pow(10000.0, ((double)(-(int)(2 * threadIdx.x))) / (double)HD), &sn, &cs);
+        sh.rope_cs[threadIdx.x][0] = cs;
+        sh.rope_cs[threadIdx.x][1] = sn;
+    }
+    csync();
+    unsigned *sched = p.barrier + 1;
+    // activation slice (registers) -> shared vector -> digits; every CTA does this redundantly, like the RMSNorm
+    auto stage = [&](const float4 (&xs)[VD]) {
+        slice_to_smem<VD>(xs, dim, q.vec);
+        csync();
+        q8_digits_phase(q.vec, dim, q, false);
+        csync();
+    };
+    for (uint32_t li = 0; li < p.n_layers; li++) {
+        const MegaLayer L = p.layers[li];
+        {   // P1
+            float4 xs[VD];
+            rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
+            stage(xs);
+            gemv_phase_q8<false>(L.q_wqkv, L.d_wqkv, nullptr, nullptr, 3 * dim, dim, q, p.qkv, nullptr, sh, sched + li * 4 + 0);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        attention_phase<HD>(p, L, past, sh, scores);
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // P3
+            float4 xs[VD];
+            merged_attention_slice<VD, HD>(p, xs, sh);
+            stage(xs);
+            gemv_phase_q8<false>(L.q_wo, L.d_wo, nullptr, nullptr, dim, dim, q, p.y, xin, sh, sched + li * 4 + 1);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // P4
+            float4 xs[VD];
+            rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
+            stage(xs);
+            gemv_phase_q8<true>(L.q_w1, L.d_w1, L.q_w3, L.d_w3, ff, dim, q, p.act, nullptr, sh, sched + li * 4 + 2);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        {   // P5: the SwiGLU output was written by other CTAs -> digits straight from L2
+            q8_digits_phase(p.act, ff, q, true);
+            csync();
+            gemv_phase_q8<false>(L.q_w2, L.d_w2, nullptr, nullptr, dim, ff, q, p.x, p.y, sh, sched + li * 4 + 3);
+        }
+        grid_barrier(p.barrier, target, gridDim.x);
+        xin = p.x;
+    }
+    if (p.final_norm) {
+        float4 xs[VD];
+        rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
+        stage(xs);
+        gemv_phase_q8<false>(p.q_output, p.d_output, nullptr, nullptr, p.vocab, dim, q, p.logits, nullptr, sh, sched + p.n_layers * 4);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 struct MegaHost {
     MegaParams p;
@@ -679,8 +932,41 @@ uint32_t decode_mega_splits(uint32_t heads) {
     return s < 1 ? 1 : (s > 32 ? 32 : s);
 }
 
+bool decode_mega_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab) {
+    int vd, vf;
+    if (heads == 0 || dim % heads) return false;
+    if (!pick_variant(dim, ff, dim / heads, vd, vf) || vd > 4) return false;
+    if (dim % 32 || ff % 32) return false;                                                  // whole Q8 blocks
+    return (3 * dim) % MGQ_TILE == 0 && dim % MGQ_TILE == 0 && ff % MGQ_TILE == 0 && vocab % MGQ_TILE == 0;  // whole row tiles
+}
+
+template <int VD, int HDV>
+static cudaError_t launch_q8_one(cudaLaunchConfig_t &cfg, const MegaParams &p, uint32_t kmax, size_t smem) {
+    static size_t set_for = 0;  // the first (eager) launch raises the limit; graph capture then finds it set
+    if (set_for < smem) {
+        cudaError_t ea = cudaFuncSetAttribute(decode_mega_q8_kernel<VD, HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return ea;
+        set_for = smem;
+    }
+    return cudaLaunchKernelEx(&cfg, decode_mega_q8_kernel<VD, HDV>, p, kmax);
+}
+
+template <int VD>
+static cudaError_t launch_q8_hd(const MegaParams &p, uint32_t hd, uint32_t kmax, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (hd == 128) return launch_q8_one<VD, 128>(cfg, p, kmax, smem);
+    if (hd == 64) return launch_q8_one<VD, 64>(cfg, p, kmax, smem);
+    return launch_q8_one<VD, 32>(cfg, p, kmax, smem);
+}
+
 void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     MegaParams p;
+    p.q_output = h.q_output; p.d_output = h.d_output;
     p.layers = reinterpret_cast<const MegaLayer *>(h.layers_dev);
     p.n_layers = h.n_layers;
     p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
@@ -701,6 +987,19 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     p.wo_static = mega_wo_static;  // 1: contiguous static split, 2: + software-pipelined half-batches
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
+    if (h.q8) {  // experiment: Q8 megakernel (int8 tensor cores)
+        LB_CHECK(decode_mega_q8_supported(h.dim, h.ff, h.heads, h.vocab), "decode_mega: unsupported Q8 shape");
+        const uint32_t kmax = h.dim > h.ff ? h.dim : h.ff;
+        const size_t smem_q8 = ((2 * (size_t)p.chunk_cap + 3) & ~(size_t)3) * 4 + (size_t)kmax * 4 + (size_t)(kmax / 32) * 32 * 4 + (size_t)(kmax / 32) * 4;
+        LB_CHECK(smem_q8 <= 200 * 1024, "decode_mega: Q8 activation staging does not fit in shared memory");
+        if (vd == 1) e = launch_q8_hd<1>(p, hd, kmax, smem_q8, st);
+        else if (vd == 2) e = launch_q8_hd<2>(p, hd, kmax, smem_q8, st);
+        else if (vd == 3) e = launch_q8_hd<3>(p, hd, kmax, smem_q8, st);
+        else e = launch_q8_hd<4>(p, hd, kmax, smem_q8, st);
+        LB_CUDA(e);
+        count_launch();
+        return;
+    }
     if (vd == 1 && vf == 1) e = launch_hd<1, 1>(p, hd, smem, st);
     else if (vd == 2 && vf == 6) e = launch_hd<2, 6>(p, hd, smem, st);
     else if (vd == 3 && vf == 7) e = launch_hd<3, 7>(p, hd, smem, st);

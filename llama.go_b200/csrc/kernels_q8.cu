@@ -231,6 +231,177 @@ gemv_q8_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (LB_Q8_MMA=1, unmeasured): the Q8 GEMV on the int8 tensor cores.  The activation vector is turned once
+// per GEMV into 4 balanced base-128 digits per element relative to its Q8 block's power-of-two scale
+// (q8_digits_kernel; x = 2^e * sum_j dig_j 128^-(j+1), exact to 2^-28 of the block maximum), stored as ready-made B
+// fragments of `mma.sync.m16n8k32.s8` (digit j = column j; columns 4..7 are zero).  The weights go from HBM into
+// the A fragment AS THEY ARE: in the 4-row interleaved planes one 32-bit word is 4 consecutive k of one row, which
+// is exactly one A register.  Per (16 rows x 32 k) tile: 4 LDG.32 + 1 MMA + 4 I2F + ~8 FP32 ops instead of
+// 3.5 instructions per weight; the s32 dot products are exact.  Index math checked on the CPU, lane by lane, in
+// tools/studies/q8_mma_layout_emulation.py; numerics in tools/studies/q8_int8_digits.py.
+__device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// one warp per Q8 block of the activation vector: lane k holds x[32 b + k]
+__global__ void __launch_bounds__(128) q8_digits_kernel(const float *__restrict__ x, uint32_t K, uint2 *__restrict__ bfrag,
+                                                        float *__restrict__ xs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= (K >> 5)) return;
+    const float v = x[(size_t)b * 32 + lane];
+    const float mx = warp_max(fabsf(v));
+    uint32_t pack = 0;  // digit j in byte j
+    float scale = 0.f;
+    if (mx >= 1e-30f && mx <= 1e30f) {  // outside: the block contributes nothing (or is not finite)
+        const int e = ilogbf(mx) + 2;   // |v| / 2^e < 0.5
+        scale = ldexpf(1.0f, e);
+        float r = v * ldexpf(1.0f, -e);  // exact
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            r *= 128.0f;                 // exact
+            const float dj = rintf(r);   // |dj| <= 64
+            r -= dj;                     // exact
+            pack |= ((uint32_t)(int)dj & 0xffu) << (8 * j);
+        }
+    }
+    // B fragment of lane L = (gid, tig): column gid (< 4: digit gid), rows tig*4..+3 (b0) and 16+tig*4..+3 (b1)
+    const int gid = lane >> 2, tig = lane & 3;
+    uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, pack, tig * 4 + i);
+        const uint32_t hi = __shfl_sync(0xffffffffu, pack, 16 + tig * 4 + i);
+        b0 |= ((lo >> (8 * (gid & 3))) & 0xffu) << (8 * i);
+        b1 |= ((hi >> (8 * (gid & 3))) & 0xffu) << (8 * i);
+    }
+    if (gid >= 4) { b0 = 0; b1 = 0; }
+    bfrag[(size_t)b * 32 + lane] = make_uint2(b0, b1);
+    if (lane == 0) xs[b] = scale;
+}
+
+constexpr int Q8M_U = 4;  // blocks (16 rows x 32 k tiles) in flight per warp
+
+template <bool SWIGLU, int KS>  // KS warps split the K blocks of one 16-row tile (x 2 matrices for SwiGLU)
+__global__ void __launch_bounds__(32 * KS * (SWIGLU ? 2 : 1))
+gemv_q8_mma_kernel(const int8_t *__restrict__ Q1, const float *__restrict__ D1, const int8_t *__restrict__ Q3,
+                   const float *__restrict__ D3, uint32_t M, uint32_t K, const uint2 *__restrict__ bfrag,
+                   const float *__restrict__ xs, float *__restrict__ y, const float *__restrict__ res) {
+    constexpr int NM = SWIGLU ? 2 : 1;
+    __shared__ float part[NM][KS][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int mtx = SWIGLU ? warp / KS : 0, kw = warp % KS;
+    const uint32_t R0 = blockIdx.x * 16, NB = K >> 5, K4 = K >> 2;
+    const uint32_t per = (NB + KS - 1) / KS, b_begin = min((uint32_t)kw * per, NB), b_end = min(b_begin + per, NB);
+    const int8_t *Q = mtx ? Q3 : Q1;
+    const float *D = mtx ? D3 : D1;
+    const uint32_t r_lo = R0 + gid, r_hi = r_lo + 8;
+    // 32-bit word of (row r, k4) in the q plane: ((r/4) * K4 + k4) * 4 + r%4;  this lane's k4 = 8 b + tig (+4)
+    const uint32_t *qa = reinterpret_cast<const uint32_t *>(Q) + ((size_t)(r_lo >> 2) * K4 + tig) * 4 + (r_lo & 3);
+    const uint32_t *qb = reinterpret_cast<const uint32_t *>(Q) + ((size_t)(r_hi >> 2) * K4 + tig) * 4 + (r_hi & 3);
+    const float *da = D + (size_t)(r_lo >> 2) * NB * 4 + (r_lo & 3);
+    const float *db = D + (size_t)(r_hi >> 2) * NB * 4 + (r_hi & 3);
+    // digit weights of this lane's two columns (tig 0: digits 0,1; tig 1: digits 2,3; tig 2,3: zero columns)
+    const float w0 = tig == 0 ? 0x1p-7f : 0x1p-21f, w1 = w0 * 0x1p-7f;
+    float acc_lo = 0.f, acc_hi = 0.f;
+    pdl_launch_dependents();
+    bool waited = false;
+    for (uint32_t bb = b_begin; bb < b_end; bb += Q8M_U) {
+        uint32_t a[Q8M_U][4];
+        float s_lo[Q8M_U], s_hi[Q8M_U], xsc[Q8M_U];
+        uint2 bf[Q8M_U];
+#pragma unroll
+        for (int u = 0; u < Q8M_U; u++) {
+            const uint32_t b = bb + u;
+            const bool ok = b < b_end;
+            const size_t w = (size_t)b * 32;  // 8 units of 4 words per block
+            a[u][0] = ok ? ld_stream_u32(qa + w) : 0u;
+            a[u][1] = ok ? ld_stream_u32(qb + w) : 0u;
+            a[u][2] = ok ? ld_stream_u32(qa + w + 16) : 0u;
+            a[u][3] = ok ? ld_stream_u32(qb + w + 16) : 0u;
+            s_lo[u] = ok ? __ldg(da + (size_t)b * 4) : 0.f;
+            s_hi[u] = ok ? __ldg(db + (size_t)b * 4) : 0.f;
+        }
+        if (!waited) { pdl_wait(); waited = true; }  // weights first, then the digits written by the predecessor grid
+#pragma unroll
+        for (int u = 0; u < Q8M_U; u++) {
+            const uint32_t b = bb + u;
+            const bool ok = b < b_end;
+            bf[u] = ok ? __ldg(bfrag + (size_t)b * 32 + lane) : make_uint2(0u, 0u);
+            xsc[u] = ok ? __ldg(xs + b) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < Q8M_U; u++) {
+            int c0, c1, c2, c3;
+            asm volatile(
+                "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3)
+                : "r"(a[u][0]), "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]), "r"(bf[u].x), "r"(bf[u].y), "r"(0));
+            const float v_lo = fmaf((float)c0, w0, (float)c1 * w1), v_hi = fmaf((float)c2, w0, (float)c3 * w1);
+            acc_lo = fmaf(s_lo[u] * xsc[u], v_lo, acc_lo);
+            acc_hi = fmaf(s_hi[u] * xsc[u], v_hi, acc_hi);
+        }
+    }
+    if (!waited) pdl_wait();
+    // columns: tig 0 and 1 hold the digits, tig 2 and 3 zeros
+    acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 1); acc_lo += __shfl_xor_sync(0xffffffffu, acc_lo, 2);
+    acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 1); acc_hi += __shfl_xor_sync(0xffffffffu, acc_hi, 2);
+    if (tig == 0) { part[mtx][kw][gid] = acc_lo; part[mtx][kw][gid + 8] = acc_hi; }
+    __syncthreads();
+    if (threadIdx.x < 16 && R0 + threadIdx.x < M) {
+        const uint32_t row = R0 + threadIdx.x;
+        float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < KS; i++) {
+            s1 += part[0][i][threadIdx.x];
+            if (SWIGLU) s3 += part[NM - 1][i][threadIdx.x];
+        }
+        float v = SWIGLU ? __fmul_rn(silu_ref(s1), s3) : s1;
+        if (!SWIGLU && res) v = __fadd_rn(v, res[row]);
+        y[row] = v;
+    }
+}
+
+// scratch of the digits (experiment: one buffer per device — callers on several streams of one device would race)
+static void q8_mma_scratch(uint32_t K, uint2 **bfrag, float **xs) {
+    static thread_local int dev_of = -1;
+    static thread_local uint2 *bf = nullptr;
+    static thread_local float *sc = nullptr;
+    static thread_local uint32_t cap = 0;
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (dev != dev_of || (K >> 5) > cap) {
+        const uint32_t nb = (K >> 5) > 1024 ? (K >> 5) : 1024;  // leaked on growth / device change: experiment only
+        LB_CUDA(cudaMalloc(&bf, (size_t)nb * 32 * sizeof(uint2)));
+        LB_CUDA(cudaMalloc(&sc, (size_t)nb * sizeof(float)));
+        cap = nb; dev_of = dev;
+    }
+    *bfrag = bf; *xs = sc;
+}
+
+template <bool SWIGLU>
+static void gemv_q8_mma(const int8_t *Q1, const float *D1, const int8_t *Q3, const float *D3, uint32_t M, uint32_t K, const float *x,
+                        float *y, const float *res, cudaStream_t st) {
+    uint2 *bfrag; float *xs;
+    q8_mma_scratch(K, &bfrag, &xs);
+    const uint32_t NB = K >> 5, tiles = M / 16;
+    launch_pdl(q8_digits_kernel, dim3((NB + 3) / 4), dim3(128), 0, st, x, K, bfrag, xs);
+    const uint32_t want = 148u * 16u;  // warps
+    const uint32_t nm = SWIGLU ? 2 : 1;
+    int ks = 2;
+    while (ks < 16 && tiles * nm * ks < want) ks *= 2;
+    if (SWIGLU && ks > 8) ks = 8;  // 2 * KS warps per block
+#define LB_Q8M(KSV) launch_pdl(gemv_q8_mma_kernel<SWIGLU, KSV>, dim3(tiles), dim3(32 * KSV * nm), 0, st, Q1, D1, Q3, D3, M, K, \
+                               (const uint2 *)bfrag, (const float *)xs, y, res)
+    switch (ks) { case 2: LB_Q8M(2); break; case 4: LB_Q8M(4); break; case 8: LB_Q8M(8); break; default: if constexpr (!SWIGLU) { LB_Q8M(16); } else { LB_Q8M(8); } }
+#undef LB_Q8M
+}
+
 // Resident blocks per SM the double-buffered kernel is compiled for: its grids must fit in ONE wave
 // ([12288 x 4096] = 768 blocks -> 6 per SM; w1|w3 = 688 blocks -> 5; the K-split grids of 1024 blocks -> 7).
 // (A bare minimum of 1 makes ptxas spend registers freely: 128 instead of 96 and a second wave for w1|w3.)
@@ -437,6 +608,8 @@ static void gemv_q8_dispatch(const int8_t *Q1, const float *D1, const int8_t *Q3
     LB_CHECK((K & 31) == 0 && (ldx & 3) == 0 && (M & 3) == 0, "gemv_q8: K must be a multiple of 32 and M of 4");
     const uint32_t groups = M / 4;
     const bool split = groups < 148u * 16u;  // few row groups (wo, w2): split K over the block's warps to fill the SMs
+    static const bool use_mma = getenv("LB_Q8_MMA") != nullptr;  // experiment: int8 tensor cores (1 column, M % 16 == 0)
+    if (use_mma && N == 1 && (M & 15) == 0) { gemv_q8_mma<SWIGLU>(Q1, D1, Q3, D3, M, K, x, y, res, st); return; }
     static const bool sync_loop = getenv("LB_Q8_SYNC") != nullptr;  // A/B aid: the single-buffered loop for every N
 #define LB_Q8_LAUNCH(kern, n, ks)                                                                                                       \
     launch_pdl(kern<n, SWIGLU, ks>, dim3(ks > 1 ? groups : (groups + Q8_WARPS - 1) / Q8_WARPS), dim3(Q8_WARPS * 32), 0, st, Q1, D1, Q3, \

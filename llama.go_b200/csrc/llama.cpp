@@ -213,12 +213,15 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     // (Q8_0 models keep the per-op kernels: a Q8 variant of the megakernel's K-sliced phases was measured
     //  slower — 173 vs 240 tok/s on 7B, too few bytes in flight per warp with 1-byte weights)
     use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
+    // experiment (unmeasured): Q8 megakernel on the int8 tensor cores
+    if (m->q8() && getenv("LB_Q8_MEGA") && k::decode_mega_q8_supported(hp.dim, hp.ff(), hp.heads, hp.vocab)) use_mega = true;
     if (use_mega) {
         std::vector<k::MegaLayerHost> ml(nl);
         for (size_t i = 0; i < nl; i++) {
             const Layer &L = m->layers[i];
             ml[i] = {L.attention_norm, L.wqkv, L.wo, L.ffn_norm, L.w1, L.w3, L.w2,
-                     kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d};
+                     kv_k + i * (size_t)cs * d, kv_v + i * (size_t)cs * d,
+                     L.wqkv8.q, L.wo8.q, L.w18.q, L.w38.q, L.w28.q, L.wqkv8.d, L.wo8.d, L.w18.d, L.w38.d, L.w28.d};
         }
         mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
@@ -274,6 +277,9 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.tokens = tokens_dev; mp.state = state_dev;
         mp.final_norm = model->has_head() ? model->norm : nullptr;
         mp.output = model->has_head() ? model->output : nullptr;
+        mp.q_output = model->has_head() ? model->output8.q : nullptr;
+        mp.d_output = model->has_head() ? model->output8.d : nullptr;
+        mp.q8 = model->q8();
         mp.x = x; mp.y = y; mp.qkv = qkv; mp.attn = attn; mp.act = act; mp.logits = logits;
         const uint32_t hd = hp.head_dim();
         mp.part_o = attn_scratch;
