@@ -119,12 +119,39 @@ def _mem_available_gb():
     return 0.0
 
 
+REF_STREAM_PATH = os.path.join(tempfile.gettempdir(), "lb_reference_stream_7b.json")
+
+
+def _ref_modules():
+    """synth.py (pure Python: hyper-parameters, tensor table, ggjt writer) loaded WITHOUT the product package's
+    ctypes binding, and the oracle wrapper whose liboracle.so generates the synthetic weights — the reference
+    arm never maps libllamab200.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_lb_synth_only", os.path.join(ROOT, "llama.go_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    sys.modules["_lb_synth_only"] = synth   # dataclasses looks the module up while the class is being built
+    spec.loader.exec_module(synth)
+    from oracle import oracle as O
+    O.build()
+    return synth, O
+
+
+def _save_reference_stream(r, hp, prompt, predict, context):
+    """Leave the binary's greedy stream on the full model where the GPU arm (run right after this one on the
+    same box) can pick it up and compare it with lb_generate_greedy."""
+    try:
+        with open(REF_STREAM_PATH, "w") as f:
+            json.dump({"model": "7b", "seed": 0, "prompt": prompt, "predict": predict, "context": context,
+                       "text_hex": r["text"].hex(), "when": time.time()}, f)
+    except Exception as e:
+        sys.stderr.write(f"[bench] could not save the reference stream: {e}\n")
+
+
 def reference_cpu_decode_full(steps, warmup, threads=None):
     """The reference binary on the FULL LLaMA-7B FP32 model (26.9 GB ggjt file in a RAM-backed scratch
     dir, same synthetic weights as the GPU arm): 8-token prompt, then warmup+steps single-token decodes;
     tok/s = steps / sum(EVAL_TIME of the timed decodes).  Needs ~60 GB of host RAM; only used when the box has it."""
-    import llama_go_b200  # noqa: F401
-    from llama_go_b200 import synth
+    synth, O = _ref_modules()
     from oracle import refbin
     threads = threads or os.cpu_count() or 1
     hp = synth.LLAMA_7B
@@ -133,10 +160,11 @@ def reference_cpu_decode_full(steps, warmup, threads=None):
     td = _scratch_dir(28e9)
     try:
         path = os.path.join(td, "llama7b.bin")
-        synth.write_ggjt(path, hp, synth.synth_model_fast(0, hp))
+        synth.write_ggjt(path, hp, O.synth_model(0, hp, synth.tensor_table(hp)))
         r = refbin.run(path, "abcde", predict, context, threads, True, port=18097, timeout=3000)
     finally:
         shutil.rmtree(td, ignore_errors=True)
+    _save_reference_stream(r, hp, "abcde", predict, context)
     dec = r["eval_ms"][1:][warmup:warmup + steps]
     if len(dec) < max(1, steps // 2):
         raise RuntimeError("reference binary produced no timing report:\n" + r["raw"][-2000:].decode("utf-8", "replace"))
@@ -155,8 +183,7 @@ def reference_cpu_decode(steps, warmup, threads=None):
     (t = t_head + L * t_layer), so the full 32-layer figure is extrapolated from the
     two measurements.  Falls back to the C oracle (kind "port") if the binary is not in oracle/_ref.
     """
-    import llama_go_b200  # noqa: F401
-    from llama_go_b200 import synth
+    synth, O = _ref_modules()
     from oracle import refbin
     threads = threads or os.cpu_count() or 1
     dims = (32000, 4096, 256, 32)
@@ -170,7 +197,7 @@ def reference_cpu_decode(steps, warmup, threads=None):
         td = _scratch_dir(4.4e9 + 2.8e9)
         try:
             hp4 = synth.HParams(*dims, 4)
-            tensors4 = list(synth.synth_model_fast(0, hp4))
+            tensors4 = list(O.synth_model(0, hp4, synth.tensor_table(hp4)))
             for L in (2, 4):
                 hp = synth.HParams(*dims, L)
                 names = {n for n, *_ in synth.tensor_table(hp)}
@@ -186,11 +213,10 @@ def reference_cpu_decode(steps, warmup, threads=None):
             shutil.rmtree(td, ignore_errors=True)
     else:
         kind = "port"
-        from oracle import oracle as O
-        O.build(); O.set_dot_mode(True); O.set_threads(threads)
+        O.set_dot_mode(True); O.set_threads(threads)
         for L in (2, 4):
             hp = synth.HParams(*dims, L)
-            om = O.OracleModel(hp).load(synth.synth_model_fast(0, hp))
+            om = O.OracleModel(hp).load(O.synth_model(0, hp, synth.tensor_table(hp)))
             oc = O.OracleContext(om, context)
             oc.eval(synth.prompt_token_ids(prompt.encode()), 0)
             ts = []
@@ -252,6 +278,38 @@ def kernel_traffic(name):
             return json.load(f).get(name)
     except Exception:
         return None
+
+
+def compare_with_reference_stream(llama, synth, model):
+    """If `--impl reference` ran on this box just before (the driver runs it first), it left the reference
+    binary's greedy token stream on the FULL 7B model in REF_STREAM_PATH: generate the same stream with
+    lb_generate_greedy (device sampler, same prompt ids, same temp 1e-6 / penalty 1.1) and compare the printed
+    text.  The CLI can drop the final token(s) (main.go:137-147 poll race), hence prefix-with-80%-coverage."""
+    try:
+        with open(REF_STREAM_PATH) as f:
+            rec = json.load(f)
+        if time.time() - rec["when"] > 6 * 3600 or rec["model"] != "7b" or rec["seed"] != 0:
+            return None
+        ids = synth.prompt_token_ids(rec["prompt"].encode())
+        c = llama.NewContext(model, rec["context"])
+        toks = llama.GenerateGreedy(c, ids, rec["predict"])
+        vocab = synth.byte_vocab(model.hp.vocab)
+        exp = b"".join(vocab[i] for i in toks).strip(b"\n ")
+        got = bytes.fromhex(rec["text_hex"])
+        ok = len(got) > 0 and (got == exp or (exp.startswith(got) and len(got) >= 0.8 * len(exp)))
+        n_match = 0
+        for t in toks:
+            piece = vocab[t]
+            if got[:len(piece)] != piece:
+                break
+            got = got[len(piece):]
+            n_match += 1
+        return {"equal": bool(ok), "tokens_compared": n_match, "tokens_generated": len(toks),
+                "what": "reference binary --avx greedy stream on the full 7B synthetic model vs lb_generate_greedy"}
+    except FileNotFoundError:
+        return None
+    except Exception as e:
+        return {"equal": None, "error": str(e)}
 
 
 def run_single_gpu(args):
@@ -329,6 +387,8 @@ def run_single_gpu(args):
         except Exception as e:  # the baseline is reported, never the target; do not lose the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
+    ref_stream = compare_with_reference_stream(llama, synth, model) if (args.model == "7b" and not q8) else None
+
     line = {
         "metric": metric_name(args.model) if not q8 else "LLaMA-%s INT8 block-quant (Q8_0) decode tokens/sec" % args.model.upper(), "value": value, "unit": UNIT,
         "n_gpus": 1, "steps": K, "warmup": W,
@@ -361,6 +421,7 @@ def run_single_gpu(args):
         "per_op_kernels": kern,
         "prefill_gemm": prefill_gemm,
         "cpu_baseline": cpu,
+        "reference_stream": ref_stream,
     }
     print(json.dumps(line), flush=True)
 

@@ -13,6 +13,29 @@ import numpy as np
 from bench import CTX, MODELS, PROMPT_LEN, UNIT, ClockSampler, measured_peak, metric_name, rank_world
 
 
+def pipeline_parity(stage, hp, device, ctx_size, prompt, gen, n_decoded, S):
+    """Single-GPU reference of the pipelined run on the last rank's GPU: unsharded model (same device RNG, seed 0),
+    prompt prefill + `n_decoded` teacher-forced single-token steps per sequence; returns the worst relative error
+    of the last step's logits over the sequences.  None when the unsharded model does not fit."""
+    from llama_go_b200 import llama
+    full_bytes = 4 * (hp.layers * (4 * hp.dim ** 2 + 3 * hp.dim * hp.ff + 2 * hp.dim) + 2 * hp.vocab * hp.dim + hp.dim)
+    stage_bytes = full_bytes * (stage.end - stage.begin) / hp.layers + 4 * hp.vocab * hp.dim
+    kv_bytes = 2 * 4 * hp.layers * ctx_size * hp.dim
+    if full_bytes + kv_bytes + stage_bytes + S * kv_bytes * (stage.end - stage.begin) / hp.layers + 12e9 > 178e9:
+        return {"rel_err": None}
+    full = llama.Model(hp, device).init_random(0)
+    worst = 0.0
+    c = llama.NewContext(full, ctx_size)
+    for s in range(S):
+        llama.Eval(c, prompt[s], 0)
+        llama.DecodeResident(c, gen[s, :n_decoded], prompt.shape[1])
+        ref = llama.ReadLogits(c).astype(np.float64)
+        got = stage.logits(s).astype(np.float64)
+        worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+    c.ReleaseContext()
+    return {"rel_err": worst}
+
+
 def run_pipeline(args):
     import torch
     import torch.distributed as dist
@@ -85,6 +108,14 @@ def run_pipeline(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e = S * K / e2e_s
 
+    # ---- parity (untimed): the last stage's logits of every in-flight sequence after the LAST pipelined step must
+    #      equal a single-GPU evaluation of the same token history (prompt + every teacher-forced token of the
+    #      four decode passes above) by the unsharded model with the same synthetic weights.
+    parity = pipeline_parity(stage, hp, local, ctx_size, prompt, gen, 2 * W + 2 * K, S) if stage.is_last else None
+    par_t = torch.tensor([-1.0 if parity is None or parity["rel_err"] is None else parity["rel_err"]], dtype=torch.float64)
+    dist.all_reduce(par_t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+
     all_launches = torch.tensor([float(launches)], dtype=torch.float64)
     dist.all_reduce(all_launches, op=dist.ReduceOp.SUM)
     if rank == 0:
@@ -112,6 +143,10 @@ def run_pipeline(args):
                          "peak": peak * world, "unit": "GB/s", "frac": round(agg_gbs / (peak * world), 4), "traffic": None,
                          "peak_source": peak_src + " x n_gpus"},
             "cpu_baseline": None,
+            "parity_rel_err": (float(par_t.item()) if par_t.item() >= 0 else None),
+            "parity": "max over the in-flight sequences of max|logits_pipeline - logits_single_gpu| / max|logits_single_gpu| "
+                      "after the last step (single-GPU lb_eval + lb_decode_resident of the same tokens, unsharded model on the "
+                      "last rank's GPU)" if par_t.item() >= 0 else "skipped: the unsharded model does not fit beside this stage on one GPU",
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

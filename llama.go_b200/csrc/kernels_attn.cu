@@ -319,10 +319,12 @@ void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, f
     LB_CHECK(hd == 32 || hd == 64 || hd == 128, "attention: head dim must be 32, 64 or 128");
     const uint32_t T = max_T;
     size_t smem = (((size_t)T + 3) & ~(size_t)3) * sizeof(float) + (size_t)ATT_THREADS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // function attributes are per device
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         LB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     LB_CHECK(smem <= 200 * 1024, "attention: context too long for the single-pass kernel");
     float scale = (float)(1.0 / sqrt((double)dim / (double)heads));  // llama.go:306

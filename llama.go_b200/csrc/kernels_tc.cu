@@ -382,10 +382,13 @@ bool gemm_tf32x3_supported(uint32_t M, uint32_t K, uint32_t ldx, const float *W,
 
 template <bool Q8>
 static void set_attr_once() {
-    static bool attr = false;
-    if (!attr) {
+    // function attributes are per device: the C-ABI lets one process hold models on several GPUs
+    static bool attr[64] = {};
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         LB_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
 }
 

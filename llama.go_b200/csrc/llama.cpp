@@ -479,6 +479,7 @@ void Context::generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_
     LB_CHECK((uint64_t)n_prompt + predict - 1 <= ctx_size, "generate_greedy : prompt + predict exceeds the context (context swapping is host policy, server.go:165-172)");
     LB_CHECK(predict <= tokens_cap, "generate_greedy : predict too large");
     LB_CHECK(temp > 0.f, "generate_greedy : temp must be > 0 (the reference replaces 0 by 0.5, main.go:379-381)");
+    for (uint32_t i = 0; i < n_prompt; i++) LB_CHECK(prompt[i] < hp.vocab, "generate_greedy : token id out of range");
     LB_CUDA(cudaSetDevice(model->device));
     if (!ring_dev) {
         ring_dev = mem.dmalloc<uint32_t>(ctx_size);

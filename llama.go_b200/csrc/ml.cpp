@@ -112,7 +112,7 @@ Tensor *MulMat(Context *ctx, Tensor *a, Tensor *b) {
     return r;
 }
 Tensor *View1D(Context *ctx, Tensor *a, uint32_t ne0, uint32_t offset) {
-    LB_CHECK((size_t)offset <= a->avail, "View1D : offset out of range");  // Go: slice bounds panic
+    LB_CHECK((size_t)offset + ne0 <= a->avail, "View1D : offset + ne0 out of range");  // Go: slice bounds panic
     Tensor *r = NewTensor(ctx, a->type, 1, ne0, 1, 1, 1, a->data + offset, a->avail - offset);
     r->op = OP_VIEW; r->src0 = a;
     return r;
@@ -215,6 +215,8 @@ static void ComputeForward(Context *ctx, Tensor *t) {
         case OP_ADD:
             LB_CHECK(s1->nb[0] == 4, "ComputeForwardAddFP32 : [src1] is NOT contiguous!");
             LB_CHECK(s0->is_contiguous() && s1->is_contiguous() && t->is_contiguous(), "ComputeForwardAddFP32 : strided rows not supported");
+            LB_CHECK(s0->nelements() == t->nelements() && s1->nelements() == t->nelements(), "ComputeForwardAddFP32 : different element counts!");
+            LB_CHECK(t->nelements() <= t->avail && s0->nelements() <= s0->avail && s1->nelements() <= s1->avail, "ComputeForwardAddFP32 : tensor exceeds its storage");  // Go: slice bounds panic
             k::add(s0->data, s1->data, t->data, t->nelements(), st);
             break;
         case OP_MUL:
@@ -249,11 +251,14 @@ static void ComputeForward(Context *ctx, Tensor *t) {
         case OP_SCALE:
             LB_CHECK(s0->is_contiguous(), "ComputeForwardScaleFP32 : [src0] is NOT contiguous!");
             LB_CHECK(t->is_contiguous(), "ComputeForwardScaleFP32 : [dst] is NOT contiguous!");
+            LB_CHECK(t->nelements() <= t->avail, "ComputeForwardScaleFP32 : tensor exceeds its storage");
             k::scale_inplace(t->data, scalar_of(ctx, s1), t->nelements(), st);
             break;
         case OP_CPY:
             LB_CHECK(t->is_contiguous(), "ComputeForwardDupFP32 : [dst] is NOT contiguous!");
             LB_CHECK(t->nelements() == s0->nelements(), "ComputeForwardDupFP32 : [dst] and [src0] capacities are different!");
+            LB_CHECK(t->nelements() <= t->avail, "ComputeForwardDupFP32 : [dst] exceeds its storage");  // Go: slice bounds panic
+            LB_CHECK(!s0->is_contiguous() || s0->nelements() <= s0->avail, "ComputeForwardDupFP32 : [src0] exceeds its storage");
             if (s0->is_contiguous())
                 LB_CUDA(cudaMemcpyAsync(t->data, s0->data, (size_t)t->nelements() * 4, cudaMemcpyDeviceToDevice, st));
             else

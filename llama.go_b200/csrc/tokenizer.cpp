@@ -75,7 +75,7 @@ std::vector<uint32_t> tokenize(const Vocab &v, const std::string &text, bool bos
         const Symbol &s = sym[i];
         auto it = v.token2id.find(text.substr(s.off, s.n));
         if (it == v.token2id.end()) {
-            for (uint32_t j = 0; j < s.n; j++) out.push_back((uint32_t)(unsigned char)text[s.off + j] + 3);  // byte fallback
+            for (uint32_t j = 0; j < s.n; j++) out.push_back((uint32_t)(uint8_t)((unsigned char)text[s.off + j] + 3));  // byte fallback in Go `byte` arithmetic: 0xFD..0xFF wrap to 0..2 (ml.go:2831)
         } else {
             out.push_back(it->second);
         }

@@ -175,6 +175,8 @@ class PodBatch:
         """tokens[n], pasts[n] -> logits [n][vocab] (row b = llama.Eval(ctxs[b], [tokens[b]], pasts[b]))."""
         t, tp = _toks(tokens)
         p, pp = _toks(pasts)
+        if t.size != len(self.ctxs) or p.size != len(self.ctxs):
+            raise ValueError("PodBatch.Eval: need one token and one position per pod")
         out = np.empty((len(self.ctxs), self.vocab), np.float32)
         check(lib().lb_batch_eval(self._h, tp, pp, out.ctypes.data_as(_f32p)))
         return out
@@ -182,6 +184,8 @@ class PodBatch:
     def DecodeResident(self, tokens, pasts) -> float:
         t = np.ascontiguousarray(tokens, dtype=np.uint32)
         p, pp = _toks(pasts)
+        if t.ndim != 2 or t.shape[0] != len(self.ctxs) or p.size != len(self.ctxs):
+            raise ValueError("PodBatch.DecodeResident: tokens must be [pods][steps], pasts [pods]")
         ms = C.c_float(0)
         check(lib().lb_batch_decode_resident(self._h, t.ctypes.data_as(_u32p), t.shape[1], pp, C.byref(ms)))
         return ms.value

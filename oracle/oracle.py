@@ -138,6 +138,24 @@ class OracleContext:
             pass
 
 
+def synth_fill(seed: int, tid: int, start: int, count: int, mean: float, sigma: float) -> np.ndarray:
+    """Elements [start, start+count) of synthetic tensor `tid` — the recipe of llama.go_b200/synth.py
+    synth_values(), multi-threaded in liboracle.so.  Lets bench.py's reference arm write the 27 GB ggjt file
+    without loading the product library."""
+    f = lib().lo_synth_fill
+    f.restype = None
+    f.argtypes = [_f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_double]
+    out = np.empty(count, np.float32)
+    f(_fp(out), count, seed, tid, start, float(mean), float(sigma))
+    return out
+
+
+def synth_model(seed: int, hp, tensor_table):
+    """(name, ndarray) for every row of synth.tensor_table(hp), generated by synth_fill()."""
+    for name, tid, shape, mean, sigma in tensor_table:
+        yield name, synth_fill(seed, tid, 0, int(np.prod(shape)), mean, sigma).reshape(shape)
+
+
 def set_dot_mode(avx: bool) -> None:
     lib().lo_set_dot_mode(1 if avx else 0)
 

@@ -42,3 +42,24 @@ def test_ggjt_roundtrip(synth):
 
 def test_prompt_ids(synth):
     assert synth.prompt_token_ids(b"abcde") == [1, 35, 35, 100, 101, 102, 103, 104]
+
+
+def test_reference_arm_generates_weights_without_the_product_library():
+    """bench.py --impl reference must not map libllamab200.so: its synthetic weights come
+    from liboracle.so's lo_synth_fill, bit-identical to synth.synth_values()."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, bench\n"
+        "synth, O = bench._ref_modules()\n"
+        "hp = synth.HParams(96, 64, 32, 2, 2)\n"
+        "for (n, a), (n2, b) in zip(O.synth_model(9, hp, synth.tensor_table(hp)), synth.synth_model(9, hp)):\n"
+        "    assert n == n2 and a.shape == b.shape and (a == b).all(), n\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libllamab200' not in maps, 'product library mapped by the reference arm'\n"
+        "assert 'liboracle' in maps\n"
+        "print('REF_ARM_CLEAN')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert out.returncode == 0 and b"REF_ARM_CLEAN" in out.stdout, out.stderr.decode()[-2000:]

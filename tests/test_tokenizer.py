@@ -51,3 +51,7 @@ def test_tokenizer_rules(ml):
     assert ml.Tokenize(v, "ü".encode(), False) == [0xC3 + 3, 0xBC + 3]
     assert ml.Tokenize(v, b"a\xe2\x82", False) == [6, 0xE2 + 3, 0x82 + 3]   # truncated multi-byte tail is clamped (ml.go:2777)
     assert ml.Tokenize(v, b"ab", True) == [1, 3]
+    # Go computes `symbol.Text[j] + 3` in byte arithmetic (ml.go:2831): 0xFD, 0xFE, 0xFF wrap to ids 0, 1, 2
+    assert ml.Tokenize(v, b"\xfd\xfe\xff", False) == [0, 1, 2]
+    assert ml.Tokenize(v, b"a\xfc\xfd", False) == [6, 0xFF, 0]
+    assert ml.Tokenize(v, b"\xff", True) == [1, 2]
