@@ -127,6 +127,27 @@ bool decode_mega_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_
 uint32_t decode_mega_splits(uint32_t heads);
 void decode_mega(const MegaParamsHost &p, cudaStream_t st);
 
+// ---- persistent pod-batch megakernel (kernels_mega_pods.cu): one decode step of B <= 8 pods, weights streamed once,
+//      B-column MulMat on the tensor cores (mma.sync tf32, 3xTF32 split in registers)
+struct MegaPodsParamsHost {
+    const MegaLayerHost *layers_dev;
+    uint32_t n_layers, B;
+    const float *tok_embeddings;
+    const uint32_t *tokens;        // device [B][tok_stride]
+    uint32_t tok_stride;
+    const uint32_t *state;         // device {unused, step}
+    const uint32_t *pasts;         // device [B]
+    float *const *Kb, *const *Vb;  // device [B]: cache bases of the pods
+    const float *final_norm, *output;
+    float *x, *y, *qkv, *attn, *act, *logits;
+    float *part_o, *part_ml;
+    unsigned *barrier;             // 2 counters, zeroed by the launcher
+    uint32_t dim, ff, heads, vocab, ctx;
+};
+bool decode_mega_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
+uint32_t decode_mega_pods_splits(uint32_t B, uint32_t heads);
+void decode_mega_pods(const MegaPodsParamsHost &p, cudaStream_t st);
+
 // ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
 // W / out are plain row-major [rows][K]; q / d are the 4-row-interleaved planes (rows % 4 == 0, K % 32 == 0)
 void quantize_q8(const float *W, int8_t *q, float *d, uint32_t rows, uint32_t K, cudaStream_t st);

@@ -137,6 +137,9 @@ struct PodBatch {
     float *logits_host = nullptr;
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool use_mega = false;              // one persistent megakernel per step (kernels_mega_pods.cu)
+    void *mega_layers_dev = nullptr;    // k::MegaLayerHost[layers]
+    unsigned *mega_barrier = nullptr;
 
     explicit PodBatch(const std::vector<Context *> &ctxs);
     ~PodBatch();

@@ -4,6 +4,8 @@
 // evals are HBM-bound on the same weights, so the B tokens are evaluated as one B-column MulMat per
 // weight: the weights stream once for B tokens.  Every pod keeps its own cache and position; RoPE, the
 // KV store and attention run per pod inside one launch (blockIdx.z / row = pod).
+#include <stdlib.h>
+
 #include "llama.hpp"
 
 namespace lb {
@@ -44,6 +46,23 @@ PodBatch::PodBatch(const std::vector<Context *> &cs) : ctxs(cs) {
     logits_host = mem.hmalloc<float>(B * V);
     ev0 = mem.event();
     ev1 = mem.event();
+    // one persistent megakernel per step (kernels_mega_pods.cu) for FP32 weights and supported shapes;
+    // LB_NO_MEGA_PODS=1 keeps the per-op B-column kernels
+    use_mega = getenv("LB_NO_MEGA_PODS") == nullptr && !model->q8() &&
+               k::decode_mega_pods_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, ctx_size);
+    if (use_mega) {
+        const size_t nl = model->layers.size();
+        std::vector<k::MegaLayerHost> ml(nl);
+        for (size_t i = 0; i < nl; i++) {
+            const Layer &L = model->layers[i];
+            ml[i] = k::MegaLayerHost();
+            ml[i].attention_norm = L.attention_norm; ml[i].wqkv = L.wqkv; ml[i].wo = L.wo; ml[i].ffn_norm = L.ffn_norm;
+            ml[i].w1 = L.w1; ml[i].w3 = L.w3; ml[i].w2 = L.w2;
+        }
+        mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
+        LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
+        mega_barrier = mem.dmalloc<unsigned>(2);
+    }
 }
 
 PodBatch::~PodBatch() {
@@ -64,6 +83,22 @@ void PodBatch::forward() {
     const HParams &hp = model->hp;
     const uint32_t d = hp.dim, ff = hp.ff(), V = hp.vocab, H = hp.heads;
     cudaStream_t st = stream;
+    if (use_mega) {
+        k::MegaPodsParamsHost mp;
+        mp.layers_dev = static_cast<const k::MegaLayerHost *>(mega_layers_dev);
+        mp.n_layers = (uint32_t)model->layers.size(); mp.B = B;
+        mp.tok_embeddings = model->tok_embeddings; mp.tokens = tokens_dev; mp.tok_stride = kTokensCap;
+        mp.state = state_dev; mp.pasts = pasts_dev; mp.Kb = kb_dev; mp.Vb = vb_dev;
+        mp.final_norm = model->norm; mp.output = model->output;
+        mp.x = x; mp.y = y; mp.qkv = qkv; mp.attn = attn; mp.act = act; mp.logits = logits;
+        mp.part_o = attn_scratch;
+        mp.part_ml = attn_scratch + (size_t)B * H * 32 * hp.head_dim();
+        mp.barrier = mega_barrier;
+        mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
+        k::decode_mega_pods(mp, st);
+        k::advance_pods(pasts_dev, state_dev, B, st);
+        return;
+    }
     PodPtrs pp;
     pp.K = kb_dev; pp.V = vb_dev; pp.pasts = pasts_dev; pp.ldq = 3 * d; pp.ldo = d;
     k::get_rows_pods(model->tok_embeddings, d, tokens_dev, kTokensCap, state_dev + 1, B, x, st);
@@ -130,7 +165,7 @@ void PodBatch::eval(const uint32_t *tokens, const uint32_t *pasts, float *logits
     stage_inputs(tokens, 1, pasts);
     ensure_graph();
     LB_CUDA(cudaGraphLaunch(graph, stream));
-    count_launch(model->layers.size() * 8 + 4);
+    count_launch(use_mega ? 2 : model->layers.size() * 8 + 4);
     const size_t nb = (size_t)B * model->hp.vocab * sizeof(float);
     if (logits_out) LB_CUDA(cudaMemcpyAsync(logits_host, logits, nb, cudaMemcpyDeviceToHost, stream));
     LB_CUDA(cudaStreamSynchronize(stream));
@@ -144,7 +179,7 @@ float PodBatch::decode_resident(const uint32_t *tokens, uint32_t steps, const ui
     LB_CUDA(cudaEventRecord(ev0, stream));
     for (uint32_t i = 0; i < steps; i++) {
         LB_CUDA(cudaGraphLaunch(graph, stream));
-        count_launch(model->layers.size() * 8 + 4);
+        count_launch(use_mega ? 2 : model->layers.size() * 8 + 4);
     }
     LB_CUDA(cudaEventRecord(ev1, stream));
     LB_CUDA(cudaStreamSynchronize(stream));

@@ -31,7 +31,7 @@ int main(int argc, char **argv) {
     if (!m) return fail("lb_model_create");
     if (lb_model_init_random(m, seed)) return fail("lb_model_init_random");
     float norm[64];
-    for (int i = 0; i < 64; i++) norm[i] = 1.0f + 0.01f * (float)i;
+    for (int i = 0; i < 64; i++) norm[i] = 1.0f + (float)i / 64.0f;   /* exactly representable: the Python side builds the same bits */
     if (lb_model_set_tensor(m, "norm.weight", LB_TYPE_F32, norm, sizeof norm)) return fail("lb_model_set_tensor");
     if (!lb_model_set_tensor(m, "layers.0.bogus.weight", LB_TYPE_F32, norm, sizeof norm)) {
         fprintf(stderr, "consumer: unknown tensor name was accepted\n");  /* llama.go:906-910 aborts */

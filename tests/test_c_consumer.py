@@ -46,7 +46,7 @@ def test_c_consumer_runs_eval_and_matches_the_ctypes_path(tmp_path):
     got_d = np.array([float.fromhex(x[2:]) for x in lines if x.startswith("D ")], np.float32)
     hp = synth.HParams(96, 64, 32, 2, 2)
     model = llama.Model(hp).init_random(7)
-    model.set_tensor("norm.weight", (1.0 + 0.01 * np.arange(64)).astype(np.float32))
+    model.set_tensor("norm.weight", (1.0 + np.arange(64) / 64.0).astype(np.float32))
     lctx = llama.NewContext(model, 32)
     ref_p = llama.Eval(lctx, [1, 35, 36, 90, 7], 0).copy()
     ref_d = llama.Eval(lctx, [11], 5).copy()

@@ -73,3 +73,40 @@ def test_pod_batch_resident_and_checks(L, synth):
         batch.Eval([1, 2, 3, 4], [rec["context"]] * 4)        # position outside the context
     with pytest.raises(L.LlamaB200Error):
         L.PodBatch([L.NewContext(model, 64) for _ in range(9)])
+
+
+@pytest.mark.parametrize("B", [8, 2])
+def test_pod_batch_7b_shaped_at_T400_matches_solo_decodes(L, synth, B):
+    """Exact LLaMA-7B layer shapes (2 layers, vocab cut to 2048), context 512, pods at positions 400 + 3b: the
+    pod-batch megakernel (B-column MulMat on the tensor cores, 3xTF32; w2 walks K = 11008 in 4 streamed passes;
+    B = 8 -> one attention item per (pod, head), B = 2 -> 4 splits + merge) against each pod's own single-sequence
+    decode, which tests/test_gpu_longctx.py checks against the oracle at the same T."""
+    hp = synth.HParams(2048, 4096, 256, 32, 2)
+    model = L.Model(hp).init_random(0)
+    rs = np.random.RandomState(3)
+    pods, solo, pasts = [], [], []
+    for b in range(B):
+        n = 400 + 3 * b
+        ids = rs.randint(3, hp.vocab, size=n).astype(np.uint32)
+        pc, sc = L.NewContext(model, 512), L.NewContext(model, 512)
+        L.Eval(pc, ids, 0)
+        L.Eval(sc, ids, 0)
+        pods.append(pc); solo.append(sc); pasts.append(n)
+    batch = L.PodBatch(pods)
+    worst = 0.0
+    for step in range(3):
+        toks = rs.randint(3, hp.vocab, size=B).astype(np.uint32)
+        got = batch.Eval(toks, [p + step for p in pasts])
+        for b in range(B):
+            ref = L.Eval(solo[b], [int(toks[b])], pasts[b] + step)
+            err = np.abs(got[b] - ref).max() / np.abs(ref).max()
+            worst = max(worst, err)
+            assert err <= 2e-5, f"pod {b} step {step}: rel err {err:.3e}"
+            assert int(np.argmax(got[b])) == int(np.argmax(ref))
+    # the pods' caches hold what the batch wrote: K/V rows of the last step equal the solo contexts'
+    for b in (0, B - 1):
+        kp, vp = pods[b].kv(1, pasts[b] + 2, 1)
+        ks, vs = solo[b].kv(1, pasts[b] + 2, 1)
+        np.testing.assert_allclose(kp, ks, rtol=0, atol=2e-5 * np.abs(ks).max())
+        np.testing.assert_allclose(vp, vs, rtol=0, atol=2e-5 * np.abs(vs).max())
+    print(f"[pods B={B}, 7B-shaped, T~400] worst rel err vs solo {worst:.3e}")
