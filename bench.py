@@ -312,6 +312,134 @@ def compare_with_reference_stream(llama, synth, model):
         return {"equal": None, "error": str(e)}
 
 
+def _repeats_for(K, est_ms_per_step, target_s=2.0, cap=64):
+    """How many times the K-step timed region is repeated so that the clocks sampler (100 ms period) sees
+    >= ~2 s of load even at the driver's --steps 20 (0.09 s per region).  Every region is exactly K steps,
+    bracketed by CUDA events; the reported time is the mean over the regions."""
+    return int(min(cap, max(1, np.ceil(target_s / max(1e-6, K * est_ms_per_step / 1e3)))))
+
+
+def measure_decode(llama, lib, hp, q8, ctx_size, K, W, sampler=None):
+    """One single-GPU decode measurement: model (device RNG, seed 0) + context, prompt prefill, `value` (device
+    resident, CUDA events) and `e2e` (lb_eval with host buffers).  Returns a dict that keeps model/lctx alive."""
+    t_setup = time.time()
+    model = llama.Model(hp, weight_type=llama.LB_TYPE_Q8_0 if q8 else llama.LB_TYPE_F32).init_random(0)
+    lctx = llama.NewContext(model, ctx_size)
+    rs = np.random.RandomState(0)
+    prompt = rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32)
+    gen = rs.randint(3, hp.vocab, size=W + K).astype(np.uint32)
+    llama.Eval(lctx, prompt, 0)                         # prefill (setup, untimed; first call also sets kernel attributes)
+    t_setup = time.time() - t_setup
+    lib.lb_context_synchronize(lctx._h)
+    t0 = time.perf_counter()
+    llama.Eval(lctx, prompt, 0)                         # the same prefill again, timed: synchronous call, host buffers
+    prefill_s = time.perf_counter() - t0
+
+    # ---- value: device-resident decode, CUDA events on the engine's stream
+    w_ms = llama.DecodeResident(lctx, gen[:max(W, 1)], PROMPT_LEN)    # warm-up (also captures the CUDA graph)
+    w_ms = llama.DecodeResident(lctx, gen[:max(W, 1)], PROMPT_LEN)
+    lib.lb_context_synchronize(lctx._h)
+    R = _repeats_for(K, w_ms / max(W, 1))
+    if sampler:
+        sampler.start()
+    l0 = lib.lb_kernel_launches()
+    reps = [llama.DecodeResident(lctx, gen[W:W + K], PROMPT_LEN + W) for _ in range(R)]
+    lib.lb_context_synchronize(lctx._h)
+    launches = (lib.lb_kernel_launches() - l0) // R
+    ms = float(np.mean(reps))
+    value = K / (ms / 1e3)
+
+    # ---- e2e: public API, host buffers, one synchronous lb_eval per token
+    for i in range(W):
+        llama.Eval(lctx, gen[i:i + 1], PROMPT_LEN + i)
+    lib.lb_context_synchronize(lctx._h)
+    e2e_reps = []
+    for _ in range(R):
+        t0 = time.perf_counter()
+        for i in range(K):
+            llama.Eval(lctx, gen[W + i:W + i + 1], PROMPT_LEN + W + i)
+        lib.lb_context_synchronize(lctx._h)
+        e2e_reps.append(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    e2e = K / float(np.mean(e2e_reps))
+    T_mid = PROMPT_LEN + W + K / 2.0
+    bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+    return {"model": model, "lctx": lctx, "value": value, "ms": ms, "e2e": e2e, "launches": int(launches), "clocks": clocks,
+            "repeats": R, "repeat_ms": [round(r, 3) for r in reps], "setup_s": t_setup, "bytes_per_token": int(bytes_per_token),
+            "prefill": {"tokens": PROMPT_LEN, "ms": round(prefill_s * 1e3, 2), "tok_s": round(PROMPT_LEN / prefill_s, 1),
+                        "what": "lb_eval of the %d-token prompt (host buffers, synchronous; tcgen05 3xTF32 GEMMs + prefill attention)" % PROMPT_LEN}}
+
+
+def sub_record(r, peak, what, K, W, extra=None):
+    gbs = r["bytes_per_token"] * r["value"] / 1e9
+    rec = {"workload": what, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K, "steps": K, "warmup": W, "repeats": r["repeats"],
+           "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "prefill": r["prefill"],
+           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                        "bytes_per_step": r["bytes_per_token"], "roofline_tok_s": round(peak * 1e9 / r["bytes_per_token"], 1)}}
+    if extra:
+        rec.update(extra)
+    return rec
+
+
+def measure_pods(llama, lib, hp, B, ctx_size, K, W, sampler=None):
+    """B pods of one model decoded in one pass over the weights per step: aggregate tokens/s."""
+    model = llama.Model(hp).init_random(0)
+    rs = np.random.RandomState(0)
+    pods = [llama.NewContext(model, ctx_size) for _ in range(B)]
+    for c in pods:
+        llama.Eval(c, rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32), 0)
+    gen = rs.randint(3, hp.vocab, size=(B, 2 * W + 2 * K)).astype(np.uint32)
+    batch = llama.PodBatch(pods)
+    w_ms = batch.DecodeResident(gen[:, :W], [PROMPT_LEN] * B)
+    w_ms = batch.DecodeResident(gen[:, :W], [PROMPT_LEN] * B)
+    R = _repeats_for(K, w_ms / max(W, 1))
+    if sampler:
+        sampler.start()
+    l0 = lib.lb_kernel_launches()
+    reps = [batch.DecodeResident(gen[:, W:W + K], [PROMPT_LEN + W] * B) for _ in range(R)]
+    launches = (lib.lb_kernel_launches() - l0) // R
+    ms = float(np.mean(reps))
+    value = B * K / (ms / 1e3)
+    for i in range(W):
+        batch.Eval(gen[:, W + K + i], [PROMPT_LEN + W + K + i] * B)
+    t0 = time.perf_counter()
+    for i in range(K):
+        batch.Eval(gen[:, 2 * W + K + i], [PROMPT_LEN + 2 * W + K + i] * B)
+    e2e = B * K / (time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    T_mid = PROMPT_LEN + W + K / 2.0
+    bytes_per_step = model.weight_bytes_per_token + B * (2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab)
+    mega = os.environ.get("LB_NO_MEGA_PODS") is None
+    return {"value": value, "ms": ms, "e2e": e2e, "launches": int(launches), "clocks": clocks, "repeats": R,
+            "bytes_per_step": int(bytes_per_step), "B": B,
+            "decode_path": ("pod-batch megakernel: one persistent launch per step, B-column MulMat on mma.sync tf32 (3xTF32)" if mega
+                            else "per-op kernels, B-column GEMV, CUDA-graph replay")}
+
+
+def pods_record(r, peak, peak_src, what, K, W):
+    gbs = r["bytes_per_step"] * (r["value"] / r["B"]) / 1e9
+    return {"workload": what, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K, "steps": K, "warmup": W, "repeats": r["repeats"],
+            "sequences_in_flight": r["B"], "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "decode_path": r["decode_path"],
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(gbs / peak, 4), "bytes_per_step": r["bytes_per_step"], "peak_source": peak_src,
+                         "roofline_tok_s": round(r["B"] * peak * 1e9 / r["bytes_per_step"], 1),
+                         "note": "bytes per step = weights once + %d x (KV read/write + logits)" % r["B"]}}
+
+
+def release(*objs):
+    import gc
+    for o in objs:
+        for name in ("free", "ReleaseContext"):
+            f = getattr(o, name, None)
+            if f:
+                try:
+                    f()
+                except Exception:
+                    pass
+    gc.collect()
+
+
 def run_single_gpu(args):
     import ctypes as C
     import llama_go_b200  # noqa: F401
@@ -322,38 +450,10 @@ def run_single_gpu(args):
     K, W = args.steps, args.warmup
     q8 = args.weights == "q8"
     ctx_size = max(args.context or (1024 if q8 else CTX), PROMPT_LEN + 2 * W + K + 1)   # config 3 (Q8) is quoted at context 1024
-    t_setup = time.time()
-    model = llama.Model(hp, weight_type=llama.LB_TYPE_Q8_0 if q8 else llama.LB_TYPE_F32).init_random(0)
-    lctx = llama.NewContext(model, ctx_size)
-    rs = np.random.RandomState(0)
-    prompt = rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32)
-    gen = rs.randint(3, hp.vocab, size=W + K).astype(np.uint32)
-    llama.Eval(lctx, prompt, 0)                         # prefill (setup, untimed)
-    t_setup = time.time() - t_setup
-
-    # ---- value: device-resident decode, CUDA events on the engine's stream
-    llama.DecodeResident(lctx, gen[:max(W, 1)], PROMPT_LEN)           # warm-up (also captures the CUDA graph)
-    check = lib.lb_context_synchronize
-    check(lctx._h)
     sampler = ClockSampler(0)
-    sampler.start()
-    l0 = lib.lb_kernel_launches()
-    ms = llama.DecodeResident(lctx, gen[W:W + K], PROMPT_LEN + W)
-    check(lctx._h)
-    launches = lib.lb_kernel_launches() - l0
-    value = K / (ms / 1e3)
-
-    # ---- e2e: public API, host buffers, one synchronous lb_eval per token
-    for i in range(W):
-        llama.Eval(lctx, gen[i:i + 1], PROMPT_LEN + i)
-    check(lctx._h)
-    t0 = time.perf_counter()
-    for i in range(K):
-        llama.Eval(lctx, gen[W + i:W + i + 1], PROMPT_LEN + W + i)
-    check(lctx._h)
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-    e2e = K / e2e_s
+    r = measure_decode(llama, lib, hp, q8, ctx_size, K, W, sampler)
+    model, lctx, value, ms, e2e, launches, clocks = r["model"], r["lctx"], r["value"], r["ms"], r["e2e"], r["launches"], r["clocks"]
+    t_setup, repeats, repeat_ms, prefill_rec = r["setup_s"], r["repeats"], r["repeat_ms"], r["prefill"]
 
     # ---- roofline of the dominant kernel + per-kernel table (live CUDA-event timing)
     peak, peak_src = measured_peak()
@@ -374,31 +474,63 @@ def run_single_gpu(args):
                     "us": round(msk.value * 1e3 / 16, 1), "fp32_equiv_TFLOPs": round(fl.value / (msk.value / 16 * 1e-3) / 1e12, 1),
                     "tensor_TFLOPs_issued": round(3 * fl.value / (msk.value / 16 * 1e-3) / 1e12, 1)}
     dom = kern[names[2]]
-    T_mid = PROMPT_LEN + W + K / 2.0
-    bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+    bytes_per_token = r["bytes_per_token"]
     step_gbs = bytes_per_token * value / 1e9
 
-    mega = ((not q8) and os.environ.get("LB_NO_MEGA") is None) or (q8 and os.environ.get("LB_Q8_MEGA") is not None)
+    mega = (not q8) and os.environ.get("LB_NO_MEGA") is None
+    ref_stream = compare_with_reference_stream(llama, synth, model) if (args.model == "7b" and not q8) else None
+
+    # ---- the other single-GPU BASELINE configurations, same process, weights freed in between
+    configs = None
+    if args.model == "7b" and not q8 and not args.no_configs:
+        configs = {}
+        release(lctx, model)
+        lctx = model = r = None
+        try:
+            rq = measure_decode(llama, lib, synth.LLAMA_7B, True, max(1024, PROMPT_LEN + 2 * W + K + 1), K, W, ClockSampler(0))
+            configs["q8_7b_ctx1024"] = sub_record(rq, peak, "BASELINE config 3: LLaMA-7B INT8 block-quant (Q8_0) decode, context 1024, %d-token prompt" % PROMPT_LEN, K, W,
+                                                  {"dtype": "q8_0 weights x f32 activations"})
+            release(rq["lctx"], rq["model"])
+            rq = None
+        except Exception as e:
+            configs["q8_7b_ctx1024"] = {"error": str(e)}
+        try:
+            rp = measure_pods(llama, lib, synth.LLAMA_7B, 8, max(CTX, PROMPT_LEN + 2 * W + 2 * K + 2), K, W, ClockSampler(0))
+            configs["pods8"] = pods_record(rp, peak, peak_src, "LLaMA-7B FP32, 8 pods (independent sequences, server.go:84-106) batched per weight pass, "
+                                           "context 512, %d-token prompts" % PROMPT_LEN, K, W)
+            rp = None
+            release()
+        except Exception as e:
+            configs["pods8"] = {"error": str(e)}
+        try:
+            r13 = measure_decode(llama, lib, synth.LLAMA_13B, False, max(CTX, PROMPT_LEN + 2 * W + K + 1), K, W, ClockSampler(0))
+            configs["llama13b_1gpu"] = sub_record(r13, peak, "LLaMA-13B FP32 single-sequence decode on 1 GPU, context 512 (BASELINE config 4's model, unsharded)", K, W,
+                                                  {"dtype": "f32"})
+            release(r13["lctx"], r13["model"])
+            r13 = None
+        except Exception as e:
+            configs["llama13b_1gpu"] = {"error": str(e)}
+
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            r = reference_cpu_decode(steps=12, warmup=2)
-            cpu = {"value": r["tok_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            rc = reference_cpu_decode(steps=12, warmup=2)
+            cpu = {"value": rc["tok_s"], "unit": UNIT, "cores": rc["cores"], "kind": rc["kind"], "sample": rc["sample"]}
         except Exception as e:  # the baseline is reported, never the target; do not lose the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
-    ref_stream = compare_with_reference_stream(llama, synth, model) if (args.model == "7b" and not q8) else None
-
+    wbytes = bytes_per_token - (2 * hp.layers * (PROMPT_LEN + W + K / 2.0) * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab)
     line = {
         "metric": metric_name(args.model) if not q8 else "LLaMA-%s INT8 block-quant (Q8_0) decode tokens/sec" % args.model.upper(), "value": value, "unit": UNIT,
-        "n_gpus": 1, "steps": K, "warmup": W,
+        "n_gpus": 1, "steps": K, "warmup": W, "repeats": repeats, "repeat_ms": repeat_ms,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if not q8 else "q8_0 weights x f32 activations", "data": "synthetic",
         "config": {"workload": "LLaMA-%s %s single-sequence decode, context %d, %d-token prompt prefilled, past %d..%d"
                                % (args.model.upper(), "Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
-                   "weights": "random-init (device RNG, seed 0) %.1f GB" % (model.weight_bytes_per_token / 1e9), "kv_cache": "fp32 in HBM",
-                   "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (%.1f GB weights per step)" % (model.weight_bytes_per_token / 1e9),
+                   "weights": "random-init (device RNG, seed 0) %.1f GB" % (wbytes / 1e9), "kv_cache": "fp32 in HBM",
+                   "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (%.1f GB weights per step)" % (wbytes / 1e9),
                    "decode_path": "persistent cooperative megakernel, CUDA-graph replay" if mega else "per-op kernels + PDL, CUDA-graph replay",
+                   "timed_regions": "%d regions of exactly %d steps each (CUDA events), mean reported" % (repeats, K),
                    "setup_s": round(t_setup, 1)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 + 8, "d2h_bytes_per_step": 4 * hp.vocab,
@@ -411,17 +543,19 @@ def run_single_gpu(args):
                       "note": "algorithmic bytes of one token (SURVEY 8d: weights + KV read/write + logits) / CUDA-event time per graph replay "
                               "(memset + megakernel + 1-thread state advance)"}
                      if mega else
-                     {"bound": "hbm", "kernel": ("gemv_q8_db_kernel<1, swiglu> (w1,w3)" if q8 else "gemv_swiglu_kernel (w1,w3)"),
+                     {"bound": "hbm", "kernel": ("gemv_q8 (w1,w3 SwiGLU)" if q8 else "gemv_swiglu_kernel (w1,w3)"),
                       "achieved": dom["GB/s"], "peak": peak,
                       "unit": "GB/s", "frac": round(dom["GB/s"] / peak, 4),
                       "traffic": kernel_traffic("gemv_q8_db_kernel_swiglu" if q8 else "gemv_swiglu_kernel"),
                       "peak_source": peak_src, "bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"]}),
         "step_roofline": {"bytes_per_token": int(bytes_per_token), "achieved_GBs": round(step_gbs, 1),
                           "frac": round(step_gbs / peak, 4), "roofline_tok_s": round(peak * 1e9 / bytes_per_token, 1)},
+        "prefill": prefill_rec,
         "per_op_kernels": kern,
         "prefill_gemm": prefill_gemm,
         "cpu_baseline": cpu,
         "reference_stream": ref_stream,
+        "configs": configs,
     }
     print(json.dumps(line), flush=True)
 
@@ -435,45 +569,19 @@ def run_pods(args):
     hp = getattr(synth, MODELS[args.model])
     K, W, B = args.steps, args.warmup, args.pods
     ctx_size = max(args.context or CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
-    model = llama.Model(hp).init_random(0)
-    rs = np.random.RandomState(0)
-    pods = [llama.NewContext(model, ctx_size) for _ in range(B)]
-    for c in pods:
-        llama.Eval(c, rs.randint(3, hp.vocab, size=PROMPT_LEN).astype(np.uint32), 0)
-    gen = rs.randint(3, hp.vocab, size=(B, 2 * W + 2 * K)).astype(np.uint32)
-    batch = llama.PodBatch(pods)
-    batch.DecodeResident(gen[:, :W], [PROMPT_LEN] * B)
-    sampler = ClockSampler(0); sampler.start()
-    l0 = lib.lb_kernel_launches()
-    ms = batch.DecodeResident(gen[:, W:W + K], [PROMPT_LEN + W] * B)
-    launches = lib.lb_kernel_launches() - l0
-    value = B * K / (ms / 1e3)
-    for i in range(W):
-        batch.Eval(gen[:, W + K + i], [PROMPT_LEN + W + K + i] * B)
-    t0 = time.perf_counter()
-    for i in range(K):
-        batch.Eval(gen[:, 2 * W + K + i], [PROMPT_LEN + 2 * W + K + i] * B)
-    e2e = B * K / (time.perf_counter() - t0)
-    clocks = sampler.stop()
+    r = measure_pods(llama, lib, hp, B, ctx_size, K, W, ClockSampler(0))
     peak, peak_src = measured_peak()
-    T_mid = PROMPT_LEN + W + K / 2.0
-    bytes_per_step = model.weight_bytes_per_token + B * (2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab)
-    gbs = bytes_per_step * (value / B) / 1e9
-    print(json.dumps({
-        "metric": "LLaMA-%s FP32 decode tokens/sec, aggregate over %d pods batched per weight pass" % (args.model.upper(), B),
-        "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "LLaMA-%s FP32, %d independent sequences (pods), one token each per step, context %d, %d-token prompts"
-                               % (args.model.upper(), B, ctx_size, PROMPT_LEN), "sequences_in_flight": B, "l2": "inputs>L2",
-                   "decode_path": "per-op kernels, B-column GEMV, CUDA-graph replay"},
-        "clocks": clocks,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * B + 8, "d2h_bytes_per_step": 4 * hp.vocab * B,
-                "api": "lb_batch_eval (host buffers, synchronous)"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src,
-                     "note": "bytes per step = weights once + %d x (KV + logits)" % B},
-        "cpu_baseline": None}), flush=True)
+    rec = pods_record(r, peak, peak_src, "LLaMA-%s FP32, %d independent sequences (pods), one token each per step, context %d, %d-token prompts"
+                      % (args.model.upper(), B, ctx_size, PROMPT_LEN), K, W)
+    line = {"metric": "LLaMA-%s FP32 decode tokens/sec, aggregate over %d pods batched per weight pass" % (args.model.upper(), B),
+            "value": rec["value"], "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "repeats": rec["repeats"], "ms_per_step": rec["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": rec["workload"], "sequences_in_flight": B, "l2": "inputs>L2", "decode_path": rec["decode_path"]},
+            "clocks": rec["clocks"],
+            "e2e": {"value": rec["e2e"], "unit": UNIT, "h2d_bytes_per_step": 8 * B + 8, "d2h_bytes_per_step": 4 * hp.vocab * B,
+                    "api": "lb_batch_eval (host buffers, synchronous)"},
+            "gpu_launches": rec["gpu_launches"], "roofline": dict(rec["roofline"], traffic=None), "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -483,6 +591,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configurations appended to the headline line")
     ap.add_argument("--weights", default="f32", choices=["f32", "q8"], help="q8 = BASELINE config 3 (not the headline metric)")
     ap.add_argument("--model", default="7b", choices=sorted(MODELS), help="default 7b = the headline metric; 13b/65b = BASELINE configs 4-5")
     ap.add_argument("--context", type=int, default=0, help="override the context size (BASELINE config 5 uses 2048)")

@@ -127,6 +127,11 @@ bool decode_mega_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_
 uint32_t decode_mega_splits(uint32_t heads);
 void decode_mega(const MegaParamsHost &p, cudaStream_t st);
 
+// ---- the same token as one persistent kernel fed by a producer warp through a shared-memory ring of TMA bulk copies
+//      (kernels_ring.cu): the weight stream runs ahead across phases and grid barriers
+bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
+void decode_ring(const MegaParamsHost &p, cudaStream_t st);
+
 // ---- persistent pod-batch megakernel (kernels_mega_pods.cu): one decode step of B <= 8 pods, weights streamed once,
 //      B-column MulMat on the tensor cores (mma.sync tf32, 3xTF32 split in registers)
 struct MegaPodsParamsHost {

@@ -1,0 +1,590 @@
+// kernels_ring.cu — the single-token forward pass (llama.Eval with N = 1, pkg/llama/llama.go:211-426) as ONE
+// persistent cooperative kernel whose weight stream never stops: a dedicated producer warp copies every weight
+// this CTA will need, in schedule order, from HBM into a shared-memory ring with cp.async.bulk (the TMA copy
+// engine, completion on mbarriers), and runs AHEAD of the 16 consumer warps — across row tiles, across phases,
+// across the grid barriers and the attention phase.  Weights do not depend on anything computed in the launch,
+// so the only thing that ever stops the stream is a full ring.
+//
+// Why (profiles/README.md, round 1): the register-fed megakernel (kernels_mega.cu) streams its four MulMat
+// phases at ~7.0 TB/s but leaves HBM idle for ~11 us of grid barriers and ~4 us of attention per 137 us layer
+// (0.914 of the measured-peak roofline); L2 prefetch hints issued around the barriers measured no gain
+// (round 2, profiles/README.md).  A ring of 9 x 16 KB per SM holds ~3.3 us of the CTA's share of the stream.
+//
+// Layout of the stream: a MulMat phase gives CTA c a contiguous block of ~M/148 output rows; the block is cut
+// into tiles of 16 rows and every tile into K/256 segments; one ring slot = 16 rows x 256 floats, filled by 16
+// bulk copies of 1 KB (one per lane of the producer warp).  Consumer warp w owns ROW w of the tile: per slot it
+// reads its 1 KB row segment (two conflict-free LDS.128 per lane) and the matching 1 KB of the activation vector
+// (kept in shared memory for the phase), 8 FMAs per lane, and keeps the row's running sum in a register across
+// the tile's segments: one warp-shuffle reduction per ROW, no cross-warp combine, no CTA barrier inside a
+// MulMat phase.  Slot hand-off: full[s] (producer's expect_tx + the copies' complete_tx) / empty[s] (16 warp arrivals).
+// Numerics are those of kernels_mega.cu (f64 RMSNorm sums, f64 RoPE, f64 exp softmax terms); only the
+// association order of the FP32 dot products differs (lane-sequential over k, then a shuffle tree).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace lb {
+namespace k {
+namespace {
+
+constexpr int RG_CWARPS = 16;                      // consumer warps
+constexpr int RG_CTHREADS = RG_CWARPS * 32;        // 512
+constexpr int RG_THREADS = RG_CTHREADS + 32;       // + the producer warp
+constexpr int RG_HALF = RG_CTHREADS / 2;
+constexpr int RG_SEG = 256;                        // floats of K per slot row (1 KB)
+constexpr int RG_ROWS = 16;                        // rows per slot
+constexpr uint32_t RG_PITCH = RG_SEG * 4 + 64;     // bytes between the rows of a slot (+64: keeps a future fragment-order read conflict-free)
+constexpr uint32_t RG_SLOT = RG_ROWS * RG_PITCH;   // 17408 B
+constexpr int RG_MAX_SLOTS = 12;
+constexpr int RG_MAX_ITEMS = 2 * kNumSMs;
+constexpr int RG_MAX_HEADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ccsync() { asm volatile("bar.sync 1, %0;" ::"n"(RG_CTHREADS) : "memory"); }   // consumers only
+__device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(RG_HALF) : "memory"); }
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline bug must not hang the box
+    }
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct RingParams {
+    const MegaLayerHost *layers;
+    uint32_t n_layers;
+    const float *tok_embeddings;  // nullptr: the residual stream comes in through x
+    const uint32_t *tokens;
+    const uint32_t *state;        // {past, step}
+    const float *final_norm, *output;  // nullptr: no lm_head on this stage
+    float *x, *y, *qkv, *attn, *act, *logits;
+    float *part_o, *part_ml;
+    unsigned *barrier;
+    uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
+    unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0
+};
+
+struct RingShared {
+    unsigned long long full[RG_MAX_SLOTS], empty[RG_MAX_SLOTS];
+    double red[RG_CWARPS];
+    double rope_cs[64][2];
+    float fred[2][RG_CWARPS / 2];
+    float hbcast[2];
+    float4 pv[RG_CTHREADS];
+    float mrg_m[RG_MAX_ITEMS], mrg_l[RG_MAX_ITEMS], mrg_w[RG_MAX_ITEMS], mrg_inv[RG_MAX_HEADS];
+};
+
+// ---- grid barrier among the consumer threads of all CTAs (the producer warps never take part)
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+    target += nctas;
+    ccsync();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        __threadfence();
+    }
+    ccsync();
+}
+
+__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
+    r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
+    r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
+}
+
+struct RingPos {
+    uint32_t slot, phase;
+    __device__ __forceinline__ void next(uint32_t n_slots) {
+        if (++slot == n_slots) { slot = 0; phase ^= 1; }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// producer: rows [r0, r1) of W (and W3 for the SwiGLU pair) -> ring, tile by tile, segment by segment
+// ---------------------------------------------------------------------------------------------------------
+template <int NM>
+__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, RingPos &pos, uint32_t ring_base,
+                                        RingShared &sh, uint32_t n_slots) {
+    const int lane = threadIdx.x & 31;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const uint32_t nseg = K / RG_SEG;
+    for (uint32_t tile = r0; tile < r1; tile += RG_ROWS) {
+        const uint32_t nrows = min((uint32_t)RG_ROWS, r1 - tile);
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const float *src = (m == 0 ? W : W3) + (size_t)(tile + lane) * K + (size_t)seg * RG_SEG;
+                const uint32_t fb = smem_u32(&sh.full[pos.slot]);
+                if (lane == 0) {
+                    mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);   // all 16 consumer warps released the slot
+                    mbar_expect_tx(fb, nrows * RG_SEG * 4);
+                }
+                __syncwarp();
+                if ((uint32_t)lane < nrows) bulk_g2s(ring_base + pos.slot * RG_SLOT + lane * RG_PITCH, src, RG_SEG * 4, fb);
+                pos.next(n_slots);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// consumer: out[row] = epilogue(W[row] . x) for this CTA's rows of an M x K matrix; x in shared memory (xs).
+// EPI: 0 none, 1 + res[row];  NM == 2: out[row] = silu(W1[row].x) * (W3[row].x)
+// ---------------------------------------------------------------------------------------------------------
+template <int NM, int EPI>
+__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs, float *out, const float *res, RingPos &pos,
+                                        const uint8_t *ring, RingShared &sh, uint32_t n_slots) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t r0, r1;
+    cta_rows(M, r0, r1);
+    const uint32_t nseg = K / RG_SEG;
+    const float4 *x4 = reinterpret_cast<const float4 *>(xs);
+    for (uint32_t tile = r0; tile < r1; tile += RG_ROWS) {
+        const uint32_t row = tile + warp;
+        const bool valid = row < r1;
+        float a1 = 0.f, a3 = 0.f;
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+            const float4 xa = x4[seg * (RG_SEG / 4) + lane], xb = x4[seg * (RG_SEG / 4) + 32 + lane];
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase);
+                if (valid) {
+                    const float4 *wr = reinterpret_cast<const float4 *>(ring + (size_t)pos.slot * RG_SLOT + (size_t)warp * RG_PITCH);
+                    const float4 wa = wr[lane], wb = wr[32 + lane];
+                    float s = m == 0 ? a1 : a3;
+                    s = fmaf(wa.x, xa.x, s); s = fmaf(wa.y, xa.y, s); s = fmaf(wa.z, xa.z, s); s = fmaf(wa.w, xa.w, s);
+                    s = fmaf(wb.x, xb.x, s); s = fmaf(wb.y, xb.y, s); s = fmaf(wb.z, xb.z, s); s = fmaf(wb.w, xb.w, s);
+                    if (m == 0) a1 = s; else a3 = s;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh.empty[pos.slot]));
+                pos.next(n_slots);
+            }
+        }
+        if (valid) {
+            a1 = warp_sum(a1);
+            if (NM == 2) a3 = warp_sum(a3);
+            if (lane == 0) {
+                float v;
+                if (NM == 2) v = __fmul_rn(silu_ref(a1), a3);
+                else if (EPI == 1) v = __fadd_rn(a1, __ldcg(res + row));
+                else v = a1;
+                out[row] = v;
+            }
+        }
+    }
+}
+
+// ---- activation vector of a phase -> shared memory -----------------------------------------------------------
+// y = w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
+__device__ __forceinline__ void fill_norm(float *xs, const float *x, const float *w, uint32_t K, RingShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    double acc = 0.0;
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) {
+        const float4 v = ldcg4(x + (size_t)f * 4);
+        x4[f] = v;
+        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
+        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.red[warp] = acc;
+    ccsync();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RG_CWARPS; i++) t += sh.red[i];
+    const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) {
+        const float4 v = x4[f];
+        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + f);
+        x4[f] = make_float4(__fmul_rn(ww.x, __fmul_rn(v.x, sc)), __fmul_rn(ww.y, __fmul_rn(v.y, sc)),
+                            __fmul_rn(ww.z, __fmul_rn(v.z, sc)), __fmul_rn(ww.w, __fmul_rn(v.w, sc)));
+    }
+    ccsync();   // also orders sh.red against its next use
+}
+__device__ __forceinline__ void fill_plain(float *xs, const float *x, uint32_t K) {
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) x4[f] = ldcg4(x + (size_t)f * 4);
+    ccsync();
+}
+// merge of the attention splits (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
+template <int HD>
+__device__ __forceinline__ void fill_merge(float *xs, const RingParams &p, RingShared &sh) {
+    const uint32_t S = p.splits, items = p.heads * S;
+    for (uint32_t i = threadIdx.x; i < items; i += RG_CTHREADS) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
+        sh.mrg_m[i] = ml.x;
+        sh.mrg_l[i] = ml.y;
+    }
+    ccsync();
+    for (uint32_t h = threadIdx.x; h < p.heads; h += RG_CTHREADS) {
+        float M = -INFINITY;
+        for (uint32_t s = 0; s < S; s++) M = fmaxf(M, sh.mrg_m[h * S + s]);
+        float Lsum = 0.f;
+        for (uint32_t s = 0; s < S; s++) {
+            const float l = sh.mrg_l[h * S + s];
+            float wgt = 0.f;
+            if (l > 0.f) {
+                wgt = expf(__fsub_rn(sh.mrg_m[h * S + s], M));
+                Lsum = fmaf(l, wgt, Lsum);
+            }
+            sh.mrg_w[h * S + s] = wgt;
+        }
+        sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
+    }
+    ccsync();
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    constexpr int MB = 12;
+    for (uint32_t f = threadIdx.x; f < p.dim / 4; f += RG_CTHREADS) {
+        const uint32_t e = f * 4, h = e / HD, d = e % HD;
+        const float *po = p.part_o + (size_t)h * S * HD + d;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t s0 = 0; s0 < S; s0 += MB) {
+            float4 pv[MB];
+#pragma unroll
+            for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < MB; u++) {
+                if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
+                    const float wgt = sh.mrg_w[h * S + s0 + u];
+                    o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
+                    o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+                }
+            }
+        }
+        const float inv = sh.mrg_inv[h];
+        x4[f] = make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv));
+    }
+    ccsync();
+}
+
+// ---- attention phase: identical to kernels_mega.cu::attention_phase (items (head, split), two per CTA at a time)
+template <int HD>
+__device__ __forceinline__ void attention_phase(const RingParams &p, const MegaLayerHost &L, uint32_t past, RingShared &sh, float *scores_all) {
+    constexpr int LANES = HD / 4;
+    constexpr int HW = RG_CWARPS / 2;
+    constexpr int KG = RG_HALF / LANES;
+    constexpr int AU = 8;
+    const int half = threadIdx.x / RG_HALF, ht = threadIdx.x % RG_HALF;
+    const int hwarp = ht >> 5, lane = threadIdx.x & 31;
+    const uint32_t dim = p.dim, S = p.splits, Tn = past + 1;
+    const float scale = (float)(1.0 / sqrt((double)HD));  // f32(1/sqrt(dim/heads)), llama.go:306
+    const uint32_t chunk = min((Tn + S - 1) / S, p.chunk_cap);
+    const uint32_t items = p.heads * S;
+    float *scores = scores_all + (size_t)half * p.chunk_cap;
+    float4 *pv = sh.pv + half * RG_HALF;
+    const uint32_t kg = ht / LANES, dl = ht % LANES;
+    for (uint32_t item = blockIdx.x * 2 + half; item < items; item += gridDim.x * 2) {
+        const uint32_t h = item / S, sp = item % S;
+        const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn), nk = t1 - t0;
+        float *Kh = L.Kc + (size_t)h * HD;
+        float *Vh = L.Vc + (size_t)h * HD;
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < LANES) {
+            const float4 qr = ldcg4(p.qkv + (size_t)h * HD + lane * 4);
+            const double c0 = sh.rope_cs[lane * 2][0], s0 = sh.rope_cs[lane * 2][1];
+            const double c1 = sh.rope_cs[lane * 2 + 1][0], s1 = sh.rope_cs[lane * 2 + 1][1];
+            qv.x = (float)(__dsub_rn(__dmul_rn((double)qr.x, c0), __dmul_rn((double)qr.y, s0)));
+            qv.y = (float)(__dadd_rn(__dmul_rn((double)qr.x, s0), __dmul_rn((double)qr.y, c0)));
+            qv.z = (float)(__dsub_rn(__dmul_rn((double)qr.z, c1), __dmul_rn((double)qr.w, s1)));
+            qv.w = (float)(__dadd_rn(__dmul_rn((double)qr.z, s1), __dmul_rn((double)qr.w, c1)));
+            if (hwarp == 0 && past >= t0 && past < t1) {
+                const float4 kr = ldcg4(p.qkv + dim + (size_t)h * HD + lane * 4);
+                float4 ko;
+                ko.x = (float)(__dsub_rn(__dmul_rn((double)kr.x, c0), __dmul_rn((double)kr.y, s0)));
+                ko.y = (float)(__dadd_rn(__dmul_rn((double)kr.x, s0), __dmul_rn((double)kr.y, c0)));
+                ko.z = (float)(__dsub_rn(__dmul_rn((double)kr.z, c1), __dmul_rn((double)kr.w, s1)));
+                ko.w = (float)(__dadd_rn(__dmul_rn((double)kr.z, s1), __dmul_rn((double)kr.w, c1)));
+                *reinterpret_cast<float4 *>(Kh + (size_t)past * dim + lane * 4) = ko;
+                *reinterpret_cast<float4 *>(Vh + (size_t)past * dim + lane * 4) = ldcg4(p.qkv + 2 * dim + (size_t)h * HD + lane * 4);
+            }
+        }
+        hsync(half);
+        for (uint32_t i = hwarp; i < nk; i += HW * AU) {
+            float4 kk[AU];
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t ii = i + u * HW;
+                kk[u] = (ii < nk && lane < LANES) ? ldcg4(Kh + (size_t)(t0 + ii) * dim + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t ii = i + u * HW;
+                float dd = kk[u].x * qv.x;
+                dd = fmaf(kk[u].y, qv.y, dd); dd = fmaf(kk[u].z, qv.z, dd); dd = fmaf(kk[u].w, qv.w, dd);
+                dd = warp_sum(dd);
+                if (lane == 0 && ii < nk) scores[ii] = __fmul_rn(dd, scale);
+            }
+        }
+        float4 vf[AU];
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const uint32_t key = kg + u * KG;
+            vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        hsync(half);
+        float m = -INFINITY;
+        for (uint32_t i = ht; i < nk; i += RG_HALF) m = fmaxf(m, scores[i]);
+        m = warp_max(m);
+        if (lane == 0) sh.fred[half][hwarp] = m;
+        hsync(half);
+        if (ht == 0) {
+            float tt = sh.fred[half][0];
+            for (int i = 1; i < HW; i++) tt = fmaxf(tt, sh.fred[half][i]);
+            sh.hbcast[half] = tt;
+        }
+        hsync(half);
+        m = sh.hbcast[half];
+        float l = 0.f;
+        for (uint32_t i = ht; i < nk; i += RG_HALF) {
+            float e = (float)exp((double)__fsub_rn(scores[i], m));
+            scores[i] = e;
+            l += e;
+        }
+        l = warp_sum(l);
+        hsync(half);
+        if (lane == 0) sh.fred[half][hwarp] = l;
+        hsync(half);
+        if (ht == 0) {
+            float tt = 0.f;
+            for (int i = 0; i < HW; i++) tt += sh.fred[half][i];
+            p.part_ml[((size_t)h * S + sp) * 2 + 0] = m;
+            p.part_ml[((size_t)h * S + sp) * 2 + 1] = tt;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t base = 0; base < nk; base += KG * AU) {
+            if (base) {
+#pragma unroll
+                for (int u = 0; u < AU; u++) {
+                    const uint32_t key = base + kg + u * KG;
+                    vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t key = base + kg + u * KG;
+                if (key < nk) {
+                    const float sc = scores[key];
+                    acc.x = fmaf(vf[u].x, sc, acc.x); acc.y = fmaf(vf[u].y, sc, acc.y);
+                    acc.z = fmaf(vf[u].z, sc, acc.z); acc.w = fmaf(vf[u].w, sc, acc.w);
+                }
+            }
+        }
+        pv[ht] = acc;
+        hsync(half);
+        if (ht < HD) {
+            const float *pvf = reinterpret_cast<const float *>(pv);
+            float r = 0.f;
+            for (int i = 0; i < KG; i++) r += pvf[i * HD + ht];
+            p.part_o[((size_t)h * S + sp) * HD + ht] = r;
+        }
+        hsync(half);
+    }
+}
+
+// dynamic shared memory: [ring: n_slots x RG_SLOT][xs: max(dim, ff) floats][scores: 2 x chunk_cap floats][RingShared]
+template <int HD>
+__global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots;
+    uint8_t *ring = smem_raw;
+    float *xs = reinterpret_cast<float *>(smem_raw + (size_t)n_slots * RG_SLOT);
+    float *scores = xs + (dim > ff ? dim : ff);
+    RingShared &sh = *reinterpret_cast<RingShared *>(scores + 2 * (size_t)((p.chunk_cap + 3) & ~3u));
+    const bool producer = threadIdx.x >= RG_CTHREADS;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < n_slots; s++) {
+            mbar_init(smem_u32(&sh.full[s]), 1);
+            mbar_init(smem_u32(&sh.empty[s]), RG_CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t past = p.state[0];
+    if (threadIdx.x < HD / 2) {  // RoPE table of this token's position (f64 pow/cos/sin, ml.go:2307-2310)
+        double sn, cs;
+        sincos((double)past * pow(10000.0, ((double)(-(int)(2 * threadIdx.x))) / (double)HD), &sn, &cs);
+        sh.rope_cs[threadIdx.x][0] = cs;
+        sh.rope_cs[threadIdx.x][1] = sn;
+    }
+    __syncthreads();   // the only CTA-wide barrier: after it the producer warp and the consumers never meet again
+
+    RingPos pos;
+    pos.slot = 0; pos.phase = 0;
+    if (producer) {
+        // ================= producer warp: the whole token's weights of this CTA, in schedule order =================
+        const uint32_t ring_base = smem_u32(ring);
+        for (uint32_t li = 0; li < p.n_layers; li++) {
+            const MegaLayerHost L = p.layers[li];
+            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, ring_base, sh, n_slots);
+            produce<1>(L.wo, nullptr, dim, dim, pos, ring_base, sh, n_slots);
+            produce<2>(L.w1, L.w3, dim, ff, pos, ring_base, sh, n_slots);
+            produce<1>(L.w2, nullptr, ff, dim, pos, ring_base, sh, n_slots);
+        }
+        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, ring_base, sh, n_slots);
+        return;
+    }
+    // ================= consumers =================
+    unsigned target = 0;
+    const float *xin = p.x;
+    if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
+    unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    auto stamp = [&](uint32_t li, int i) {
+        if (tr) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tr[li * 13 + i] = t;
+        }
+    };
+    for (uint32_t li = 0; li < p.n_layers; li++) {
+        const MegaLayerHost L = p.layers[li];
+        stamp(li, 0);
+        // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
+        fill_norm(xs, xin, L.attention_norm, dim, sh);
+        stamp(li, 1);
+        consume<1, 0>(dim, 3 * dim, xs, p.qkv, nullptr, pos, ring, sh, n_slots);
+        stamp(li, 2);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 3);
+        // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
+        attention_phase<HD>(p, L, past, sh, scores);
+        stamp(li, 4);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 5);
+        // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
+        fill_merge<HD>(xs, p, sh);
+        consume<1, 1>(dim, dim, xs, p.y, xin, pos, ring, sh, n_slots);
+        stamp(li, 6);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 7);
+        // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
+        fill_norm(xs, p.y, L.ffn_norm, dim, sh);
+        stamp(li, 8);
+        consume<2, 0>(dim, ff, xs, p.act, nullptr, pos, ring, sh, n_slots);
+        stamp(li, 9);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 10);
+        // ---- P5: w2 + residual (llama.go:363-366)
+        fill_plain(xs, p.act, ff);
+        consume<1, 1>(ff, dim, xs, p.x, p.y, pos, ring, sh, n_slots);
+        stamp(li, 11);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 12);
+        xin = p.x;
+    }
+    if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
+        fill_norm(xs, xin, p.final_norm, dim, sh);
+        consume<1, 0>(dim, p.vocab, xs, p.logits, nullptr, pos, ring, sh, n_slots);
+    }
+}
+
+template <int HD>
+static cudaError_t launch(const RingParams &p, size_t smem, cudaStream_t st) {
+    static size_t attr[64] = {};  // function attributes are per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || attr[dev] < smem) {
+        e = cudaFuncSetAttribute(decode_ring_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr[dev] = 227 * 1024;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_ring_kernel<HD>, p);
+}
+
+static uint32_t ring_splits(uint32_t heads) {
+    uint32_t s = (2 * kNumSMs) / heads;
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+// shared-memory plan: returns the number of ring slots (0 = does not fit)
+static uint32_t ring_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx, size_t *smem_out) {
+    const uint32_t S = ring_splits(heads), chunk_cap = (ctx + S - 1) / S;
+    const size_t fixed = (size_t)(dim > ff ? dim : ff) * 4 + 2 * (size_t)((chunk_cap + 3) & ~3u) * 4 + sizeof(RingShared) + 128;
+    const size_t cap = 227 * 1024;
+    if (fixed + 4 * (size_t)RG_SLOT > cap) return 0;
+    uint32_t n = (uint32_t)((cap - fixed) / RG_SLOT);
+    if (n > RG_MAX_SLOTS) n = RG_MAX_SLOTS;
+    if (smem_out) *smem_out = fixed - 128 + (size_t)n * RG_SLOT;
+    return n;
+}
+
+}  // namespace
+
+bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
+    if (heads == 0 || dim % heads || heads > (uint32_t)RG_MAX_HEADS) return false;
+    const uint32_t hd = dim / heads;
+    if (hd != 128 && hd != 64 && hd != 32) return false;
+    if (dim % RG_SEG || ff % RG_SEG) return false;     // rows are streamed in 1 KB segments
+    (void)vocab;
+    return ring_plan(dim, ff, heads, ctx, nullptr) >= 4;
+}
+
+void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
+    LB_CHECK(decode_ring_supported(h.dim, h.ff, h.heads, h.vocab, h.ctx), "decode_ring: unsupported shape");
+    RingParams p;
+    p.layers = h.layers_dev;
+    p.n_layers = h.n_layers;
+    p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
+    p.final_norm = h.final_norm; p.output = h.output;
+    p.x = h.x; p.y = h.y; p.qkv = h.qkv; p.attn = h.attn; p.act = h.act; p.logits = h.logits;
+    p.part_o = h.part_o; p.part_ml = h.part_ml; p.barrier = h.barrier;
+    p.dim = h.dim; p.ff = h.ff; p.heads = h.heads; p.vocab = h.vocab; p.ctx = h.ctx;
+    p.splits = ring_splits(h.heads);
+    p.chunk_cap = (h.ctx + p.splits - 1) / p.splits;
+    size_t smem = 0;
+    p.n_slots = ring_plan(h.dim, h.ff, h.heads, h.ctx, &smem);
+    if (const char *e = getenv("LB_RING_SLOTS")) {   // profiling aid: a shallower ring
+        const uint32_t n = (uint32_t)atoi(e);
+        if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
+    }
+    p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
+    const uint32_t hd = h.dim / h.heads;
+    cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);
+    LB_CUDA(e);
+    count_launch();
+}
+
+}  // namespace k
+}  // namespace lb

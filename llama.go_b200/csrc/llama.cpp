@@ -212,9 +212,10 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     // persistent megakernel for N == 1 (FP32 weights, supported shapes); LB_NO_MEGA=1 keeps the per-op kernels
     // (Q8_0 models keep the per-op kernels: a Q8 variant of the megakernel's K-sliced phases was measured
     //  slower — 173 vs 240 tok/s on 7B, too few bytes in flight per warp with 1-byte weights)
-    use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
-    // experiment (unmeasured): Q8 megakernel on the int8 tensor cores
-    if (m->q8() && getenv("LB_Q8_MEGA") && k::decode_mega_q8_supported(hp.dim, hp.ff(), hp.heads, hp.vocab)) use_mega = true;
+    const bool mega_ok = k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
+    const bool ring_ok = getenv("LB_NO_RING") == nullptr && k::decode_ring_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
+    use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && (mega_ok || ring_ok);
+    use_ring = use_mega && ring_ok;   // TMA-ring megakernel (kernels_ring.cu); LB_NO_RING=1 keeps the register-fed one
     if (use_mega) {
         std::vector<k::MegaLayerHost> ml(nl);
         for (size_t i = 0; i < nl; i++) {
@@ -288,7 +289,8 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.barrier = mega_barrier;
         mp.trace = mega_trace;
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
-        k::decode_mega(mp, st);
+        if (use_ring) k::decode_ring(mp, st);
+        else k::decode_mega(mp, st);
         if (hidden_out && hidden_out != x)
             LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return;

@@ -80,6 +80,7 @@ struct Context {
     unsigned *mega_barrier = nullptr;  // grid-barrier counter of the megakernel
     void *mega_trace = nullptr;        // LB_MEGA_TRACE=1: per-phase globaltimer stamps of CTA 0
     bool use_mega = false;             // single-token forward = one persistent cooperative kernel
+    bool use_ring = false;             // ... the TMA-ring variant (kernels_ring.cu) instead of the register-fed one
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
