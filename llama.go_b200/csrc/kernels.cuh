@@ -152,6 +152,9 @@ struct MegaPodsParamsHost {
 bool decode_mega_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
 uint32_t decode_mega_pods_splits(uint32_t B, uint32_t heads);
 void decode_mega_pods(const MegaPodsParamsHost &p, cudaStream_t st);
+// the same step with the weights arriving through a producer warp's TMA ring (kernels_ring_pods.cu)
+bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
+void decode_ring_pods(const MegaPodsParamsHost &p, cudaStream_t st);
 
 // ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
 // W / out are plain row-major [rows][K]; q / d are the 4-row-interleaved planes (rows % 4 == 0, K % 32 == 0)

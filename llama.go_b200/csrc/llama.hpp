@@ -138,7 +138,8 @@ struct PodBatch {
     float *logits_host = nullptr;
     cudaGraphExec_t graph = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool use_mega = false;              // one persistent megakernel per step (kernels_mega_pods.cu)
+    bool use_mega = false;              // one persistent megakernel per step (kernels_mega_pods.cu / kernels_ring_pods.cu)
+    bool use_ring = false;              // ... the TMA-ring variant
     void *mega_layers_dev = nullptr;    // k::MegaLayerHost[layers]
     unsigned *mega_barrier = nullptr;
 

@@ -48,8 +48,11 @@ PodBatch::PodBatch(const std::vector<Context *> &cs) : ctxs(cs) {
     ev1 = mem.event();
     // one persistent megakernel per step (kernels_mega_pods.cu) for FP32 weights and supported shapes;
     // LB_NO_MEGA_PODS=1 keeps the per-op B-column kernels
-    use_mega = getenv("LB_NO_MEGA_PODS") == nullptr && !model->q8() &&
-               k::decode_mega_pods_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, ctx_size);
+    // (TMA-ring variant kernels_ring_pods.cu when the shape allows, LB_NO_RING_PODS=1: the register-fed kernels_mega_pods.cu)
+    use_ring = getenv("LB_NO_MEGA_PODS") == nullptr && getenv("LB_NO_RING_PODS") == nullptr && !model->q8() &&
+               k::decode_ring_pods_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, ctx_size);
+    use_mega = use_ring || (getenv("LB_NO_MEGA_PODS") == nullptr && !model->q8() &&
+                            k::decode_mega_pods_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, ctx_size));
     if (use_mega) {
         const size_t nl = model->layers.size();
         std::vector<k::MegaLayerHost> ml(nl);
@@ -95,7 +98,8 @@ void PodBatch::forward() {
         mp.part_ml = attn_scratch + (size_t)B * H * 32 * hp.head_dim();
         mp.barrier = mega_barrier;
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
-        k::decode_mega_pods(mp, st);
+        if (use_ring) k::decode_ring_pods(mp, st);
+        else k::decode_mega_pods(mp, st);
         k::advance_pods(pasts_dev, state_dev, B, st);
         return;
     }

@@ -21,3 +21,11 @@ for combo in "" "LB_NO_RING=1"; do
   env $combo timeout 300 python bench.py --model 13b --no-cpu-baseline --no-configs --steps 50 > $OUT/bench13_$TAG.json 2> $OUT/bench13_$TAG.err; rc=$?
   python -c "import json;d=json.load(open('$OUT/bench13_$TAG.json'));print('[13b $combo] rc=$rc value',round(d['value'],1),'frac',d['roofline']['frac'])" || tail -3 $OUT/bench13_$TAG.err
 done
+echo "=== pods on the ring: parity, then bench"
+timeout 600 python -m pytest tests/test_gpu_pods.py -q -s -m gpu > $OUT/pytest_pods_$TAG.log 2>&1; echo "rc=$?"; grep -E "rel err|worst|Error|error" $OUT/pytest_pods_$TAG.log | tail -20; tail -3 $OUT/pytest_pods_$TAG.log
+for combo in "" "LB_NO_RING_PODS=1"; do
+  env $combo timeout 300 python bench.py --pods 8 --steps 50 > $OUT/bench_pods8_$TAG.json 2> $OUT/bench_pods8_$TAG.err; rc=$?
+  python -c "import json;d=json.load(open('$OUT/bench_pods8_$TAG.json'));print('[pods8 $combo] rc=$rc value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'frac',d['roofline']['frac'])" || tail -3 $OUT/bench_pods8_$TAG.err
+done
+timeout 300 python bench.py --pods 4 --steps 50 > $OUT/bench_pods4_$TAG.json 2> $OUT/bench_pods4_$TAG.err
+python -c "import json;d=json.load(open('$OUT/bench_pods4_$TAG.json'));print('[pods4] value',round(d['value'],1),'frac',d['roofline']['frac'])"
