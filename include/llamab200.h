@@ -107,6 +107,25 @@ LB_API int lb_decode_resident(lb_context *c, const uint32_t *tokens, uint32_t st
  * single-token eval], no host round trip per token.  out_tokens receives the `predict` generated ids. */
 LB_API int lb_generate_greedy(lb_context *c, const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp,
                               float repeat_penalty, uint32_t *out_tokens);
+/* llama.SampleTopPTopK (pkg/llama/llama.go:455-707) on the device, on the logits of the context's last eval:
+ * repetition penalty for the ids in last_n_tokens (membership only, :501-527), descending sort + top-k cut (:548-565),
+ * softmax in f64 -> f32 (:579-599), top-p cut + renormalisation (:614-629), pick argmax p*p*f*f (:658-673).  The
+ * reference seeds its generator with time.Now() (:655): `seed` replaces it (f_i from splitmix64(seed + i)).
+ * cand_ids_out / cand_probs_out (optional, capacity top_k) receive the candidate set after both cuts. */
+LB_API int lb_sample_top_p_top_k(lb_context *c, const uint32_t *last_n_tokens, uint32_t n_last, uint32_t top_k, float top_p,
+                                 float temp, float repeat_penalty, uint64_t seed, uint32_t *cand_ids_out, float *cand_probs_out,
+                                 uint32_t *n_cand_out, uint32_t *token_out);
+/* The generate loop of pkg/server.Do (pkg/server/server.go:127-237): prompt consumed in batches of batch_size, the
+ * context-swap rule when the context is full (:158-172, keep_count = Params.KeepCount), one device sample per token
+ * (seed + token index).  out_tokens receives the `predict` sampled ids. */
+LB_API int lb_generate(lb_context *c, const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, uint32_t top_k, float top_p,
+                       float temp, float repeat_penalty, uint32_t keep_count, uint32_t batch_size, uint64_t seed,
+                       uint32_t *out_tokens);
+/* The context-swap rule alone (server.go:165-172; main.go:190-200), pure host code: if *past_io + n_embd > ctx_size then
+ * *past_io = keep_count and the last (past - keep_count) / 2 ids of `history` (oldest first) are put in front of embd.
+ * Returns the new length written to embd_out (capacity cap), or -1 on error. */
+LB_API int64_t lb_context_swap(uint32_t ctx_size, uint32_t keep_count, const uint32_t *history, uint32_t n_history,
+                               uint32_t *past_io, const uint32_t *embd, uint32_t n_embd, uint32_t *embd_out, uint32_t cap);
 LB_API int lb_context_read_logits(lb_context *c, float *logits_out);              /* last eval's row */
 LB_API int lb_context_read_kv(lb_context *c, uint32_t layer, uint32_t t0, uint32_t nt, float *k_out, float *v_out);
 LB_API int lb_context_read_hidden(lb_context *c, uint32_t n, float *hidden_out);  /* residual stream before final norm */

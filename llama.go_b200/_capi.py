@@ -45,6 +45,11 @@ _SIGS = {
     "lb_eval_graph": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, _f32p]),
     "lb_decode_resident": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, _f32p]),
     "lb_generate_greedy": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _u32p]),
+    "lb_sample_top_p_top_k": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint64, _u32p, _f32p,
+                                        _u32p, _u32p]),
+    "lb_generate": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32,
+                              C.c_uint64, _u32p]),
+    "lb_context_swap": (C.c_int64, [C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _u32p, _u32p, C.c_uint32, _u32p, C.c_uint32]),
     "lb_context_read_logits": (C.c_int, [_vp, _f32p]),
     "lb_context_read_kv": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _f32p]),
     "lb_context_read_hidden": (C.c_int, [_vp, C.c_uint32, _f32p]),

@@ -143,6 +143,26 @@ int lb_generate_greedy(lb_context *c, const uint32_t *prompt, uint32_t n_prompt,
                        uint32_t *out_tokens) {
     LB_TRY_INT(LB_CHECK(c, "nil context"); c->c->generate_greedy(prompt, n_prompt, predict, temp, repeat_penalty, out_tokens));
 }
+int lb_sample_top_p_top_k(lb_context *c, const uint32_t *last_n_tokens, uint32_t n_last, uint32_t top_k, float top_p, float temp,
+                          float repeat_penalty, uint64_t seed, uint32_t *cand_ids_out, float *cand_probs_out, uint32_t *n_cand_out,
+                          uint32_t *token_out) {
+    LB_TRY_INT(LB_CHECK(c && token_out, "nil argument");
+               *token_out = c->c->sample(last_n_tokens, n_last, top_k, top_p, temp, repeat_penalty, seed, cand_ids_out, cand_probs_out, n_cand_out));
+}
+int lb_generate(lb_context *c, const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, uint32_t top_k, float top_p, float temp,
+                float repeat_penalty, uint32_t keep_count, uint32_t batch_size, uint64_t seed, uint32_t *out_tokens) {
+    LB_TRY_INT(LB_CHECK(c, "nil context");
+               c->c->generate(prompt, n_prompt, predict, top_k, top_p, temp, repeat_penalty, keep_count, batch_size, seed, out_tokens));
+}
+int64_t lb_context_swap(uint32_t ctx_size, uint32_t keep_count, const uint32_t *history, uint32_t n_history, uint32_t *past_io,
+                        const uint32_t *embd, uint32_t n_embd, uint32_t *embd_out, uint32_t cap) {
+    try {
+        return lb::llama::context_swap(ctx_size, keep_count, history, n_history, past_io, embd, n_embd, embd_out, cap);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 int lb_context_read_logits(lb_context *c, float *out) {
     LB_TRY_INT(LB_CHECK(c && out, "nil argument"); LB_CHECK(c->c->model->has_head(), "this stage has no lm_head");
                LB_CUDA(cudaSetDevice(c->c->model->device));

@@ -97,6 +97,12 @@ void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, 
 // greedy (temp -> 0) sampling with the reference's repetition penalty, on the device (kernels_elementwise.cu)
 void sample_greedy(const float *logits, uint32_t V, float scale, float penalty, uint32_t *present, uint32_t *ring,
                    uint32_t ring_size, uint32_t *ring_pos, uint32_t *tokens, const uint32_t *state, cudaStream_t st);
+// SampleTopPTopK on the device (kernels_sample.cu): candidate ids/probabilities after the top-k and top-p cuts
+// (out_ids/out_probs sized top_k), out_n_token = {count, picked token}
+size_t sample_top_p_top_k_smem(uint32_t V, uint32_t top_k);
+void sample_top_p_top_k(const float *logits, uint32_t V, const uint32_t *last_n_dev, uint32_t n_last, uint32_t top_k, float top_p,
+                        float temp, float penalty, uint64_t seed, uint32_t *out_ids, float *out_probs, uint32_t *out_n_token,
+                        cudaStream_t st);
 // state[0] (= past) += dp; state[1] (= step) += ds
 void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
 

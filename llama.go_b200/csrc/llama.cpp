@@ -523,6 +523,97 @@ void Context::generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_
     memcpy(out_tokens, tokens_host, predict * sizeof(uint32_t));
 }
 
+int64_t context_swap(uint32_t ctx_size, uint32_t keep, const uint32_t *history, uint32_t n_history, uint32_t *past,
+                     const uint32_t *embd, uint32_t n_embd, uint32_t *embd_out, uint32_t cap) {
+    LB_CHECK(past && (embd || !n_embd) && embd_out, "context_swap : nil argument");
+    uint32_t n_front = 0;
+    if ((uint64_t)*past + n_embd > ctx_size) {              // server.go:165
+        LB_CHECK(keep <= *past, "context_swap : keep exceeds pastCount");
+        const uint32_t left = *past - keep;                  // :166
+        *past = keep;                                        // :167
+        n_front = left / 2;                                  // :171  ExtractTokens(lastNTokens.Move(-left/2), left/2)
+        LB_CHECK(n_front <= n_history, "context_swap : history shorter than the tokens to re-evaluate");
+    }
+    LB_CHECK((uint64_t)n_front + n_embd <= cap, "context_swap : output capacity too small");
+    for (uint32_t i = 0; i < n_front; i++) embd_out[i] = history[n_history - n_front + i];
+    for (uint32_t i = 0; i < n_embd; i++) embd_out[n_front + i] = embd[i];
+    return (int64_t)n_front + n_embd;
+}
+
+uint32_t Context::sample(const uint32_t *last_n, uint32_t n_last, uint32_t top_k, float top_p, float temp, float repeat_penalty,
+                         uint64_t seed, uint32_t *ids_out, float *probs_out, uint32_t *n_out) {
+    const HParams &hp = model->hp;
+    LB_CHECK(model->has_head(), "SampleTopPTopK : this stage has no logits");
+    LB_CHECK(last_n || !n_last, "SampleTopPTopK : nil lastNTokens");
+    LB_CHECK(top_k >= 1 && top_k <= hp.vocab, "SampleTopPTopK : topK must be in 1..vocab");
+    LB_CUDA(cudaSetDevice(model->device));
+    if (!smp_ids_dev) {
+        smp_ids_dev = mem.dmalloc<uint32_t>(hp.vocab);
+        smp_probs_dev = mem.dmalloc<float>(hp.vocab);
+        smp_nt_dev = mem.dmalloc<uint32_t>(2);
+        smp_host = mem.hmalloc<uint32_t>(2);
+    }
+    if (n_last > smp_last_cap) {
+        smp_last_cap = n_last > ctx_size ? n_last : ctx_size;
+        smp_last_dev = mem.dmalloc<uint32_t>(smp_last_cap, false);
+    }
+    if (n_last) LB_CUDA(cudaMemcpyAsync(smp_last_dev, last_n, n_last * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    k::sample_top_p_top_k(logits, hp.vocab, smp_last_dev, n_last, top_k, top_p, temp, repeat_penalty, seed, smp_ids_dev, smp_probs_dev,
+                          smp_nt_dev, stream);
+    LB_CUDA(cudaMemcpyAsync(smp_host, smp_nt_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    LB_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t n = smp_host[0], tok = smp_host[1];
+    if (ids_out) LB_CUDA(cudaMemcpy(ids_out, smp_ids_dev, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (probs_out) LB_CUDA(cudaMemcpy(probs_out, smp_probs_dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    return tok;
+}
+
+void Context::generate(const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, uint32_t top_k, float top_p, float temp,
+                       float repeat_penalty, uint32_t keep_count, uint32_t batch_size, uint64_t seed, uint32_t *out_tokens) {
+    const HParams &hp = model->hp;
+    LB_CHECK(model->has_embedding() && model->has_head(), "generate : needs a single-stage model");
+    LB_CHECK(prompt && out_tokens && n_prompt >= 1 && predict >= 1 && batch_size >= 1, "generate : bad arguments");
+    for (uint32_t i = 0; i < n_prompt; i++) LB_CHECK(prompt[i] < hp.vocab, "generate : token id out of range");
+    // ring of the last ctx_size ids, zero-filled (server.go:127-138); kept here oldest-first in a flat history
+    std::vector<uint32_t> ring(ctx_size, 0u);
+    uint32_t rpos = 0;
+    auto append = [&](uint32_t t) { ring[rpos] = t; rpos = (rpos + 1) % ctx_size; };
+    auto history = [&]() {   // chronological order, oldest first
+        std::vector<uint32_t> h(ctx_size);
+        for (uint32_t i = 0; i < ctx_size; i++) h[i] = ring[(rpos + i) % ctx_size];
+        return h;
+    };
+    std::vector<uint32_t> embd, tmp((size_t)ctx_size * 2 + batch_size);
+    uint32_t past = 0, consumed = 0, remained = predict, produced = 0;
+    while (remained > 0) {   // server.go:153
+        if (!embd.empty()) {
+            if ((uint64_t)past + embd.size() > ctx_size) {   // :165-172
+                const std::vector<uint32_t> h = history();
+                const int64_t n = context_swap(ctx_size, keep_count, h.data(), ctx_size, &past, embd.data(), (uint32_t)embd.size(), tmp.data(),
+                                               (uint32_t)tmp.size());
+                embd.assign(tmp.begin(), tmp.begin() + n);
+            }
+            eval(embd.data(), (uint32_t)embd.size(), past, nullptr, false);   // :175
+        }
+        past += (uint32_t)embd.size();   // :183
+        embd.clear();
+        if (consumed < n_prompt) {        // :186-194
+            while (consumed < n_prompt && embd.size() < batch_size) {
+                embd.push_back(prompt[consumed]);
+                append(prompt[consumed]);
+                consumed++;
+            }
+        } else {                           // :196-214
+            const uint32_t id = sample(ring.data(), ctx_size, top_k, top_p, temp, repeat_penalty, seed + produced, nullptr, nullptr, nullptr);
+            append(id);
+            embd.push_back(id);
+            out_tokens[produced++] = id;
+            remained--;
+        }
+    }
+}
+
 float Context::bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch) {
     const HParams &hp = model->hp;
     const uint32_t d = hp.dim, ff = hp.ff(), V = hp.vocab, H = hp.heads;

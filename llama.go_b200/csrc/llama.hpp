@@ -86,6 +86,9 @@ struct Context {
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
     uint32_t tokens_cap = 0;
     uint32_t *ring_dev = nullptr, *present_dev = nullptr, *ring_pos_dev = nullptr;  // sampler state (last-N ring)
+    uint32_t *smp_last_dev = nullptr, *smp_ids_dev = nullptr, *smp_nt_dev = nullptr, *smp_host = nullptr;  // top-k/top-p sampler buffers
+    float *smp_probs_dev = nullptr;
+    uint32_t smp_last_cap = 0;
     uint32_t *state_dev = nullptr;   // {past, step}
     uint32_t *state_host = nullptr;  // pinned {past, step}
     uint32_t *tokens_host = nullptr; // pinned staging
@@ -109,6 +112,15 @@ struct Context {
     // `predict` x (penalised argmax -> single-token eval); returns the generated ids
     void generate_greedy(const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, float temp, float repeat_penalty,
                          uint32_t *out_tokens);
+    // llama.SampleTopPTopK (llama.go:455-707) on the device, on the logits of the last eval.  last_n = the ids of the
+    // last-N ring (membership is all the reference uses, :501-511).  Returns the picked token; ids/probs (optional,
+    // capacity top_k) receive the candidate set after the top-k and top-p cuts, *n_out its size.
+    uint32_t sample(const uint32_t *last_n, uint32_t n_last, uint32_t top_k, float top_p, float temp, float repeat_penalty,
+                    uint64_t seed, uint32_t *ids_out, float *probs_out, uint32_t *n_out);
+    // the generate loop of pkg/server.Do (server.go:127-237): prompt in batches, context swap when the context is
+    // full (:158-172), one sample per generated token; out_tokens receives the `predict` sampled ids
+    void generate(const uint32_t *prompt, uint32_t n_prompt, uint32_t predict, uint32_t top_k, float top_p, float temp,
+                  float repeat_penalty, uint32_t keep_count, uint32_t batch_size, uint64_t seed, uint32_t *out_tokens);
     float bench_kernel(int which, uint32_t iters, uint32_t past, uint64_t *bytes_per_launch);
     // capture (once) the single-token forward of this stage's layers on stream `st`:
     // [embedding gather on stage 0] -> layers -> [norm + lm_head on the last stage] -> advance {past, step}
@@ -165,6 +177,13 @@ float pipeline_decode(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tok
 void pipeline_prefill(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past);
 }  // namespace pipe
 namespace llama {
+// The context-swap rule of server.Do (pkg/server/server.go:158-172; main.go:190-200): when pastCount + len(embd)
+// would exceed the context, keep the first `keep` positions, re-evaluate the last (pastCount - keep) / 2 tokens of
+// the last-N history in front of embd.  history = ids oldest first (the ring in chronological order, which at that
+// point already ends with the just-sampled token — the reference appends to the ring before it extends embd).
+// Returns the new embd length (written to embd_out, capacity cap) and updates *past; no swap -> embd copied as is.
+int64_t context_swap(uint32_t ctx_size, uint32_t keep, const uint32_t *history, uint32_t n_history, uint32_t *past,
+                     const uint32_t *embd, uint32_t n_embd, uint32_t *embd_out, uint32_t cap);
 // ggjt v1 file -> device model (loader.cpp); vocab strings/scores are returned for the tokenizer side
 struct LoadedModel {
     std::unique_ptr<Model> model;

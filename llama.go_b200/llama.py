@@ -161,6 +161,41 @@ def GenerateGreedy(lctx: Context, prompt_ids, predict: int, temp: float = 1e-6, 
     return out.tolist()
 
 
+def SampleTopPTopK(lctx: Context, lastNTokens, topK: int = 40, topP: float = 0.95, temp: float = 0.8, repeatPenalty: float = 1.10,
+                   seed: int = 0):
+    """llama.SampleTopPTopK (llama.go:455-707) on the device, on the logits of lctx's last Eval.  Returns
+    (token, candidate ids, candidate probabilities) — the candidate set after the top-k and top-p cuts."""
+    t, p = _toks(lastNTokens)
+    ids = np.zeros(topK, np.uint32)
+    probs = np.zeros(topK, np.float32)
+    n, tok = C.c_uint32(0), C.c_uint32(0)
+    check(lib().lb_sample_top_p_top_k(lctx._h, p, t.size, topK, topP, temp, repeatPenalty, seed, ids.ctypes.data_as(_u32p),
+                                      probs.ctypes.data_as(_f32p), C.byref(n), C.byref(tok)))
+    return tok.value, ids[:n.value].copy(), probs[:n.value].copy()
+
+
+def Generate(lctx: Context, prompt_ids, predict: int, topK: int = 40, topP: float = 0.95, temp: float = 0.8, repeatPenalty: float = 1.10,
+             keepCount: int = 0, batchSize: int | None = None, seed: int = 0):
+    """The generate loop of pkg/server.Do (server.go:127-237) incl. the context swap (:158-172); returns the sampled ids."""
+    t, p = _toks(prompt_ids)
+    out = np.zeros(predict, np.uint32)
+    check(lib().lb_generate(lctx._h, p, t.size, predict, topK, topP, temp, repeatPenalty, keepCount,
+                            batchSize if batchSize else lctx.ctx_size, seed, out.ctypes.data_as(_u32p)))
+    return out.tolist()
+
+
+def ContextSwap(ctxSize: int, keepCount: int, history, pastCount: int, embd):
+    """The context-swap rule of server.Do (server.go:165-172): returns (new pastCount, new embd)."""
+    h, hp_ = _toks(history)
+    e, ep = _toks(embd)
+    past = C.c_uint32(pastCount)
+    out = np.zeros(h.size + e.size + 1, np.uint32)
+    n = lib().lb_context_swap(ctxSize, keepCount, hp_, h.size, C.byref(past), ep, e.size, out.ctypes.data_as(_u32p), out.size)
+    if n < 0:
+        check(1)
+    return past.value, out[:n].tolist()
+
+
 class PodBatch:
     """Up to 8 llama.Contexts ("pods", pkg/server/server.go:84-106) of one Model decoded together: one
     pass over the weights per step for all of them."""

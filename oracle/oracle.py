@@ -311,3 +311,102 @@ def greedy_stream(octx: OracleContext, prompt_ids, predict: int, ctx_size: int, 
     if return_logits:
         return out, np.stack(all_logits), margins
     return out
+
+
+# ----------------------------------------------------------------------------- sampler + server.Do loop
+def _splitmix64(x: int) -> int:
+    m = (1 << 64) - 1
+    z = (x + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+def sample_candidates(logits, last_n_tokens, top_k: int = 40, top_p: float = 0.95, temp: float = 0.8, penalty: float = 1.10):
+    """SampleTopPTopK up to (not including) the random pick, pkg/llama/llama.go:498-634, in the reference's own
+    arithmetic: FP32 scale / penalty (:500-527), descending sort (ties: lower id first — the reference's sort.Slice is
+    unstable, any tie order is legal), top-k cut (:565), p = f32(exp(f64(v - max))), f64 sequential sum, p /= f32(sum)
+    (:579-599), sequential FP32 cumsum cut at top_p and renormalisation by f32(1/cumsum) (:614-629).
+    Returns (ids uint32[n], probs float32[n])."""
+    lg = np.asarray(logits, np.float32)
+    scale = np.float32(1.0) / np.float32(temp)
+    pen = lg * scale
+    present = np.zeros(lg.size, bool)
+    ln = np.asarray(last_n_tokens, np.int64)
+    present[ln[ln < lg.size]] = True
+    neg = lg < 0
+    pen = np.where(present & neg, pen * np.float32(penalty), pen).astype(np.float32)
+    pen = np.where(present & ~neg, (lg * scale) / np.float32(penalty), pen).astype(np.float32)
+    order = np.argsort(-pen, kind="stable")[:top_k]
+    vals = pen[order]
+    maxl = vals[0]
+    probs = np.empty(len(order), np.float32)
+    s = 0.0
+    for i, v in enumerate(vals):
+        p = float(np.exp(np.float64(np.float32(v - maxl))))
+        probs[i] = np.float32(p)
+        s += p
+    probs = (probs / np.float32(s)).astype(np.float32)
+    n = len(order)
+    if top_p < 1.0:
+        cumsum = np.float32(0.0)
+        for i in range(n):
+            cumsum = np.float32(cumsum + probs[i])
+            if cumsum >= np.float32(top_p):
+                n = i + 1
+                break
+        inv = np.float32(np.float32(1.0) / cumsum)
+        probs = (probs[:n] * inv).astype(np.float32)
+    return order[:n].astype(np.uint32), probs
+
+
+def sample_pick(ids, probs, seed: int) -> int:
+    """The pick of llama.go:655-673 — argmax_i p_i*p_i*f_i*f_i, f_i = float32(Int63)/2^63 — with Int63 drawn from
+    splitmix64(seed + i) instead of the reference's time-seeded generator (which nothing can reproduce)."""
+    best, idx = None, 0
+    for i, p in enumerate(probs):
+        f = np.float32(np.float32(_splitmix64((seed + i) & ((1 << 64) - 1)) >> 1) * np.float32(2.0 ** -63))
+        v = np.float32(np.float32(np.float32(p * p) * f) * f)
+        if best is None or v > best:
+            best, idx = v, i
+    return int(ids[idx])
+
+
+def context_swap(ctx_size: int, keep: int, history, past: int, embd):
+    """server.go:165-172.  history = last-N ids oldest first."""
+    embd = list(embd)
+    if past + len(embd) > ctx_size:
+        left = past - keep
+        past = keep
+        n = left // 2
+        embd = [int(t) for t in history[len(history) - n:]] + embd if n else embd
+    return past, embd
+
+
+def generate_stream(octx: OracleContext, prompt_ids, predict: int, ctx_size: int, top_k: int = 40, top_p: float = 0.95,
+                    temp: float = 1e-6, penalty: float = 1.10, keep: int = 0, batch: int | None = None, seed: int = 0):
+    """The generate loop of pkg/server.Do (server.go:127-237) on the oracle: prompt in batches, context swap, one
+    SampleTopPTopK per generated token.  Returns the sampled ids."""
+    batch = batch or ctx_size
+    ring = [0] * ctx_size            # oldest first; append = drop the oldest (container/ring of size CtxSize, zero-filled)
+    embd, out = [], []
+    past = consumed = 0
+    logits = None
+    while len(out) < predict:
+        if embd:
+            past, embd = context_swap(ctx_size, keep, ring, past, embd)
+            logits = octx.eval(embd, past)
+        past += len(embd)
+        embd = []
+        if consumed < len(prompt_ids):
+            while consumed < len(prompt_ids) and len(embd) < batch:
+                embd.append(int(prompt_ids[consumed]))
+                ring = ring[1:] + [int(prompt_ids[consumed])]
+                consumed += 1
+        else:
+            ids, probs = sample_candidates(logits, ring, top_k, top_p, temp, penalty)
+            tok = sample_pick(ids, probs, seed + len(out))
+            ring = ring[1:] + [tok]
+            embd.append(tok)
+            out.append(tok)
+    return out

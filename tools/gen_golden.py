@@ -92,5 +92,36 @@ def main():
     print("done")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "swap" not in sys.argv[1:]:
     main()
+
+
+def gen_swap():
+    """refbin_swap.json — the reference binary run PAST its context (context 40, 30-token prompt, predict 40): the
+    context-swap rule of server.go:158-172 fires three times.  Pins oracle.generate_stream (and through it
+    lb_generate / lb_context_swap)."""
+    O.build()
+    hpt, seed, prompt, context, predict = (512, 64, 32, 2, 2), 7, "hello world, this is a test", 40, 40
+    hp = synth.HParams(*hpt)
+    vocab = synth.byte_vocab(hp.vocab)
+    ids = synth.prompt_token_ids(prompt.encode())
+    rec = {"hparams": list(hpt), "seed": seed, "prompt": prompt, "prompt_ids": ids, "context": context, "predict": predict, "runs": {}}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "m.bin")
+        synth.write_ggjt(path, hp, synth.synth_model(seed, hp), vocab)
+        for mode, avx, thr in (("scalar", False, 1), ("avx", True, 4)):
+            r = refbin.run(path, prompt, predict, context, thr, avx, port=18190)
+            rec["runs"][mode] = {"text_hex": r["text"].hex(), "evals": len(r["eval_ms"])}
+    m = O.OracleModel(hp).load(synth.synth_model(seed, hp))
+    toks = O.generate_stream(O.OracleContext(m, context), ids, predict, context)
+    exp = refbin.expected_text(vocab, ids, toks)
+    for mode in rec["runs"]:
+        assert refbin.same_stream(bytes.fromhex(rec["runs"][mode]["text_hex"]), exp), mode
+    rec["oracle_tokens"] = toks
+    with open(os.path.join(ROOT, "tests", "golden", "refbin_swap.json"), "w") as f:
+        json.dump(rec, f)
+    print("swap:", len(toks), "tokens")
+
+
+if __name__ == "__main__" and "swap" in sys.argv[1:]:
+    gen_swap()
