@@ -36,28 +36,12 @@ def pipeline_parity(stage, hp, device, ctx_size, prompt, gen, n_decoded, S):
     return {"rel_err": worst}
 
 
-def run_pipeline(args):
-    import torch
-    import torch.distributed as dist
-    import llama_go_b200  # noqa: F401
-    from llama_go_b200 import _capi, pipeline, synth
-
-    rank, world, local = rank_world()
-    # stdout carries exactly one JSON line: NCCL prints "NCCL version ..." there when NCCL_DEBUG=VERSION is inherited
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29511")
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    _capi.require_gpu()
-    lib = _capi.lib()
-    uid = pipeline.exchange_unique_id(rank, dist)
-    _capi.check(lib.lb_comm_init(uid, rank, world, local))
-
-    hp = getattr(synth, MODELS[args.model])
-    K, W = args.steps, args.warmup
+def pipeline_measure(args, hp, model_key, ctx_size, K, W, env):
+    """One layer-sharded measurement on the already initialised process group / NCCL communicator.  Returns the record
+    (meaningful on rank 0) — value (device timed, max over ranks), e2e, parity vs the unsharded model, roofline."""
+    torch, dist, lib, pipeline, rank, world, local = env
+    from llama_go_b200 import _capi
     S = world                                   # sequences in flight
-    ctx_size = max(args.context or CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
     t_setup = time.time()
     stage = pipeline.Stage(hp, rank, world, local, ctx_size, S, seed=0)
     rs = np.random.RandomState(0)
@@ -118,36 +102,75 @@ def run_pipeline(args):
 
     all_launches = torch.tensor([float(launches)], dtype=torch.float64)
     dist.all_reduce(all_launches, op=dist.ReduceOp.SUM)
+    stage.free()
+    dist.barrier()
+    peak, peak_src = measured_peak()
+    T_mid = PROMPT_LEN + W + K / 2.0
+    wbytes = 4 * (hp.layers * (4 * hp.dim ** 2 + 3 * hp.dim * hp.ff + 2 * hp.dim) + hp.vocab * hp.dim + 2 * hp.dim)
+    bytes_per_token = wbytes + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
+    agg_gbs = bytes_per_token * value / 1e9
+    have_par = par_t.item() >= 0
+    return {
+        "metric": metric_name(model_key), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LLaMA-%s FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
+                               % (model_key.upper(), ctx_size, PROMPT_LEN, S),
+                   "parallelism": "pp%d (layer-sharded, %d layers/GPU, NCCL send/recv of the residual)" % (world, hp.layers // world),
+                   "sequences_in_flight": S, "tokens_per_step": S, "weights": "random-init (device RNG, seed 0)",
+                   "kv_cache": "fp32 in HBM", "l2": "inputs>L2", "setup_s": round(t_setup, 1),
+                   "note": "a single sequence gains nothing from layer sharding (dependency chain); "
+                           "throughput is aggregate over the in-flight sequences (the reference's pods)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * S + 8 * S, "d2h_bytes_per_step": 4 * hp.vocab * S,
+                "api": "lb_pipeline_decode(steps=1) + lb_context_read_logits per sequence, synchronous per step"},
+        "gpu_launches": int(all_launches.item()),
+        "roofline": {"bound": "hbm", "kernel": "whole step (aggregate over GPUs)", "achieved": round(agg_gbs, 1),
+                     "peak": peak * world, "unit": "GB/s", "frac": round(agg_gbs / (peak * world), 4), "traffic": None,
+                     "peak_source": peak_src + " x n_gpus"},
+        "cpu_baseline": None,
+        "parity_rel_err": (float(par_t.item()) if have_par else None),
+        "parity": ("max over the in-flight sequences of max|logits_pipeline - logits_single_gpu| / max|logits_single_gpu| "
+                   "after the last step (single-GPU lb_eval + lb_decode_resident of the same tokens, unsharded model on the "
+                   "last rank's GPU)" if have_par else "skipped: the unsharded model does not fit beside this stage on one GPU"),
+    }
+
+
+def run_pipeline(args):
+    import torch
+    import torch.distributed as dist
+    import llama_go_b200  # noqa: F401
+    from llama_go_b200 import _capi, pipeline, synth
+
+    rank, world, local = rank_world()
+    # stdout carries exactly one JSON line: NCCL prints "NCCL version ..." there when NCCL_DEBUG=VERSION is inherited
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _capi.require_gpu()
+    lib = _capi.lib()
+    uid = pipeline.exchange_unique_id(rank, dist)
+    _capi.check(lib.lb_comm_init(uid, rank, world, local))
+    env = (torch, dist, lib, pipeline, rank, world, local)
+
+    hp = getattr(synth, MODELS[args.model])
+    K, W = args.steps, args.warmup
+    ctx_size = max(args.context or CTX, PROMPT_LEN + 2 * W + 2 * K + 2)
+    line = pipeline_measure(args, hp, args.model, ctx_size, K, W, env)
+    # ---- the multi-GPU BASELINE configurations next to the 7B headline: 13B on 2/4 GPUs (config 4),
+    #      65B at context 2048 on 8 GPUs (config 5)
+    if args.model == "7b" and not getattr(args, "no_configs", False):
+        extra = {2: ("13b", "llama13b_ctx512", CTX), 4: ("13b", "llama13b_ctx512", CTX), 8: ("65b", "llama65b_ctx2048", 2048)}.get(world)
+        if extra:
+            key, name, cctx = extra
+            try:
+                rec = pipeline_measure(args, getattr(synth, MODELS[key]), key, max(cctx, PROMPT_LEN + 2 * W + 2 * K + 2), K, W, env)
+            except Exception as e:   # keep the headline
+                rec = {"error": str(e)}
+            line["configs"] = {name: rec}
     if rank == 0:
-        peak, peak_src = measured_peak()
-        T_mid = PROMPT_LEN + W + K / 2.0
-        wbytes = 4 * (hp.layers * (4 * hp.dim ** 2 + 3 * hp.dim * hp.ff + 2 * hp.dim) + hp.vocab * hp.dim + 2 * hp.dim)
-        bytes_per_token = wbytes + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
-        agg_gbs = bytes_per_token * value / 1e9
-        line = {
-            "metric": metric_name(args.model), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LLaMA-%s FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
-                                   % (args.model.upper(), ctx_size, PROMPT_LEN, S),
-                       "parallelism": "pp%d (layer-sharded, %d layers/GPU, NCCL send/recv of the residual)" % (world, hp.layers // world),
-                       "sequences_in_flight": S, "tokens_per_step": S, "weights": "random-init (device RNG, seed 0)",
-                       "kv_cache": "fp32 in HBM", "l2": "inputs>L2", "setup_s": round(t_setup, 1),
-                       "note": "a single sequence gains nothing from layer sharding (dependency chain); "
-                               "throughput is aggregate over the in-flight sequences (the reference's pods)"},
-            "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 * S + 8 * S, "d2h_bytes_per_step": 4 * hp.vocab * S,
-                    "api": "lb_pipeline_decode(steps=1) + lb_context_read_logits per sequence, synchronous per step"},
-            "gpu_launches": int(all_launches.item()),
-            "roofline": {"bound": "hbm", "kernel": "whole step (aggregate over GPUs)", "achieved": round(agg_gbs, 1),
-                         "peak": peak * world, "unit": "GB/s", "frac": round(agg_gbs / (peak * world), 4), "traffic": None,
-                         "peak_source": peak_src + " x n_gpus"},
-            "cpu_baseline": None,
-            "parity_rel_err": (float(par_t.item()) if par_t.item() >= 0 else None),
-            "parity": "max over the in-flight sequences of max|logits_pipeline - logits_single_gpu| / max|logits_single_gpu| "
-                      "after the last step (single-GPU lb_eval + lb_decode_resident of the same tokens, unsharded model on the "
-                      "last rank's GPU)" if par_t.item() >= 0 else "skipped: the unsharded model does not fit beside this stage on one GPU",
-        }
         print(json.dumps(line), flush=True)
     dist.barrier()
     lib.lb_comm_destroy()

@@ -153,6 +153,7 @@ struct MegaPodsParamsHost {
     float *x, *y, *qkv, *attn, *act, *logits;
     float *part_o, *part_ml;
     unsigned *barrier;             // 2 counters, zeroed by the launcher
+    const void *tmaps = nullptr;   // host pointer to the ring_pods_make_maps() blob (TMA-ring variant only)
     uint32_t dim, ff, heads, vocab, ctx;
 };
 bool decode_mega_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
@@ -161,6 +162,9 @@ void decode_mega_pods(const MegaPodsParamsHost &p, cudaStream_t st);
 // the same step with the weights arriving through a producer warp's TMA ring (kernels_ring_pods.cu)
 bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
 void decode_ring_pods(const MegaPodsParamsHost &p, cudaStream_t st);
+size_t ring_pods_maps_bytes();
+void ring_pods_make_maps(const MegaLayerHost *layers_host, uint32_t n_layers, uint32_t dim, uint32_t ff, uint32_t vocab,
+                         const float *output, void *maps_out);
 
 // ---- Q8_0 block-quantised weights (kernels_q8.cu; format in DESIGN.md §6) ----
 // W / out are plain row-major [rows][K]; q / d are the 4-row-interleaved planes (rows % 4 == 0, K % 32 == 0)

@@ -10,13 +10,13 @@
 // (0.914 of the measured-peak roofline); L2 prefetch hints issued around the barriers measured no gain
 // (round 2, profiles/README.md).  A ring of 9 x 16 KB per SM holds ~3.3 us of the CTA's share of the stream.
 //
-// Layout of the stream: a MulMat phase gives CTA c a contiguous block of ~M/148 output rows; the block is cut
-// into tiles of 16 rows and every tile into K/256 segments; one ring slot = 16 rows x 256 floats, filled by 16
-// bulk copies of 1 KB (one per lane of the producer warp).  Consumer warp w owns ROW w of the tile: per slot it
-// reads its 1 KB row segment (two conflict-free LDS.128 per lane) and the matching 1 KB of the activation vector
-// (kept in shared memory for the phase), 8 FMAs per lane, and keeps the row's running sum in a register across
-// the tile's segments: one warp-shuffle reduction per ROW, no cross-warp combine, no CTA barrier inside a
-// MulMat phase.  Slot hand-off: full[s] (producer's expect_tx + the copies' complete_tx) / empty[s] (16 warp arrivals).
+// Layout of the stream: a MulMat phase gives CTA c a contiguous block of ~M/148 output rows.  One ring slot = one
+// row (K <= 4096) or one K chunk of a longer row, filled by ONE bulk copy of up to 16 KB (1 KB copies were measured
+// copy-engine bound at ~75 clk per copy: 4 TB/s, profiles/README.md).  Consumer warp w owns the rows r0 + w, r0 + w + 16,
+// ... and consumes the slots of its rows by itself: 32 conflict-free LDS.128 of weights against the activation vector
+// kept in shared memory for the phase, one warp-shuffle reduction per ROW, no cross-warp combine and no CTA barrier
+// inside a MulMat phase.  Slot q lives in ring entry q % n; full[] (expect_tx + the copy's complete_tx) / empty[] (the
+// owning warp's arrival); both sides compute q from (phase base, row, chunk), so there is no shared cursor.
 // Numerics are those of kernels_mega.cu (f64 RMSNorm sums, f64 RoPE, f64 exp softmax terms); only the
 // association order of the FP32 dot products differs (lane-sequential over k, then a shuffle tree).
 #include <cooperative_groups.h>
@@ -33,10 +33,8 @@ constexpr int RG_CWARPS = 16;                      // consumer warps
 constexpr int RG_CTHREADS = RG_CWARPS * 32;        // 512
 constexpr int RG_THREADS = RG_CTHREADS + 32;       // + the producer warp
 constexpr int RG_HALF = RG_CTHREADS / 2;
-constexpr int RG_SEG = 256;                        // floats of K per slot row (1 KB)
-constexpr int RG_ROWS = 16;                        // rows per slot
-constexpr uint32_t RG_PITCH = RG_SEG * 4 + 64;     // bytes between the rows of a slot (+64: keeps a future fragment-order read conflict-free)
-constexpr uint32_t RG_SLOT = RG_ROWS * RG_PITCH;   // 17408 B
+constexpr uint32_t RG_SLOT_FLOATS = 4096;          // one slot = one row (or a K chunk of a longer row): ONE bulk copy of <= 16 KB
+constexpr uint32_t RG_SLOT = RG_SLOT_FLOATS * 4;
 constexpr int RG_MAX_SLOTS = 12;
 constexpr int RG_MAX_ITEMS = 2 * kNumSMs;
 constexpr int RG_MAX_HEADS = 256;
@@ -126,37 +124,30 @@ __device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1)
     r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
 }
 
-struct RingPos {
-    uint32_t slot, phase;
-    __device__ __forceinline__ void next(uint32_t n_slots) {
-        if (++slot == n_slots) { slot = 0; phase ^= 1; }
-    }
-};
+// The stream is a sequence of slots numbered from the start of the launch: slot q lives in ring entry q % n_slots, its
+// mbarrier phase bit is (q / n_slots) & 1.  Both sides derive q from (phase base, row, chunk, matrix) — no shared cursor.
+__device__ __forceinline__ uint32_t chunk_floats(uint32_t K, uint32_t nch) { return ((K / 4 + nch - 1) / nch) * 4; }
 
 // ---------------------------------------------------------------------------------------------------------
-// producer: rows [r0, r1) of W (and W3 for the SwiGLU pair) -> ring, tile by tile, segment by segment
+// producer (one thread): rows [r0, r1) of W (and W3 for the SwiGLU pair) -> ring; one bulk copy per (row, chunk, matrix)
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, RingPos &pos, uint32_t ring_base,
+__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t ring_base,
                                         RingShared &sh, uint32_t n_slots) {
-    const int lane = threadIdx.x & 31;
     uint32_t r0, r1;
     cta_rows(M, r0, r1);
-    const uint32_t nseg = K / RG_SEG;
-    for (uint32_t tile = r0; tile < r1; tile += RG_ROWS) {
-        const uint32_t nrows = min((uint32_t)RG_ROWS, r1 - tile);
-        for (uint32_t seg = 0; seg < nseg; seg++) {
+    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
+    for (uint32_t row = r0; row < r1; row++) {
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t k0 = c * CH, len = min(CH, K - k0);
 #pragma unroll
             for (int m = 0; m < NM; m++) {
-                const float *src = (m == 0 ? W : W3) + (size_t)(tile + lane) * K + (size_t)seg * RG_SEG;
-                const uint32_t fb = smem_u32(&sh.full[pos.slot]);
-                if (lane == 0) {
-                    mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);   // all 16 consumer warps released the slot
-                    mbar_expect_tx(fb, nrows * RG_SEG * 4);
-                }
-                __syncwarp();
-                if ((uint32_t)lane < nrows) bulk_g2s(ring_base + pos.slot * RG_SLOT + lane * RG_PITCH, src, RG_SEG * 4, fb);
-                pos.next(n_slots);
+                const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
+                const uint32_t fb = smem_u32(&sh.full[slot]);
+                mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // the consumer warp of slot q - n_slots released it
+                mbar_expect_tx(fb, len * 4);
+                bulk_g2s(ring_base + slot * RG_SLOT, (m == 0 ? W : W3) + (size_t)row * K + k0, len * 4, fb);
+                q++;
             }
         }
     }
@@ -164,50 +155,57 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
 
 // ---------------------------------------------------------------------------------------------------------
 // consumer: out[row] = epilogue(W[row] . x) for this CTA's rows of an M x K matrix; x in shared memory (xs).
+// Warp w owns rows r0 + w, r0 + w + 16, ... and consumes every slot of its rows by itself.
 // EPI: 0 none, 1 + res[row];  NM == 2: out[row] = silu(W1[row].x) * (W3[row].x)
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI>
-__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs, float *out, const float *res, RingPos &pos,
+__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs, float *out, const float *res, uint32_t &qbase,
                                         const uint8_t *ring, RingShared &sh, uint32_t n_slots) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t r0, r1;
     cta_rows(M, r0, r1);
-    const uint32_t nseg = K / RG_SEG;
-    const float4 *x4 = reinterpret_cast<const float4 *>(xs);
-    for (uint32_t tile = r0; tile < r1; tile += RG_ROWS) {
-        const uint32_t row = tile + warp;
-        const bool valid = row < r1;
-        float a1 = 0.f, a3 = 0.f;
-        for (uint32_t seg = 0; seg < nseg; seg++) {
-            const float4 xa = x4[seg * (RG_SEG / 4) + lane], xb = x4[seg * (RG_SEG / 4) + 32 + lane];
+    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
+    for (uint32_t row = r0 + warp; row < r1; row += RG_CWARPS) {
+        float acc[NM][2];
 #pragma unroll
-            for (int m = 0; m < NM; m++) {
-                mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase);
-                if (valid) {
-                    const float4 *wr = reinterpret_cast<const float4 *>(ring + (size_t)pos.slot * RG_SLOT + (size_t)warp * RG_PITCH);
-                    const float4 wa = wr[lane], wb = wr[32 + lane];
-                    float s = m == 0 ? a1 : a3;
-                    s = fmaf(wa.x, xa.x, s); s = fmaf(wa.y, xa.y, s); s = fmaf(wa.z, xa.z, s); s = fmaf(wa.w, xa.w, s);
-                    s = fmaf(wb.x, xb.x, s); s = fmaf(wb.y, xb.y, s); s = fmaf(wb.z, xb.z, s); s = fmaf(wb.w, xb.w, s);
-                    if (m == 0) a1 = s; else a3 = s;
+        for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
+        uint32_t q = qbase + (row - r0) * nch * NM;
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t k0 = c * CH, len4 = min(CH, K - k0) / 4;
+            const float4 *x4 = reinterpret_cast<const float4 *>(xs + k0);
+#pragma unroll
+            for (int m = 0; m < NM; m++, q++) {
+                const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
+                mbar_wait(smem_u32(&sh.full[slot]), ph);
+                const float4 *w4 = reinterpret_cast<const float4 *>(ring + (size_t)slot * RG_SLOT);
+                float s0 = acc[m][0], s1 = acc[m][1];
+                uint32_t f = lane;
+                for (; f + 32 < len4; f += 64) {
+                    const float4 wa = w4[f], wb = w4[f + 32], xa = x4[f], xb = x4[f + 32];
+                    s0 = fmaf(wa.x, xa.x, s0); s0 = fmaf(wa.y, xa.y, s0); s0 = fmaf(wa.z, xa.z, s0); s0 = fmaf(wa.w, xa.w, s0);
+                    s1 = fmaf(wb.x, xb.x, s1); s1 = fmaf(wb.y, xb.y, s1); s1 = fmaf(wb.z, xb.z, s1); s1 = fmaf(wb.w, xb.w, s1);
                 }
+                if (f < len4) {
+                    const float4 wa = w4[f], xa = x4[f];
+                    s0 = fmaf(wa.x, xa.x, s0); s0 = fmaf(wa.y, xa.y, s0); s0 = fmaf(wa.z, xa.z, s0); s0 = fmaf(wa.w, xa.w, s0);
+                }
+                acc[m][0] = s0; acc[m][1] = s1;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sh.empty[pos.slot]));
-                pos.next(n_slots);
+                if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
             }
         }
-        if (valid) {
-            a1 = warp_sum(a1);
-            if (NM == 2) a3 = warp_sum(a3);
-            if (lane == 0) {
-                float v;
-                if (NM == 2) v = __fmul_rn(silu_ref(a1), a3);
-                else if (EPI == 1) v = __fadd_rn(a1, __ldcg(res + row));
-                else v = a1;
-                out[row] = v;
-            }
+        float a1 = warp_sum(__fadd_rn(acc[0][0], acc[0][1]));
+        float a3 = 0.f;
+        if (NM == 2) a3 = warp_sum(__fadd_rn(acc[NM - 1][0], acc[NM - 1][1]));
+        if (lane == 0) {
+            float v;
+            if (NM == 2) v = __fmul_rn(silu_ref(a1), a3);
+            else if (EPI == 1) v = __fadd_rn(a1, __ldcg(res + row));
+            else v = a1;
+            out[row] = v;
         }
     }
+    qbase += (r1 - r0) * nch * NM;
 }
 
 // ---- activation vector of a phase -> shared memory -----------------------------------------------------------
@@ -419,7 +417,7 @@ __device__ __forceinline__ void attention_phase(const RingParams &p, const MegaL
 
 // dynamic shared memory: [ring: n_slots x RG_SLOT][xs: max(dim, ff) floats][scores: 2 x chunk_cap floats][RingShared]
 template <int HD>
-__global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingParams p) {
+__global__ void __maxnreg__(112) decode_ring_kernel(const RingParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots;
     uint8_t *ring = smem_raw;
@@ -431,7 +429,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_slots; s++) {
             mbar_init(smem_u32(&sh.full[s]), 1);
-            mbar_init(smem_u32(&sh.empty[s]), RG_CWARPS);
+            mbar_init(smem_u32(&sh.empty[s]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -444,9 +442,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     }
     __syncthreads();   // the only CTA-wide barrier: after it the producer warp and the consumers never meet again
 
-    RingPos pos;
-    pos.slot = 0; pos.phase = 0;
+    uint32_t pos = 0;   // slot counter (producer: next slot to fill; consumers: first slot of the current phase)
     if (producer) {
+        if (threadIdx.x != RG_CTHREADS) return;   // one thread drives the copy engine
         // ================= producer warp: the whole token's weights of this CTA, in schedule order =================
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
@@ -555,7 +553,7 @@ bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t v
     if (heads == 0 || dim % heads || heads > (uint32_t)RG_MAX_HEADS) return false;
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
-    if (dim % RG_SEG || ff % RG_SEG) return false;     // rows are streamed in 1 KB segments
+    if (dim % 4 || ff % 4) return false;               // 16-byte bulk copies
     (void)vocab;
     return ring_plan(dim, ff, heads, ctx, nullptr) >= 4;
 }

@@ -21,7 +21,9 @@
 //     (deterministic) and accumulated across passes.
 // Attention / RMSNorm / RoPE numerics: kernels_mega.cu.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -38,7 +40,7 @@ constexpr int RP_HALF = RP_CTHREADS / 2;
 constexpr int RP_MAXB = 8;
 constexpr int RP_SEG = 256;                        // floats of K per slot row
 constexpr int RP_ROWS = 16;
-constexpr uint32_t RP_PITCH = RP_SEG * 4 + 64;     // row pitch = 16 words mod 32: fragment-order LDS.128 is conflict-free
+constexpr uint32_t RP_PITCH = RP_SEG * 4;          // dense rows (one 3-D tensor-map box per slot): fragment-order LDS.128 is 2-way conflicted
 constexpr uint32_t RP_SLOT = RP_ROWS * RP_PITCH;
 constexpr int RP_MAX_SLOTS = 8;
 constexpr uint32_t RP_PASS_SEGS = 8;               // segments per K pass
@@ -99,6 +101,18 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], float a0, float a1, floa
 // v - trunc_tf32(v): exact in FP32 (the tensor core reads only the upper 19 bits of an operand register)
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 tf32_lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
+
+// 3-D tiled load (k, row, layer) -> dense [16][256] floats in shared memory, ONE instruction per slot: 1-D bulk copies
+// of 1 KB per row were measured copy-engine bound (~75 clk per copy instruction, 4 TB/s; profiles/README.md)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+struct RPMaps {   // one map per weight kind: dims {K, rows, layers} with the model's layer stride; box {256, 16, 1}
+    CUtensorMap wqkv, wo, w1, w3, w2, output;
+};
 
 struct RPParams {
     const MegaLayerHost *layers;   // Kc/Vc unused: every pod has its own cache (Kb/Vb + layer_off)
@@ -162,27 +176,21 @@ struct RingPos {
 // producer: for K pass, for tile, for segment of the pass (, for matrix): one slot
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, RingPos &pos, uint32_t ring_base,
-                                        RPShared &sh, uint32_t n_slots) {
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, RingPos &pos,
+                                        uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
     uint32_t r0, r1;
     cta_rows(M, r0, r1);
     const uint32_t nseg = K / RP_SEG;
     for (uint32_t s0 = 0; s0 < nseg; s0 += RP_PASS_SEGS) {
         const uint32_t s1 = min(s0 + RP_PASS_SEGS, nseg);
         for (uint32_t tile = r0; tile < r1; tile += RP_ROWS) {
-            const uint32_t nrows = min((uint32_t)RP_ROWS, r1 - tile);
             for (uint32_t seg = s0; seg < s1; seg++) {
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
-                    const float *src = (m == 0 ? W : W3) + (size_t)(tile + lane) * K + (size_t)seg * RP_SEG;
                     const uint32_t fb = smem_u32(&sh.full[pos.slot]);
-                    if (lane == 0) {
-                        mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
-                        mbar_expect_tx(fb, nrows * RP_SEG * 4);
-                    }
-                    __syncwarp();
-                    if ((uint32_t)lane < nrows) bulk_g2s(ring_base + pos.slot * RP_SLOT + lane * RP_PITCH, src, RP_SEG * 4, fb);
+                    mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
+                    mbar_expect_tx(fb, RP_SLOT);   // rows past the matrix end are zero-filled by the copy engine and still counted
+                    tma_load_3d(ring_base + pos.slot * RP_SLOT, m == 0 ? mapA : mapB, fb, (int)(seg * RP_SEG), (int)tile, layer);
                     pos.next(n_slots);
                 }
             }
@@ -505,7 +513,7 @@ __device__ __forceinline__ void attention_pods(const RPParams &p, size_t layer_o
 
 // dynamic shared memory: [ring: n_slots x RP_SLOT][xs: 64 KB (attention scores overlay it)][RPShared]
 template <int HD>
-__global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(const RPParams p) {
+__global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(const RPParams p, const __grid_constant__ RPMaps maps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots, B = p.B;
     uint8_t *ring = smem_raw;
@@ -537,15 +545,15 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
     RingPos pos;
     pos.slot = 0; pos.phase = 0;
     if (producer) {
+        if (threadIdx.x != RP_CTHREADS) return;   // one thread drives the copy engine
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
-            const MegaLayerHost L = p.layers[li];
-            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, ring_base, sh, n_slots);
-            produce<1>(L.wo, nullptr, dim, dim, pos, ring_base, sh, n_slots);
-            produce<2>(L.w1, L.w3, dim, ff, pos, ring_base, sh, n_slots);
-            produce<1>(L.w2, nullptr, ff, dim, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.wqkv, nullptr, (int)li, dim, 3 * dim, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.wo, nullptr, (int)li, dim, dim, pos, ring_base, sh, n_slots);
+            produce<2>(&maps.w1, &maps.w3, (int)li, dim, ff, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.w2, nullptr, (int)li, ff, dim, pos, ring_base, sh, n_slots);
         }
-        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(&maps.output, nullptr, 0, dim, p.vocab, pos, ring_base, sh, n_slots);
         return;
     }
     unsigned target = 0;
@@ -599,7 +607,7 @@ static uint32_t pods_plan(size_t *smem_out) {
 }
 
 template <int HD>
-static cudaError_t launch(const RPParams &p, size_t smem, cudaStream_t st) {
+static cudaError_t launch(const RPParams &p, const RPMaps &maps, size_t smem, cudaStream_t st) {
     static bool attr[64] = {};  // function attributes are per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -615,7 +623,7 @@ static cudaError_t launch(const RPParams &p, size_t smem, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_ring_pods_kernel<HD>, p);
+    return cudaLaunchKernelEx(&cfg, decode_ring_pods_kernel<HD>, p, maps);
 }
 
 }  // namespace
@@ -651,9 +659,58 @@ void decode_ring_pods(const MegaPodsParamsHost &h, cudaStream_t st) {
     p.n_slots = pods_plan(&smem);
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
     const uint32_t hd = h.dim / h.heads;
-    cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);
+    LB_CHECK(h.tmaps != nullptr, "decode_ring_pods: tensor maps missing (ring_pods_make_maps)");
+    const RPMaps &maps = *static_cast<const RPMaps *>(h.tmaps);
+    cudaError_t e = hd == 128 ? launch<128>(p, maps, smem, st) : hd == 64 ? launch<64>(p, maps, smem, st) : launch<32>(p, maps, smem, st);
     LB_CUDA(e);
     count_launch();
+}
+
+// ---- tensor maps -------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled_rp)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats) {
+    static PFN_encodeTiled_rp fn = nullptr;
+    if (!fn) {
+        void *pfn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        LB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &q));
+        LB_CHECK(pfn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<PFN_encodeTiled_rp>(pfn);
+    }
+    CUtensorMap m;
+    cuuint64_t dims[3] = {K, rows, layers};
+    cuuint64_t strides[2] = {K * 4, (layers > 1 ? layer_stride_floats : K * rows) * 4};
+    cuuint32_t box[3] = {RP_SEG, RP_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+size_t ring_pods_maps_bytes() { return sizeof(RPMaps); }
+
+// layers_host = the host copy of the MegaLayerHost array: every layer must sit at the same stride in one slab
+void ring_pods_make_maps(const MegaLayerHost *L, uint32_t n_layers, uint32_t dim, uint32_t ff, uint32_t vocab, const float *output,
+                         void *maps_out) {
+    LB_CHECK(L && n_layers >= 1 && maps_out, "ring_pods_make_maps: nil argument");
+    ptrdiff_t stride = n_layers > 1 ? L[1].wqkv - L[0].wqkv : 0;
+    for (uint32_t i = 1; i < n_layers; i++) {
+        LB_CHECK(L[i].wqkv - L[i - 1].wqkv == stride && L[i].wo - L[i - 1].wo == stride && L[i].w1 - L[i - 1].w1 == stride &&
+                     L[i].w3 - L[i - 1].w3 == stride && L[i].w2 - L[i - 1].w2 == stride,
+                 "ring_pods_make_maps: layers are not equally spaced in one slab");
+    }
+    LB_CHECK(stride >= 0 && (stride % 4) == 0, "ring_pods_make_maps: bad layer stride");
+    RPMaps m;
+    m.wqkv = rp_map(L[0].wqkv, dim, 3ull * dim, n_layers, (uint64_t)stride);
+    m.wo = rp_map(L[0].wo, dim, dim, n_layers, (uint64_t)stride);
+    m.w1 = rp_map(L[0].w1, dim, ff, n_layers, (uint64_t)stride);
+    m.w3 = rp_map(L[0].w3, dim, ff, n_layers, (uint64_t)stride);
+    m.w2 = rp_map(L[0].w2, ff, dim, n_layers, (uint64_t)stride);
+    m.output = output ? rp_map(output, dim, vocab, 1, 0) : m.wo;
+    memcpy(maps_out, &m, sizeof(RPMaps));
 }
 
 }  // namespace k

@@ -154,6 +154,8 @@ struct PodBatch {
     bool use_ring = false;              // ... the TMA-ring variant
     void *mega_layers_dev = nullptr;    // k::MegaLayerHost[layers]
     unsigned *mega_barrier = nullptr;
+    std::vector<uint8_t> tmaps;         // TMA tensor maps of the weight matrices (k::ring_pods_make_maps)
+    const void *tmaps_ptr = nullptr;
 
     explicit PodBatch(const std::vector<Context *> &ctxs);
     ~PodBatch();

@@ -80,3 +80,10 @@ class Stage:
 
     def logits(self, seq: int) -> np.ndarray:
         return llama.ReadLogits(self.ctxs[seq]).copy()
+
+    def free(self):
+        """Release the contexts, then the stage model (device memory) now rather than at garbage collection."""
+        for c in self.ctxs:
+            c.ReleaseContext()
+        self.ctxs = []
+        self.model.free()
