@@ -4,6 +4,8 @@
 // (the reference re-transposes the whole layer's V cache every call, llama.go:315-322).
 // Numerics: FP32 dot, FP32 multiply by f32(1/sqrt(hd)), FP32 max, e = f32(exp(f64(s - max))),
 // p = e * f32(1/sum) (ml.go:2472-2499), FP32 P·V.  The sums are tree-ordered.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -313,10 +315,157 @@ static void attention_decode_launch(const float *q, const float *Kc, const float
         launch_pdl(attention_decode_kernel<32>, grid, dim3(DEC_THREADS), smem, st, q, Kc, Vc, out, past_dev, dim, scale, part_o, part_ml, tickets, chunk_cap, pods);
 }
 
+// ------------------------------------------------------------------------------------------
+// Prefill attention, tiled (N > 1): one CTA per (head, 16 consecutive queries).  The single-pass kernel above
+// re-reads every query's whole K/V prefix from L2 (O(N*T) traffic: 2.4 GB per 7B layer at N = 384); here a
+// 64-key tile of K and V is staged ONCE in shared memory for the 16 queries of the CTA (two per warp),
+// scores by FP32 dots out of shared memory, online softmax per query (running max m, sum l and output acc,
+// rescaled by f32(exp(f64(m - m'))) when the maximum moves; the terms e = f32(exp(f64(s - m'))) as in
+// ml.go:2472-2499), P.V from the staged V tile, out = acc * f32(1/l).  Versus the reference's two-pass row softmax
+// this reassociates the sums (a few 1e-7 relative).
+// ------------------------------------------------------------------------------------------
+constexpr int ATP_THREADS = 256;   // 8 warps x 2 queries
+constexpr int ATP_QT = 16;         // queries per CTA
+constexpr int ATP_KT = 64;         // keys per tile: lane l scores keys l and l + 32
+
+template <int HD>
+__global__ void __launch_bounds__(ATP_THREADS)
+attention_tiled_kernel(const float *__restrict__ q, uint32_t ldq, const float *__restrict__ Kc, const float *__restrict__ Vc,
+                       float *__restrict__ out, const uint32_t *__restrict__ past_dev, uint32_t N, uint32_t dim, float scale) {
+    constexpr int KP = HD + 4;                 // K tile row pitch: 4 words mod 32 -> the 8 lanes of an LDS.128 phase hit 8 bank groups
+    constexpr int D4 = HD / 4;
+    extern __shared__ float smt[];
+    float *Ks = smt;                           // [ATP_KT][KP]
+    float *Vs = Ks + ATP_KT * KP;              // [ATP_KT][HD]
+    float *Qs = Vs + ATP_KT * HD;              // [ATP_QT][HD]
+    float *Ps = Qs + ATP_QT * HD;              // [ATP_QT][ATP_KT]
+    const uint32_t past = *past_dev;
+    const uint32_t h = blockIdx.x, q0 = blockIdx.y * ATP_QT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nq = min((uint32_t)ATP_QT, N - q0);
+    const uint32_t Tmax = past + q0 + nq;      // keys 0 .. Tmax-1 are visible to the last query of the tile (DiagMaskInf, ml.go:2399-2408)
+    for (uint32_t i = threadIdx.x; i < ATP_QT * D4; i += ATP_THREADS) {
+        const uint32_t qi = i / D4, d4 = i % D4;
+        reinterpret_cast<float4 *>(Qs)[i] = qi < nq ? *reinterpret_cast<const float4 *>(q + (size_t)(q0 + qi) * ldq + (size_t)h * HD + d4 * 4)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const uint32_t qa = warp * 2, qb = warp * 2 + 1;           // this warp's two queries
+    const uint32_t ta = past + q0 + qa, tb = past + q0 + qb;   // last visible key of each
+    float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;      // lane l owns output dims 4l .. 4l+3 (lanes >= D4 idle for small heads)
+    for (uint32_t k0 = 0; k0 < Tmax; k0 += ATP_KT) {
+        __syncthreads();                                       // previous tile fully consumed (and Qs written, first trip)
+        const uint32_t nk = min((uint32_t)ATP_KT, Tmax - k0);
+        for (uint32_t i = threadIdx.x; i < ATP_KT * D4; i += ATP_THREADS) {
+            const uint32_t kj = i / D4, d4 = i % D4;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (kj < nk) {
+                kv = *reinterpret_cast<const float4 *>(Kc + (size_t)(k0 + kj) * dim + (size_t)h * HD + d4 * 4);
+                vv = *reinterpret_cast<const float4 *>(Vc + (size_t)(k0 + kj) * dim + (size_t)h * HD + d4 * 4);
+            }
+            *reinterpret_cast<float4 *>(Ks + kj * KP + d4 * 4) = kv;
+            *reinterpret_cast<float4 *>(Vs + kj * HD + d4 * 4) = vv;
+        }
+        __syncthreads();
+        if (qa < nq) {
+            // ---- scores of keys k0 + lane and k0 + lane + 32 for both queries
+            float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;
+            const float4 *k0p = reinterpret_cast<const float4 *>(Ks + lane * KP), *k1p = reinterpret_cast<const float4 *>(Ks + (lane + 32) * KP);
+            const float4 *qap = reinterpret_cast<const float4 *>(Qs + qa * HD), *qbp = reinterpret_cast<const float4 *>(Qs + qb * HD);
+#pragma unroll 8
+            for (int d4 = 0; d4 < D4; d4++) {
+                const float4 ka = k0p[d4], kb = k1p[d4], xa = qap[d4], xb = qbp[d4];
+                sa0 = fmaf(ka.x, xa.x, sa0); sa0 = fmaf(ka.y, xa.y, sa0); sa0 = fmaf(ka.z, xa.z, sa0); sa0 = fmaf(ka.w, xa.w, sa0);
+                sa1 = fmaf(kb.x, xa.x, sa1); sa1 = fmaf(kb.y, xa.y, sa1); sa1 = fmaf(kb.z, xa.z, sa1); sa1 = fmaf(kb.w, xa.w, sa1);
+                sb0 = fmaf(ka.x, xb.x, sb0); sb0 = fmaf(ka.y, xb.y, sb0); sb0 = fmaf(ka.z, xb.z, sb0); sb0 = fmaf(ka.w, xb.w, sb0);
+                sb1 = fmaf(kb.x, xb.x, sb1); sb1 = fmaf(kb.y, xb.y, sb1); sb1 = fmaf(kb.z, xb.z, sb1); sb1 = fmaf(kb.w, xb.w, sb1);
+            }
+            const uint32_t key0 = k0 + lane, key1 = k0 + lane + 32;
+            // Scale (llama.go:303-307) then the causal mask
+            sa0 = key0 <= ta ? __fmul_rn(sa0, scale) : -INFINITY; sa1 = key1 <= ta ? __fmul_rn(sa1, scale) : -INFINITY;
+            sb0 = (qb < nq && key0 <= tb) ? __fmul_rn(sb0, scale) : -INFINITY; sb1 = (qb < nq && key1 <= tb) ? __fmul_rn(sb1, scale) : -INFINITY;
+            // ---- online softmax, query a
+            {
+                const float mt = warp_max(fmaxf(sa0, sa1));
+                const float mn = fmaxf(ma, mt);
+                if (mn != -INFINITY) {
+                    const float alpha = ma == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(ma, mn));
+                    const float e0 = sa0 == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(sa0, mn));
+                    const float e1 = sa1 == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(sa1, mn));
+                    Ps[qa * ATP_KT + lane] = e0; Ps[qa * ATP_KT + lane + 32] = e1;
+                    la = fmaf(la, alpha, warp_sum(e0 + e1));
+                    oa.x *= alpha; oa.y *= alpha; oa.z *= alpha; oa.w *= alpha;
+                    ma = mn;
+                } else { Ps[qa * ATP_KT + lane] = 0.f; Ps[qa * ATP_KT + lane + 32] = 0.f; }
+            }
+            if (qb < nq) {
+                const float mt = warp_max(fmaxf(sb0, sb1));
+                const float mn = fmaxf(mb, mt);
+                if (mn != -INFINITY) {
+                    const float alpha = mb == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(mb, mn));
+                    const float e0 = sb0 == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(sb0, mn));
+                    const float e1 = sb1 == -INFINITY ? 0.f : (float)exp((double)__fsub_rn(sb1, mn));
+                    Ps[qb * ATP_KT + lane] = e0; Ps[qb * ATP_KT + lane + 32] = e1;
+                    lb = fmaf(lb, alpha, warp_sum(e0 + e1));
+                    ob.x *= alpha; ob.y *= alpha; ob.z *= alpha; ob.w *= alpha;
+                    mb = mn;
+                } else { Ps[qb * ATP_KT + lane] = 0.f; Ps[qb * ATP_KT + lane + 32] = 0.f; }
+            } else { Ps[qb * ATP_KT + lane] = 0.f; Ps[qb * ATP_KT + lane + 32] = 0.f; }
+            __syncwarp();
+            // ---- P.V for both queries: lane l accumulates dims 4l .. 4l+3 over the tile's keys
+            if (lane < D4) {
+                const float *pa = Ps + qa * ATP_KT, *pb = Ps + qb * ATP_KT;
+                for (uint32_t j = 0; j < nk; j++) {   // masked keys carry weight 0
+                    const float4 v = *reinterpret_cast<const float4 *>(Vs + j * HD + lane * 4);
+                    const float wa = pa[j], wb = pb[j];
+                    oa.x = fmaf(v.x, wa, oa.x); oa.y = fmaf(v.y, wa, oa.y); oa.z = fmaf(v.z, wa, oa.z); oa.w = fmaf(v.w, wa, oa.w);
+                    ob.x = fmaf(v.x, wb, ob.x); ob.y = fmaf(v.y, wb, ob.y); ob.z = fmaf(v.z, wb, ob.z); ob.w = fmaf(v.w, wb, ob.w);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane < D4) {
+        if (qa < nq) {
+            const float inv = __fdiv_rn(1.0f, la);
+            *reinterpret_cast<float4 *>(out + (size_t)(q0 + qa) * dim + (size_t)h * HD + lane * 4) =
+                make_float4(__fmul_rn(oa.x, inv), __fmul_rn(oa.y, inv), __fmul_rn(oa.z, inv), __fmul_rn(oa.w, inv));
+        }
+        if (qb < nq) {
+            const float inv = __fdiv_rn(1.0f, lb);
+            *reinterpret_cast<float4 *>(out + (size_t)(q0 + qb) * dim + (size_t)h * HD + lane * 4) =
+                make_float4(__fmul_rn(ob.x, inv), __fmul_rn(ob.y, inv), __fmul_rn(ob.z, inv), __fmul_rn(ob.w, inv));
+        }
+    }
+}
+
+template <int HD>
+static void attention_tiled_launch(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,
+                                   const uint32_t *past_dev, uint32_t dim, uint32_t heads, float scale, cudaStream_t st) {
+    const size_t smem = ((size_t)ATP_KT * (HD + 4) + (size_t)ATP_KT * HD + (size_t)ATP_QT * HD + (size_t)ATP_QT * ATP_KT) * sizeof(float);
+    static bool attr_set[64] = {};  // function attributes are per device
+    int dev = 0;
+    LB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        LB_CUDA(cudaFuncSetAttribute(attention_tiled_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    attention_tiled_kernel<HD><<<dim3(heads, (N + ATP_QT - 1) / ATP_QT), ATP_THREADS, smem, st>>>(q, ldq, Kc, Vc, out, past_dev, N, dim, scale);
+    LB_LAUNCH_CHECK();
+}
+
 void attention(const float *q, uint32_t ldq, const float *Kc, const float *Vc, float *out, uint32_t N,
                const uint32_t *past_dev, uint32_t max_T, uint32_t dim, uint32_t heads, cudaStream_t st) {
     const uint32_t hd = dim / heads;
     LB_CHECK(hd == 32 || hd == 64 || hd == 128, "attention: head dim must be 32, 64 or 128");
+    static const bool single_pass = getenv("LB_ATTN_SINGLE_PASS") != nullptr;   // A/B switch: the round-1 kernel
+    if (!single_pass) {
+        const float sc = (float)(1.0 / sqrt((double)dim / (double)heads));  // llama.go:306
+        if (hd == 128) attention_tiled_launch<128>(q, ldq, Kc, Vc, out, N, past_dev, dim, heads, sc, st);
+        else if (hd == 64) attention_tiled_launch<64>(q, ldq, Kc, Vc, out, N, past_dev, dim, heads, sc, st);
+        else attention_tiled_launch<32>(q, ldq, Kc, Vc, out, N, past_dev, dim, heads, sc, st);
+        return;
+    }
     const uint32_t T = max_T;
     size_t smem = (((size_t)T + 3) & ~(size_t)3) * sizeof(float) + (size_t)ATT_THREADS * sizeof(float);
     static bool attr_set[64] = {};  // function attributes are per device

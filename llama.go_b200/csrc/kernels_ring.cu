@@ -417,7 +417,7 @@ __device__ __forceinline__ void attention_phase(const RingParams &p, const MegaL
 
 // dynamic shared memory: [ring: n_slots x RG_SLOT][xs: max(dim, ff) floats][scores: 2 x chunk_cap floats][RingShared]
 template <int HD>
-__global__ void __maxnreg__(112) decode_ring_kernel(const RingParams p) {
+__global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots;
     uint8_t *ring = smem_raw;

@@ -161,10 +161,17 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
     }
     ccsync();
 }
-__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
-    r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
-    r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
+// Rows of an M-row matrix owned by this CTA in MulMat phase number `ph`: whole 16-row tiles (a TMA box never fetches
+// rows the CTA does not use — contiguous balanced row ranges wasted ~11 % of the stream on ragged last tiles),
+// ceil(M/16) tiles dealt out evenly; which CTAs get the extra tile rotates with the phase number, and the ring's
+// run-ahead lets a CTA that is short one tile start on the next phase's weights while the others finish.
+__device__ __forceinline__ void cta_tile_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
+    const uint32_t ntiles = (M + RP_ROWS - 1) / RP_ROWS;
+    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
+    r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RP_ROWS);
+    r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RP_ROWS);
 }
+
 struct RingPos {
     uint32_t slot, phase;
     __device__ __forceinline__ void next(uint32_t n_slots) {
@@ -176,10 +183,10 @@ struct RingPos {
 // producer: for K pass, for tile, for segment of the pass (, for matrix): one slot
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, RingPos &pos,
-                                        uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
+__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, uint32_t &ph,
+                                        RingPos &pos, uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
     uint32_t r0, r1;
-    cta_rows(M, r0, r1);
+    cta_tile_rows(M, ph++, r0, r1);
     const uint32_t nseg = K / RP_SEG;
     for (uint32_t s0 = 0; s0 < nseg; s0 += RP_PASS_SEGS) {
         const uint32_t s1 = min(s0 + RP_PASS_SEGS, nseg);
@@ -297,12 +304,12 @@ __device__ __forceinline__ void merge_stats(const RPParams &p, RPShared &sh) {
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI, int XMODE, int HD>
 __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsrc, uint32_t ldx, const float *wnorm,
-                                        float *out, uint32_t ldo, const float *res, uint32_t ldr, RingPos &pos,
+                                        float *out, uint32_t ldo, const float *res, uint32_t ldr, uint32_t &ph, RingPos &pos,
                                         const uint8_t *ring, float4 *xs, const RPParams &p, RPShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint32_t n_slots = p.n_slots, B = p.B;
     uint32_t r0, r1;
-    cta_rows(M, r0, r1);
+    cta_tile_rows(M, ph++, r0, r1);
     const uint32_t nseg = K / RP_SEG;
     const uint32_t npass = (nseg + RP_PASS_SEGS - 1) / RP_PASS_SEGS;
     const uint32_t wofs = (uint32_t)g * RP_PITCH + (uint32_t)warp * 64 + (uint32_t)t * 16;   // this lane's 16 B of row g inside a slot
@@ -544,16 +551,17 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
 
     RingPos pos;
     pos.slot = 0; pos.phase = 0;
+    uint32_t ph = 0;   // MulMat phase counter (rotates the tile assignment; identical on both sides)
     if (producer) {
         if (threadIdx.x != RP_CTHREADS) return;   // one thread drives the copy engine
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
-            produce<1>(&maps.wqkv, nullptr, (int)li, dim, 3 * dim, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.wo, nullptr, (int)li, dim, dim, pos, ring_base, sh, n_slots);
-            produce<2>(&maps.w1, &maps.w3, (int)li, dim, ff, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.w2, nullptr, (int)li, ff, dim, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.wqkv, nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.wo, nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
+            produce<2>(&maps.w1, &maps.w3, (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.w2, nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
         }
-        if (p.final_norm) produce<1>(&maps.output, nullptr, 0, dim, p.vocab, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(&maps.output, nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
         return;
     }
     unsigned target = 0;
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         const size_t layer_off = (size_t)li * p.ctx * dim;
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         rms_scales(dim, B, sh);
-        consume<1, 0, 1, HD>(dim, 3 * dim, nullptr, 0, L.attention_norm, p.qkv, 3 * dim, nullptr, 0, pos, ring, xs, p, sh);
+        consume<1, 0, 1, HD>(dim, 3 * dim, nullptr, 0, L.attention_norm, p.qkv, 3 * dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         grid_barrier(p.barrier, target, gridDim.x);
         // ---- P2: RoPE, KV store, attention (llama.go:274-333)
         attention_pods<HD>(p, layer_off, sh, scores);
@@ -570,26 +578,26 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         // ---- P3: wo + residual (llama.go:336-340)
         if (p.splits > 1) {
             merge_stats(p, sh);
-            consume<1, 1, 2, HD>(dim, dim, nullptr, 0, nullptr, p.y, dim, nullptr, 0, pos, ring, xs, p, sh);
+            consume<1, 1, 2, HD>(dim, dim, nullptr, 0, nullptr, p.y, dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         } else {
-            consume<1, 1, 0, HD>(dim, dim, p.attn, dim, nullptr, p.y, dim, nullptr, 0, pos, ring, xs, p, sh);
+            consume<1, 1, 0, HD>(dim, dim, p.attn, dim, nullptr, p.y, dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         }
         grid_barrier(p.barrier, target, gridDim.x);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         if (threadIdx.x < RP_MAXB) sh.xrow[threadIdx.x] = threadIdx.x < B ? p.y + (size_t)threadIdx.x * dim : nullptr;
         ccsync();
         rms_scales(dim, B, sh);
-        consume<2, 0, 1, HD>(dim, ff, nullptr, 0, L.ffn_norm, p.act, ff, nullptr, 0, pos, ring, xs, p, sh);
+        consume<2, 0, 1, HD>(dim, ff, nullptr, 0, L.ffn_norm, p.act, ff, nullptr, 0, ph, pos, ring, xs, p, sh);
         grid_barrier(p.barrier, target, gridDim.x);
         // ---- P5: w2 + residual (llama.go:363-366)
-        consume<1, 1, 0, HD>(ff, dim, p.act, ff, nullptr, p.x, dim, p.y, dim, pos, ring, xs, p, sh);
+        consume<1, 1, 0, HD>(ff, dim, p.act, ff, nullptr, p.x, dim, p.y, dim, ph, pos, ring, xs, p, sh);
         grid_barrier(p.barrier, target, gridDim.x);
         if (threadIdx.x < RP_MAXB) sh.xrow[threadIdx.x] = threadIdx.x < B ? p.x + (size_t)threadIdx.x * dim : nullptr;
         ccsync();
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         rms_scales(dim, B, sh);
-        consume<1, 0, 1, HD>(dim, p.vocab, nullptr, 0, p.final_norm, p.logits, p.vocab, nullptr, 0, pos, ring, xs, p, sh);
+        consume<1, 0, 1, HD>(dim, p.vocab, nullptr, 0, p.final_norm, p.logits, p.vocab, nullptr, 0, ph, pos, ring, xs, p, sh);
     }
 }
 
@@ -633,9 +641,8 @@ bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint3
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
     if (dim % RP_SEG || ff % RP_SEG) return false;
-    if (vocab < (uint32_t)kNumSMs || dim < (uint32_t)kNumSMs) return false;                 // every CTA owns rows in every phase
-    const uint32_t max_rows = ((ff > vocab ? ff : vocab) > 3 * dim ? (ff > vocab ? ff : vocab) : 3 * dim) / kNumSMs + 1;
-    if ((max_rows + RP_ROWS - 1) / RP_ROWS + 1 > (uint32_t)RP_MAX_TILES) return false;   // acc[] rows
+    const uint32_t max_m = (ff > vocab ? ff : vocab) > 3 * dim ? (ff > vocab ? ff : vocab) : 3 * dim;
+    if (((max_m + RP_ROWS - 1) / RP_ROWS + kNumSMs - 1) / kNumSMs > (uint32_t)RP_MAX_TILES) return false;   // acc[] rows
     if ((size_t)2 * ctx * sizeof(float) > (size_t)RP_XS_F4 * 16) return false;             // attention scores overlay the stage
     return pods_plan(nullptr) >= 3;
 }

@@ -1,0 +1,749 @@
+// kernels_ring_q8.cu — single-token decode with Q8_0 block-quantised weights (BASELINE config 3; format DESIGN.md §6)
+// as ONE persistent cooperative kernel on the TMA ring, with the MulMat on the INT8 tensor cores.
+//
+// Round-1/2 history (profiles/README.md): the per-op Q8 path is a latency chain per kernel (0.50 of its roofline:
+// a Q8 matrix is 4x smaller than its FP32 twin, so every kernel is one wave of resident warps, and the PRMT/FADD
+// dequantisation costs ~3.5 CUDA-core instructions per weight); a register-fed Q8 megakernel (173 / 290 tok/s) and an
+// int8-mma per-op GEMV (382 tok/s) were measured slower.  Here
+//   * the weight stream is decoupled from the consumers: a producer thread feeds a shared-memory ring with 3-D
+//     tensor-map TMA loads (slot = 16 rows x 1024 int8 + their 16 x 32 block scales), running ahead across tiles,
+//     phases and grid barriers (kernels_ring.cu);
+//   * the int8 weights are consumed AS STORED by mma.sync.m16n8k32.s8 (A = 16 rows x 32 k = one Q8 block per row);
+//     the FP32 activation block (32 values) enters as four balanced base-128 digit planes relative to the block's
+//     power-of-two scale s (x = s * (d0/2^6 + d1/2^13 + d2/2^20 + d3/2^27) +- s * 2^-28), four of the eight B columns;
+//     the s32 products are exact, one FMA per (row, block) applies d_w * s.  No dequantisation instruction per weight:
+//     ~24 instructions per 512 weights instead of ~1800.
+// The result differs from "the FP32 path on the dequantised weights d*q" (the parity target, tests/test_gpu_q8.py)
+// only by summation order and the 2^-28 digit truncation.
+// Attention / RMSNorm / RoPE numerics: kernels_mega.cu.
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace lb {
+namespace k {
+namespace {
+
+constexpr int RQ_CWARPS = 16;
+constexpr int RQ_CTHREADS = RQ_CWARPS * 32;
+constexpr int RQ_THREADS = RQ_CTHREADS + 32;       // + the producer warp
+constexpr int RQ_HALF = RQ_CTHREADS / 2;
+constexpr uint32_t RQ_SEGK = 1024;                 // k per slot row
+constexpr uint32_t RQ_ROWS = 16;
+constexpr uint32_t RQ_QBYTES = RQ_ROWS * RQ_SEGK;              // 16 KB of int8
+constexpr uint32_t RQ_DBYTES = RQ_ROWS * (RQ_SEGK / 32) * 4;   // 2 KB of block scales
+constexpr uint32_t RQ_SLOT = RQ_QBYTES + RQ_DBYTES;            // 18432
+constexpr int RQ_MAX_SLOTS = 10;
+constexpr int RQ_MAX_ITEMS = 2 * kNumSMs;
+constexpr int RQ_MAX_HEADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ccsync() { asm volatile("bar.sync 1, %0;" ::"n"(RQ_CTHREADS) : "memory"); }   // consumers only
+__device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(RQ_HALF) : "memory"); }
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline bug must not hang the box
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// D(16x8, s32) = A(16x32, s8, row) * B(32x8, s8, col)
+__device__ __forceinline__ void mma_s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+
+struct RQMaps {   // per weight kind: q plane viewed as uint32 [layers][rows][K/4] (box 256 x 16 x 1), d plane [layers][rows][K/32] (box 32 x 16 x 1)
+    CUtensorMap q_wqkv, d_wqkv, q_wo, d_wo, q_w1, d_w1, q_w3, d_w3, q_w2, d_w2, q_out, d_out;
+};
+
+struct RQParams {
+    const MegaLayerHost *layers;      // norm vectors and the KV slabs (the matrices come through the tensor maps)
+    uint32_t n_layers;
+    const float *tok_embeddings;
+    const uint32_t *tokens;
+    const uint32_t *state;            // {past, step}
+    const float *final_norm;          // nullptr: no lm_head on this stage
+    float *x, *y, *qkv, *attn, *act, *logits;
+    float *part_o, *part_ml;
+    unsigned *barrier;
+    uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots, kpad;   // kpad = max(dim, ff) rounded up to 1024
+    unsigned long long *trace;
+};
+
+struct RQShared {
+    unsigned long long full[RQ_MAX_SLOTS], empty[RQ_MAX_SLOTS];
+    double red[RQ_CWARPS];
+    double rope_cs[64][2];
+    float fred[2][RQ_CWARPS / 2];
+    float hbcast[2];
+    float part[2][RQ_CWARPS][16];     // [matrix][warp][row of the tile]
+    float4 pv[RQ_CTHREADS];
+    float mrg_m[RQ_MAX_ITEMS], mrg_l[RQ_MAX_ITEMS], mrg_w[RQ_MAX_ITEMS], mrg_inv[RQ_MAX_HEADS];
+};
+
+// ---- grid barrier among the consumer threads of all CTAs (the producer warps never take part)
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+    target += nctas;
+    ccsync();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        __threadfence();
+    }
+    ccsync();
+}
+
+
+
+// Rows of an M-row matrix owned by this CTA in MulMat phase number `ph`: whole 16-row tiles (a TMA box never fetches
+// rows the CTA does not use), ceil(M/16) tiles dealt out evenly; WHICH CTAs get the extra tile rotates with the phase
+// number, and the run-ahead of the ring lets a CTA that is short one tile in this phase start on the next phase's
+// weights while the others finish — the per-phase imbalance averages out over a layer.
+__device__ __forceinline__ void cta_tile_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
+    const uint32_t ntiles = (M + RQ_ROWS - 1) / RQ_ROWS;
+    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
+    r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RQ_ROWS);
+    r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RQ_ROWS);
+}
+
+struct RingPos {
+    uint32_t slot, phase;
+    __device__ __forceinline__ void next(uint32_t n_slots) {
+        if (++slot == n_slots) { slot = 0; phase ^= 1; }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// producer (one thread): for tile, for segment (, for matrix): the int8 box and its scale box into one slot
+// ---------------------------------------------------------------------------------------------------------
+template <int NM>
+__device__ __forceinline__ void produce(const CUtensorMap *qA, const CUtensorMap *dA, const CUtensorMap *qB, const CUtensorMap *dB, int layer,
+                                        uint32_t K, uint32_t M, uint32_t &ph, RingPos &pos, uint32_t ring_base, RQShared &sh, uint32_t n_slots) {
+    uint32_t r0, r1;
+    cta_tile_rows(M, ph++, r0, r1);
+    const uint32_t nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
+    for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const uint32_t fb = smem_u32(&sh.full[pos.slot]);
+                mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
+                mbar_expect_tx(fb, RQ_SLOT);   // out-of-range rows / columns are zero-filled by the copy engine and still counted
+                const uint32_t dst = ring_base + pos.slot * RQ_SLOT;
+                tma_load_3d(dst, m == 0 ? qA : qB, fb, (int)(seg * (RQ_SEGK / 4)), (int)tile, layer);
+                tma_load_3d(dst + RQ_QBYTES, m == 0 ? dA : dB, fb, (int)(seg * (RQ_SEGK / 32)), (int)tile, layer);
+                pos.next(n_slots);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// activation vector (FP32, in xs) -> IN PLACE digit planes: block b's 32 floats (128 bytes) become its four digit planes
+// dig[(b * 4 + plane) * 32 + k % 32] (the same 128 bytes), block scales in xsc[b]; blocks up to kp/32, columns >= K are zero.
+// One warp per block, one lane per element.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void make_digits(float *xs, uint32_t K, uint32_t kp, float *xsc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int8_t *dig = reinterpret_cast<int8_t *>(xs);
+    for (uint32_t b = warp; b < kp / 32; b += RQ_CWARPS) {
+        const uint32_t kk = b * 32 + lane;
+        const float v = kk < K ? xs[kk] : 0.f;
+        const float m = warp_max(fabsf(v));      // (also orders every lane's read of the block before the writes below)
+        int e = 0;
+        if (m > 0.f) frexpf(m, &e);                    // m = f * 2^e, f in [0.5, 1)  ->  |v| / 2^e < 1
+        const float s = ldexpf(1.0f, e), inv = ldexpf(1.0f, -e);
+        float r = __fmul_rn(v, inv);                   // exact (power of two)
+        int d[4];
+        r = __fmul_rn(r, 64.0f);
+        d[0] = __float2int_rn(r); r = __fsub_rn(r, (float)d[0]);
+#pragma unroll
+        for (int i = 1; i < 4; i++) {
+            r = __fmul_rn(r, 128.0f);
+            d[i] = __float2int_rn(r);
+            r = __fsub_rn(r, (float)d[i]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++) dig[(b * 4 + i) * 32 + lane] = (int8_t)d[i];
+        if (lane == 0) xsc[b] = s;
+    }
+    ccsync();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// consumer: out[row] = epilogue(sum_k d[row][k/32] q[row][k] x[k]) for this CTA's rows; NM == 2: silu(W1.x) * (W3.x)
+// Warp w takes blocks 2w and 2w + 1 of every slot (64 of its 1024 k) for all 16 rows; K-slices are combined
+// across the 16 warps per tile in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+template <int NM, int EPI>
+__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs_dig, const float *xsc, float *out, const float *res,
+                                        uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint32_t r0, r1;
+    cta_tile_rows(M, ph++, r0, r1);
+    const uint32_t nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
+    const int8_t *dig = reinterpret_cast<const int8_t *>(xs_dig);
+    // digit weights of this lane's two D columns (2t, 2t + 1): digits 0..3 live in columns 0..3, columns 4..7 are zero planes
+    const float w0 = t == 0 ? 0.015625f : (t == 1 ? 9.5367431640625e-07f : 0.f);            // 2^-6, 2^-20
+    const float w1 = t == 0 ? 1.220703125e-04f : (t == 1 ? 7.450580596923828e-09f : 0.f);   // 2^-13, 2^-27
+    for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
+        float acc[NM][2];
+#pragma unroll
+        for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
+        for (uint32_t seg = 0; seg < nseg; seg++) {
+            // B fragments (digits) of this warp's two blocks: plane g (g < 4), 8 bytes at 8t
+            uint2 bd[2];
+            float sx[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t b = seg * (RQ_SEGK / 32) + warp * 2 + j;
+                bd[j] = g < 4 ? *reinterpret_cast<const uint2 *>(dig + (b * 4 + g) * 32 + t * 8) : make_uint2(0u, 0u);
+                sx[j] = xsc[b];
+            }
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase);
+                const uint8_t *sl = ring + (size_t)pos.slot * RQ_SLOT;
+                uint2 qa[2], qb[2];
+                float da[2], db[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint32_t bl = warp * 2 + j;   // block inside the slot
+                    qa[j] = *reinterpret_cast<const uint2 *>(sl + g * RQ_SEGK + bl * 32 + t * 8);          // row g,     8 int8
+                    qb[j] = *reinterpret_cast<const uint2 *>(sl + (g + 8) * RQ_SEGK + bl * 32 + t * 8);    // row g + 8
+                    da[j] = *reinterpret_cast<const float *>(sl + RQ_QBYTES + (g * (RQ_SEGK / 32) + bl) * 4);
+                    db[j] = *reinterpret_cast<const float *>(sl + RQ_QBYTES + ((g + 8) * (RQ_SEGK / 32) + bl) * 4);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int c[4];
+                    mma_s8(c, qa[j].x, qb[j].x, qa[j].y, qb[j].y, bd[j].x, bd[j].y);
+                    float va = fmaf((float)c[1], w1, __fmul_rn((float)c[0], w0));   // row g:     this lane's two digit columns
+                    float vb = fmaf((float)c[3], w1, __fmul_rn((float)c[2], w0));   // row g + 8
+                    va += __shfl_xor_sync(0xffffffffu, va, 1);                       // digits 0,1 (t = 0) + digits 2,3 (t = 1)
+                    vb += __shfl_xor_sync(0xffffffffu, vb, 1);
+                    acc[m][0] = fmaf(va, __fmul_rn(da[j], sx[j]), acc[m][0]);
+                    acc[m][1] = fmaf(vb, __fmul_rn(db[j], sx[j]), acc[m][1]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh.empty[pos.slot]));
+                pos.next(n_slots);
+            }
+        }
+        // ---- combine the 16 warps' K-slices of this tile (lanes t == 0 hold rows g and g + 8)
+        if (t == 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                sh.part[m][warp][g] = acc[m][0];
+                sh.part[m][warp][g + 8] = acc[m][1];
+            }
+        }
+        ccsync();
+        if (threadIdx.x < RQ_ROWS) {
+            const uint32_t row = tile + threadIdx.x;
+            float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < RQ_CWARPS; wv++) {
+                s1 += sh.part[0][wv][threadIdx.x];
+                if (NM == 2) s3 += sh.part[NM - 1][wv][threadIdx.x];
+            }
+            if (row < r1) {
+                float v;
+                if (NM == 2) v = __fmul_rn(silu_ref(s1), s3);
+                else if (EPI == 1) v = __fadd_rn(s1, __ldcg(res + row));
+                else v = s1;
+                out[row] = v;
+            }
+        }
+        ccsync();   // part[] is reused by the next tile
+    }
+}
+
+// ---- activation vector of a phase -> shared memory -----------------------------------------------------------
+// y = w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
+__device__ __forceinline__ void fill_norm(float *xs, const float *x, const float *w, uint32_t K, RQShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    double acc = 0.0;
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) {
+        const float4 v = ldcg4(x + (size_t)f * 4);
+        x4[f] = v;
+        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
+        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.red[warp] = acc;
+    ccsync();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RQ_CWARPS; i++) t += sh.red[i];
+    const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) {
+        const float4 v = x4[f];
+        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + f);
+        x4[f] = make_float4(__fmul_rn(ww.x, __fmul_rn(v.x, sc)), __fmul_rn(ww.y, __fmul_rn(v.y, sc)),
+                            __fmul_rn(ww.z, __fmul_rn(v.z, sc)), __fmul_rn(ww.w, __fmul_rn(v.w, sc)));
+    }
+    ccsync();   // also orders sh.red against its next use
+}
+__device__ __forceinline__ void fill_plain(float *xs, const float *x, uint32_t K) {
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) x4[f] = ldcg4(x + (size_t)f * 4);
+    ccsync();
+}
+// merge of the attention splits (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
+template <int HD>
+__device__ __forceinline__ void fill_merge(float *xs, const RQParams &p, RQShared &sh) {
+    const uint32_t S = p.splits, items = p.heads * S;
+    for (uint32_t i = threadIdx.x; i < items; i += RQ_CTHREADS) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
+        sh.mrg_m[i] = ml.x;
+        sh.mrg_l[i] = ml.y;
+    }
+    ccsync();
+    for (uint32_t h = threadIdx.x; h < p.heads; h += RQ_CTHREADS) {
+        float M = -INFINITY;
+        for (uint32_t s = 0; s < S; s++) M = fmaxf(M, sh.mrg_m[h * S + s]);
+        float Lsum = 0.f;
+        for (uint32_t s = 0; s < S; s++) {
+            const float l = sh.mrg_l[h * S + s];
+            float wgt = 0.f;
+            if (l > 0.f) {
+                wgt = expf(__fsub_rn(sh.mrg_m[h * S + s], M));
+                Lsum = fmaf(l, wgt, Lsum);
+            }
+            sh.mrg_w[h * S + s] = wgt;
+        }
+        sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
+    }
+    ccsync();
+    float4 *x4 = reinterpret_cast<float4 *>(xs);
+    constexpr int MB = 12;
+    for (uint32_t f = threadIdx.x; f < p.dim / 4; f += RQ_CTHREADS) {
+        const uint32_t e = f * 4, h = e / HD, d = e % HD;
+        const float *po = p.part_o + (size_t)h * S * HD + d;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t s0 = 0; s0 < S; s0 += MB) {
+            float4 pv[MB];
+#pragma unroll
+            for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < MB; u++) {
+                if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
+                    const float wgt = sh.mrg_w[h * S + s0 + u];
+                    o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
+                    o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+                }
+            }
+        }
+        const float inv = sh.mrg_inv[h];
+        x4[f] = make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv));
+    }
+    ccsync();
+}
+
+// ---- attention phase: identical to kernels_mega.cu::attention_phase (items (head, split), two per CTA at a time)
+template <int HD>
+__device__ __forceinline__ void attention_phase(const RQParams &p, const MegaLayerHost &L, uint32_t past, RQShared &sh, float *scores_all) {
+    constexpr int LANES = HD / 4;
+    constexpr int HW = RQ_CWARPS / 2;
+    constexpr int KG = RQ_HALF / LANES;
+    constexpr int AU = 8;
+    const int half = threadIdx.x / RQ_HALF, ht = threadIdx.x % RQ_HALF;
+    const int hwarp = ht >> 5, lane = threadIdx.x & 31;
+    const uint32_t dim = p.dim, S = p.splits, Tn = past + 1;
+    const float scale = (float)(1.0 / sqrt((double)HD));  // f32(1/sqrt(dim/heads)), llama.go:306
+    const uint32_t chunk = min((Tn + S - 1) / S, p.chunk_cap);
+    const uint32_t items = p.heads * S;
+    float *scores = scores_all + (size_t)half * p.chunk_cap;
+    float4 *pv = sh.pv + half * RQ_HALF;
+    const uint32_t kg = ht / LANES, dl = ht % LANES;
+    for (uint32_t item = blockIdx.x * 2 + half; item < items; item += gridDim.x * 2) {
+        const uint32_t h = item / S, sp = item % S;
+        const uint32_t t0 = min(sp * chunk, Tn), t1 = min(t0 + chunk, Tn), nk = t1 - t0;
+        float *Kh = L.Kc + (size_t)h * HD;
+        float *Vh = L.Vc + (size_t)h * HD;
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < LANES) {
+            const float4 qr = ldcg4(p.qkv + (size_t)h * HD + lane * 4);
+            const double c0 = sh.rope_cs[lane * 2][0], s0 = sh.rope_cs[lane * 2][1];
+            const double c1 = sh.rope_cs[lane * 2 + 1][0], s1 = sh.rope_cs[lane * 2 + 1][1];
+            qv.x = (float)(__dsub_rn(__dmul_rn((double)qr.x, c0), __dmul_rn((double)qr.y, s0)));
+            qv.y = (float)(__dadd_rn(__dmul_rn((double)qr.x, s0), __dmul_rn((double)qr.y, c0)));
+            qv.z = (float)(__dsub_rn(__dmul_rn((double)qr.z, c1), __dmul_rn((double)qr.w, s1)));
+            qv.w = (float)(__dadd_rn(__dmul_rn((double)qr.z, s1), __dmul_rn((double)qr.w, c1)));
+            if (hwarp == 0 && past >= t0 && past < t1) {
+                const float4 kr = ldcg4(p.qkv + dim + (size_t)h * HD + lane * 4);
+                float4 ko;
+                ko.x = (float)(__dsub_rn(__dmul_rn((double)kr.x, c0), __dmul_rn((double)kr.y, s0)));
+                ko.y = (float)(__dadd_rn(__dmul_rn((double)kr.x, s0), __dmul_rn((double)kr.y, c0)));
+                ko.z = (float)(__dsub_rn(__dmul_rn((double)kr.z, c1), __dmul_rn((double)kr.w, s1)));
+                ko.w = (float)(__dadd_rn(__dmul_rn((double)kr.z, s1), __dmul_rn((double)kr.w, c1)));
+                *reinterpret_cast<float4 *>(Kh + (size_t)past * dim + lane * 4) = ko;
+                *reinterpret_cast<float4 *>(Vh + (size_t)past * dim + lane * 4) = ldcg4(p.qkv + 2 * dim + (size_t)h * HD + lane * 4);
+            }
+        }
+        hsync(half);
+        for (uint32_t i = hwarp; i < nk; i += HW * AU) {
+            float4 kk[AU];
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t ii = i + u * HW;
+                kk[u] = (ii < nk && lane < LANES) ? ldcg4(Kh + (size_t)(t0 + ii) * dim + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t ii = i + u * HW;
+                float dd = kk[u].x * qv.x;
+                dd = fmaf(kk[u].y, qv.y, dd); dd = fmaf(kk[u].z, qv.z, dd); dd = fmaf(kk[u].w, qv.w, dd);
+                dd = warp_sum(dd);
+                if (lane == 0 && ii < nk) scores[ii] = __fmul_rn(dd, scale);
+            }
+        }
+        float4 vf[AU];
+#pragma unroll
+        for (int u = 0; u < AU; u++) {
+            const uint32_t key = kg + u * KG;
+            vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        hsync(half);
+        float m = -INFINITY;
+        for (uint32_t i = ht; i < nk; i += RQ_HALF) m = fmaxf(m, scores[i]);
+        m = warp_max(m);
+        if (lane == 0) sh.fred[half][hwarp] = m;
+        hsync(half);
+        if (ht == 0) {
+            float tt = sh.fred[half][0];
+            for (int i = 1; i < HW; i++) tt = fmaxf(tt, sh.fred[half][i]);
+            sh.hbcast[half] = tt;
+        }
+        hsync(half);
+        m = sh.hbcast[half];
+        float l = 0.f;
+        for (uint32_t i = ht; i < nk; i += RQ_HALF) {
+            float e = (float)exp((double)__fsub_rn(scores[i], m));
+            scores[i] = e;
+            l += e;
+        }
+        l = warp_sum(l);
+        hsync(half);
+        if (lane == 0) sh.fred[half][hwarp] = l;
+        hsync(half);
+        if (ht == 0) {
+            float tt = 0.f;
+            for (int i = 0; i < HW; i++) tt += sh.fred[half][i];
+            p.part_ml[((size_t)h * S + sp) * 2 + 0] = m;
+            p.part_ml[((size_t)h * S + sp) * 2 + 1] = tt;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t base = 0; base < nk; base += KG * AU) {
+            if (base) {
+#pragma unroll
+                for (int u = 0; u < AU; u++) {
+                    const uint32_t key = base + kg + u * KG;
+                    vf[u] = key < nk ? ldcg4(Vh + (size_t)(t0 + key) * dim + dl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AU; u++) {
+                const uint32_t key = base + kg + u * KG;
+                if (key < nk) {
+                    const float sc = scores[key];
+                    acc.x = fmaf(vf[u].x, sc, acc.x); acc.y = fmaf(vf[u].y, sc, acc.y);
+                    acc.z = fmaf(vf[u].z, sc, acc.z); acc.w = fmaf(vf[u].w, sc, acc.w);
+                }
+            }
+        }
+        pv[ht] = acc;
+        hsync(half);
+        if (ht < HD) {
+            const float *pvf = reinterpret_cast<const float *>(pv);
+            float r = 0.f;
+            for (int i = 0; i < KG; i++) r += pvf[i * HD + ht];
+            p.part_o[((size_t)h * S + sp) * HD + ht] = r;
+        }
+        hsync(half);
+    }
+}
+
+// dynamic shared memory: [ring: n_slots x RQ_SLOT][xs: kpad floats, digit planes in place][xsc: kpad/32 floats][scores][RQShared]
+template <int HD>
+__global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQParams p, const __grid_constant__ RQMaps maps) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots, kpad = p.kpad;
+    uint8_t *ring = smem_raw;
+    float *xs = reinterpret_cast<float *>(smem_raw + (size_t)n_slots * RQ_SLOT);
+    float *xsc = xs + kpad;
+    float *scores = xsc + kpad / 32;
+    RQShared &sh = *reinterpret_cast<RQShared *>(scores + 2 * (size_t)((p.chunk_cap + 3) & ~3u));
+    const bool producer = threadIdx.x >= RQ_CTHREADS;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < n_slots; s++) {
+            mbar_init(smem_u32(&sh.full[s]), 1);
+            mbar_init(smem_u32(&sh.empty[s]), RQ_CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t past = p.state[0];
+    if (threadIdx.x < HD / 2) {  // RoPE table of this token's position (f64 pow/cos/sin, ml.go:2307-2310)
+        double sn, cs;
+        sincos((double)past * pow(10000.0, ((double)(-(int)(2 * threadIdx.x))) / (double)HD), &sn, &cs);
+        sh.rope_cs[threadIdx.x][0] = cs;
+        sh.rope_cs[threadIdx.x][1] = sn;
+    }
+    __syncthreads();   // the only CTA-wide barrier
+
+    RingPos pos;
+    pos.slot = 0; pos.phase = 0;
+    uint32_t ph = 0;   // MulMat phase counter (rotates the tile assignment; identical on both sides)
+    if (producer) {
+        if (threadIdx.x != RQ_CTHREADS) return;   // one thread drives the copy engine
+        const uint32_t ring_base = smem_u32(ring);
+        for (uint32_t li = 0; li < p.n_layers; li++) {
+            produce<1>(&maps.q_wqkv, &maps.d_wqkv, nullptr, nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.q_wo, &maps.d_wo, nullptr, nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
+            produce<2>(&maps.q_w1, &maps.d_w1, &maps.q_w3, &maps.d_w3, (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.q_w2, &maps.d_w2, nullptr, nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
+        }
+        if (p.final_norm) produce<1>(&maps.q_out, &maps.d_out, nullptr, nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
+        return;
+    }
+    unsigned target = 0;
+    const float *xin = p.x;
+    if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
+    unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    auto stamp = [&](uint32_t li, int i) {
+        if (tr) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            tr[li * 13 + i] = tt;
+        }
+    };
+    for (uint32_t li = 0; li < p.n_layers; li++) {
+        const MegaLayerHost L = p.layers[li];
+        stamp(li, 0);
+        // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
+        fill_norm(xs, xin, L.attention_norm, dim, sh);
+        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        stamp(li, 1);
+        consume<1, 0>(dim, 3 * dim, xs, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots);
+        stamp(li, 2);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 3);
+        // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
+        attention_phase<HD>(p, L, past, sh, scores);
+        stamp(li, 4);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 5);
+        // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
+        fill_merge<HD>(xs, p, sh);
+        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        consume<1, 1>(dim, dim, xs, xsc, p.y, xin, ph, pos, ring, sh, n_slots);
+        stamp(li, 6);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 7);
+        // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
+        fill_norm(xs, p.y, L.ffn_norm, dim, sh);
+        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        stamp(li, 8);
+        consume<2, 0>(dim, ff, xs, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots);
+        stamp(li, 9);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 10);
+        // ---- P5: w2 + residual (llama.go:363-366)
+        fill_plain(xs, p.act, ff);
+        make_digits(xs, ff, (ff + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        consume<1, 1>(ff, dim, xs, xsc, p.x, p.y, ph, pos, ring, sh, n_slots);
+        stamp(li, 11);
+        grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 12);
+        xin = p.x;
+    }
+    if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
+        fill_norm(xs, xin, p.final_norm, dim, sh);
+        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        consume<1, 0>(dim, p.vocab, xs, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots);
+    }
+}
+
+template <int HD>
+static cudaError_t launch(const RQParams &p, const RQMaps &maps, size_t smem, cudaStream_t st) {
+    static bool attr[64] = {};  // function attributes are per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        e = cudaFuncSetAttribute(decode_ring_q8_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(RQ_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_ring_q8_kernel<HD>, p, maps);
+}
+
+static uint32_t q8_splits(uint32_t heads) {
+    uint32_t s = (2 * kNumSMs) / heads;
+    return s < 1 ? 1 : (s > 32 ? 32 : s);
+}
+static uint32_t q8_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx, uint32_t *kpad_out, size_t *smem_out) {
+    const uint32_t S = q8_splits(heads), chunk_cap = (ctx + S - 1) / S;
+    const uint32_t kmax = dim > ff ? dim : ff, kpad = (kmax + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK;
+    const size_t fixed = (size_t)kpad * 4 + (size_t)kpad / 32 * 4 + 2 * (size_t)((chunk_cap + 3) & ~3u) * 4 + sizeof(RQShared) + 128;
+    const size_t cap = 227 * 1024;
+    if (kpad_out) *kpad_out = kpad;
+    if (fixed + 3 * (size_t)RQ_SLOT > cap) return 0;
+    uint32_t n = (uint32_t)((cap - fixed) / RQ_SLOT);
+    if (n > RQ_MAX_SLOTS) n = RQ_MAX_SLOTS;
+    if (smem_out) *smem_out = fixed - 128 + (size_t)n * RQ_SLOT;
+    return n;
+}
+
+// ---- interleaved planes (kernels_q8.cu) -> the row-major planes this kernel streams ---------------------------------
+__global__ void q8_to_row_major_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, int8_t *__restrict__ q_rm,
+                                       float *__restrict__ d_rm, uint32_t rows, uint32_t K) {
+    const size_t n4 = (size_t)rows * (K / 4), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint32_t r = (uint32_t)(i / (K / 4)), k4 = (uint32_t)(i % (K / 4));
+        // interleaved: ((r / 4) * (K / 4) + k4) * 16 + (r % 4) * 4 bytes
+        reinterpret_cast<uint32_t *>(q_rm)[i] = *reinterpret_cast<const uint32_t *>(q + ((size_t)(r >> 2) * (K >> 2) + k4) * 16 + (r & 3) * 4);
+        if ((k4 & 7) == 0) d_rm[(size_t)r * (K / 32) + (k4 >> 3)] = d[((size_t)(r >> 2) * (K >> 5) + (k4 >> 3)) * 4 + (r & 3)];
+    }
+}
+
+}  // namespace
+
+void q8_to_row_major(const int8_t *q, const float *d, int8_t *q_rm, float *d_rm, uint32_t rows, uint32_t K, cudaStream_t st) {
+    LB_CHECK(K % 32 == 0 && rows % 4 == 0, "q8_to_row_major: K must be a multiple of 32 and the row count a multiple of 4");
+    if (!rows) return;
+    q8_to_row_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, q_rm, d_rm, rows, K);
+    LB_LAUNCH_CHECK();
+}
+
+bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
+    if (heads == 0 || dim % heads || heads > (uint32_t)RQ_MAX_HEADS) return false;
+    const uint32_t hd = dim / heads;
+    if (hd != 128 && hd != 64 && hd != 32) return false;
+    if (dim % 32 || ff % 32 || dim < 256) return false;
+    (void)vocab;
+    return q8_plan(dim, ff, heads, ctx, nullptr, nullptr) >= 3;
+}
+
+static CUtensorMap q8_map(const void *base, CUtensorMapDataType dt, uint64_t inner, uint64_t rows, uint64_t layers, uint64_t layer_stride_elems,
+                          uint32_t box_inner) {
+    typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                            const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static PFN fn = nullptr;
+    if (!fn) {
+        void *pfn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        LB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qr));
+        LB_CHECK(pfn != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<PFN>(pfn);
+    }
+    CUtensorMap m;
+    cuuint64_t dims[3] = {inner, rows, layers};
+    cuuint64_t strides[2] = {inner * 4, (layers > 1 ? layer_stride_elems : inner * rows) * 4};
+    cuuint32_t box[3] = {box_inner, RQ_ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+size_t ring_q8_maps_bytes() { return sizeof(RQMaps); }
+
+// q_rm / d_rm: row-major planes of layer 0's matrices in the order wqkv, wo, w1, w3, w2 (+ output); q/d layer strides in bytes / floats
+void ring_q8_make_maps(const RingQ8Planes &pl, uint32_t n_layers, uint32_t dim, uint32_t ff, uint32_t vocab, void *maps_out) {
+    LB_CHECK(maps_out && n_layers >= 1, "ring_q8_make_maps: nil argument");
+    LB_CHECK(pl.q_layer_stride % 4 == 0, "ring_q8_make_maps: q layer stride must be a multiple of 4 bytes");
+    RQMaps m;
+    auto qm = [&](const int8_t *q, uint64_t K, uint64_t rows, bool per_layer) {
+        return q8_map(q, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / 4, rows, per_layer ? n_layers : 1, pl.q_layer_stride / 4, RQ_SEGK / 4);
+    };
+    auto dm = [&](const float *d, uint64_t K, uint64_t rows, bool per_layer) {
+        return q8_map(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, K / 32, rows, per_layer ? n_layers : 1, pl.d_layer_stride, RQ_SEGK / 32);
+    };
+    m.q_wqkv = qm(pl.q[0], dim, 3ull * dim, true); m.d_wqkv = dm(pl.d[0], dim, 3ull * dim, true);
+    m.q_wo = qm(pl.q[1], dim, dim, true);          m.d_wo = dm(pl.d[1], dim, dim, true);
+    m.q_w1 = qm(pl.q[2], dim, ff, true);           m.d_w1 = dm(pl.d[2], dim, ff, true);
+    m.q_w3 = qm(pl.q[3], dim, ff, true);           m.d_w3 = dm(pl.d[3], dim, ff, true);
+    m.q_w2 = qm(pl.q[4], ff, dim, true);           m.d_w2 = dm(pl.d[4], ff, dim, true);
+    if (pl.q[5]) { m.q_out = qm(pl.q[5], dim, vocab, false); m.d_out = dm(pl.d[5], dim, vocab, false); }
+    else { m.q_out = m.q_wo; m.d_out = m.d_wo; }
+    memcpy(maps_out, &m, sizeof(RQMaps));
+}
+
+void decode_ring_q8(const MegaParamsHost &h, const void *tmaps, cudaStream_t st) {
+    LB_CHECK(decode_ring_q8_supported(h.dim, h.ff, h.heads, h.vocab, h.ctx), "decode_ring_q8: unsupported shape");
+    LB_CHECK(tmaps != nullptr, "decode_ring_q8: tensor maps missing (ring_q8_make_maps)");
+    RQParams p;
+    p.layers = h.layers_dev;
+    p.n_layers = h.n_layers;
+    p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
+    p.final_norm = h.final_norm;
+    p.x = h.x; p.y = h.y; p.qkv = h.qkv; p.attn = h.attn; p.act = h.act; p.logits = h.logits;
+    p.part_o = h.part_o; p.part_ml = h.part_ml; p.barrier = h.barrier;
+    p.dim = h.dim; p.ff = h.ff; p.heads = h.heads; p.vocab = h.vocab; p.ctx = h.ctx;
+    p.splits = q8_splits(h.heads);
+    p.chunk_cap = (h.ctx + p.splits - 1) / p.splits;
+    size_t smem = 0;
+    p.n_slots = q8_plan(h.dim, h.ff, h.heads, h.ctx, &p.kpad, &smem);
+    p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
+    const RQMaps &maps = *static_cast<const RQMaps *>(tmaps);
+    const uint32_t hd = h.dim / h.heads;
+    cudaError_t e = hd == 128 ? launch<128>(p, maps, smem, st) : hd == 64 ? launch<64>(p, maps, smem, st) : launch<32>(p, maps, smem, st);
+    LB_CUDA(e);
+    count_launch();
+}
+
+}  // namespace k
+}  // namespace lb

@@ -64,11 +64,16 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     if (q8()) {
         qslab = mem.dmalloc<int8_t>(qtotal);
         dslab = mem.dmalloc<float>(dtotal);
+        qslab_rm = mem.dmalloc<int8_t>(qtotal);
+        dslab_rm = mem.dmalloc<float>(dtotal);
     }
     auto fptr = [&](const MOff &o) { return q8() ? nullptr : slab + o.f; };
     auto qmat = [&](const MOff &o, size_t row_off_elems = 0) {
         Q8Mat m;
-        if (q8()) { m.q = qslab + o.q + row_off_elems; m.d = dslab + o.d + row_off_elems / 32; }
+        if (q8()) {
+            m.q = qslab + o.q + row_off_elems; m.d = dslab + o.d + row_off_elems / 32;
+            m.q_rm = qslab_rm + o.q + row_off_elems; m.d_rm = dslab_rm + o.d + row_off_elems / 32;
+        }
         return m;
     };
     const float sdd = (float)pow((double)d, -0.5), sf = (float)pow((double)ff, -0.5);
@@ -128,7 +133,10 @@ void Model::set_tensor(const std::string &name, int dtype, const void *host, siz
         LB_CUDA(cudaMemcpy(tmp16, host, nbytes, cudaMemcpyHostToDevice));
         k::f16_to_f32(static_cast<const uint16_t *>(tmp16), dst, e.nelem, 0);
     }
-    if (quant) k::quantize_q8(dst, e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+    if (quant) {
+        k::quantize_q8(dst, e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+        k::q8_to_row_major(e.q8.q, e.q8.d, e.q8.q_rm, e.q8.d_rm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+    }
     LB_CUDA(cudaDeviceSynchronize());
     if (tmp16) cudaFree(tmp16);
     if (tmp32) cudaFree(tmp32);
@@ -165,6 +173,7 @@ void Model::init_random(uint64_t seed) {
         if (e.q8.q) {
             k::init_random(static_cast<float *>(tmp), e.nelem, seed, e.tid, e.mean, sscale, 0);
             k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+            k::q8_to_row_major(e.q8.q, e.q8.d, e.q8.q_rm, e.q8.d_rm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
         } else {
             k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
         }
@@ -216,6 +225,10 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     const bool ring_ok = getenv("LB_NO_RING") == nullptr && k::decode_ring_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
     use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && (mega_ok || ring_ok);
     use_ring = use_mega && ring_ok;   // TMA-ring megakernel (kernels_ring.cu); LB_NO_RING=1 keeps the register-fed one
+    // Q8_0 weights: TMA ring + int8 tensor cores (kernels_ring_q8.cu); LB_NO_RING_Q8=1 keeps the per-op kernels
+    use_ring_q8 = m->q8() && getenv("LB_NO_MEGA") == nullptr && getenv("LB_NO_RING_Q8") == nullptr &&
+                  k::decode_ring_q8_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
+    if (use_ring_q8) use_mega = true;
     if (use_mega) {
         std::vector<k::MegaLayerHost> ml(nl);
         for (size_t i = 0; i < nl; i++) {
@@ -228,6 +241,22 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
         mega_barrier = mem.dmalloc<unsigned>(2 + 4 * nl);  // grid barrier + per-phase ticket counters
         if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13 + 5 * 148);
+        if (use_ring_q8) {
+            const Layer &L0 = m->layers[0];
+            k::RingQ8Planes pl = {};
+            const Q8Mat *mats[5] = {&L0.wqkv8, &L0.wo8, &L0.w18, &L0.w38, &L0.w28};
+            for (int i = 0; i < 5; i++) { pl.q[i] = mats[i]->q_rm; pl.d[i] = mats[i]->d_rm; }
+            pl.q[5] = m->has_head() ? m->output8.q_rm : nullptr;
+            pl.d[5] = m->has_head() ? m->output8.d_rm : nullptr;
+            if (nl > 1) {
+                pl.q_layer_stride = (uint64_t)(m->layers[1].wqkv8.q_rm - L0.wqkv8.q_rm);
+                pl.d_layer_stride = (uint64_t)(m->layers[1].wqkv8.d_rm - L0.wqkv8.d_rm);
+            }
+            q8_tmaps.resize(k::ring_q8_maps_bytes() + 64);
+            void *al = reinterpret_cast<void *>(((uintptr_t)q8_tmaps.data() + 63) & ~(uintptr_t)63);
+            k::ring_q8_make_maps(pl, (uint32_t)nl, hp.dim, hp.ff(), hp.vocab, al);
+            q8_tmaps_ptr = al;
+        }
     }
 }
 
@@ -289,7 +318,8 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.barrier = mega_barrier;
         mp.trace = mega_trace;
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
-        if (use_ring) k::decode_ring(mp, st);
+        if (use_ring_q8) k::decode_ring_q8(mp, q8_tmaps_ptr, st);
+        else if (use_ring) k::decode_ring(mp, st);
         else k::decode_mega(mp, st);
         if (hidden_out && hidden_out != x)
             LB_CUDA(cudaMemcpyAsync(hidden_out, x, (size_t)d * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -19,9 +19,12 @@ struct HParams {  // llama.go:149-158
     uint32_t head_dim() const { return dim / heads; }
 };
 
-struct Q8Mat {  // Q8_0 planes of one matrix (kernels_q8.cu): q[M][K] int8, d[M][K/32] float
+struct Q8Mat {  // Q8_0 planes of one matrix: 4-row-interleaved (kernels_q8.cu: per-op GEMV, tcgen05 GEMM) and a
+                // row-major copy q_rm[M][K] int8, d_rm[M][K/32] float streamed by the decode ring (kernels_ring_q8.cu)
     int8_t *q = nullptr;
     float *d = nullptr;
+    int8_t *q_rm = nullptr;
+    float *d_rm = nullptr;
 };
 
 struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] matrix
@@ -49,6 +52,8 @@ struct Model {
     Q8Mat output8;
     int8_t *qslab = nullptr;  // Q8_0: int8 plane of every MulMat matrix of the stage
     float *dslab = nullptr;   //       and the per-block scales
+    int8_t *qslab_rm = nullptr;  // the same planes row-major (decode ring)
+    float *dslab_rm = nullptr;
     std::vector<Layer> layers;  // index = global layer - layer_begin
     bool q8() const { return weight_type == 16; }
 
@@ -81,6 +86,9 @@ struct Context {
     void *mega_trace = nullptr;        // LB_MEGA_TRACE=1: per-phase globaltimer stamps of CTA 0
     bool use_mega = false;             // single-token forward = one persistent cooperative kernel
     bool use_ring = false;             // ... the TMA-ring variant (kernels_ring.cu) instead of the register-fed one
+    bool use_ring_q8 = false;          // Q8_0 weights: TMA ring + int8 tensor cores (kernels_ring_q8.cu)
+    std::vector<uint8_t> q8_tmaps;     // its tensor maps (k::ring_q8_make_maps)
+    const void *q8_tmaps_ptr = nullptr;
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
