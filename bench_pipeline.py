@@ -47,6 +47,7 @@ def pipeline_measure(args, hp, model_key, ctx_size, K, W, env):
     rs = np.random.RandomState(0)
     prompt = rs.randint(3, hp.vocab, size=(S, PROMPT_LEN)).astype(np.uint32)
     gen = rs.randint(3, hp.vocab, size=(S, 2 * W + 2 * K)).astype(np.uint32)
+    p2p = stage.enable_p2p(dist)                # fused NVLink hand-off in the stage kernels (else NCCL send/recv)
     stage.prefill(prompt, 0)                    # setup, untimed
     t_setup = time.time() - t_setup
 
@@ -116,7 +117,11 @@ def pipeline_measure(args, hp, model_key, ctx_size, K, W, env):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LLaMA-%s FP32 decode, context %d, %d-token prompts prefilled, %d sequences in flight"
                                % (model_key.upper(), ctx_size, PROMPT_LEN, S),
-                   "parallelism": "pp%d (layer-sharded, %d layers/GPU, NCCL send/recv of the residual)" % (world, hp.layers // world),
+                   "parallelism": "pp%d (layer-sharded, %d layers/GPU, %s)" % (
+                       world, hp.layers // world,
+                       "residual handed to the next stage by the stage kernel itself: NVLink peer stores + flag (CUDA IPC), NCCL for the prefill"
+                       if p2p else "NCCL send/recv of the residual"),
+                   "handoff": "p2p-fused" if p2p else "nccl",
                    "sequences_in_flight": S, "tokens_per_step": S, "weights": "random-init (device RNG, seed 0)",
                    "kv_cache": "fp32 in HBM", "l2": "inputs>L2", "setup_s": round(t_setup, 1),
                    "note": "a single sequence gains nothing from layer sharding (dependency chain); "

@@ -166,6 +166,15 @@ LB_API int  lb_comm_unique_id(void *out128);                 /* rank 0: ncclGetU
 LB_API int  lb_comm_init(const void *id128, int rank, int world, int device);   /* ncclCommInitRank */
 LB_API void lb_comm_destroy(void);
 LB_API int  lb_nccl_version(void);
+/* Fused stage hand-off over NVLink peer memory (one process per GPU): instead of ncclRecv / stage kernels / ncclSend per
+ * (step, sequence) slot, the stage's persistent kernel stores the residual stream straight into the next stage's buffer
+ * (CUDA IPC mapping) and raises a flag there, which the next stage's kernel waits for while it already streams its weights.
+ * export: handles_out receives n x 128 bytes for this stage's n contexts; every rank exchanges them (any transport);
+ * import: the bytes of the downstream stage (NULL on the last stage) and of the upstream stage (NULL on the first), before
+ * the first lb_pipeline_decode.  Without import, lb_pipeline_decode uses NCCL send/recv as before; prefill always does. */
+LB_API int lb_pipeline_p2p_export(lb_context **ctxs, uint32_t n, void *handles_out);
+LB_API int lb_pipeline_p2p_import(lb_context **ctxs, uint32_t n, const void *downstream_handles, const void *upstream_handles);
+LB_API int lb_pipeline_p2p_disable(lb_context **ctxs, uint32_t n);   /* back to NCCL (e.g. another rank's import failed) */
 /* Pipelined steady-state decode of `n_seq` in-flight sequences ("pods", server.go:84-106) for `steps`
  * tokens each, starting at position `past`: per (step, sequence) this rank receives the residual
  * [dim] from rank-1, runs its layers, sends it to rank+1; all on one stream, no host sync.  tokens

@@ -73,6 +73,9 @@ _SIGS = {
     "lb_nccl_version": (C.c_int, []),
     "lb_pipeline_decode": (C.c_int, [C.POINTER(_vp), C.c_uint32, _u32p, C.c_uint32, C.c_uint32, _f32p]),
     "lb_pipeline_prefill": (C.c_int, [C.POINTER(_vp), C.c_uint32, _u32p, C.c_uint32, C.c_uint32]),
+    "lb_pipeline_p2p_export": (C.c_int, [C.POINTER(_vp), C.c_uint32, _vp]),
+    "lb_pipeline_p2p_import": (C.c_int, [C.POINTER(_vp), C.c_uint32, C.c_char_p, C.c_char_p]),
+    "lb_pipeline_p2p_disable": (C.c_int, [C.POINTER(_vp), C.c_uint32]),
     "lb_ml_new_context": (_vp, [C.c_int]),
     "lb_ml_release_context": (None, [_vp]),
     "lb_new_tensor": (_vp, [_vp, C.c_int] + [C.c_uint32] * 5 + [_f32p]),

@@ -234,6 +234,24 @@ int lb_pipeline_decode(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens
                if (ms_out) *ms_out = ms);
 }
 
+int lb_pipeline_p2p_export(lb_context **ctxs, uint32_t n_seq, void *handles_out) {
+    LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1 && handles_out, "nil argument");
+               std::vector<llama::Context *> v(n_seq);
+               for (uint32_t i = 0; i < n_seq; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+               pipe::p2p_export(v.data(), n_seq, handles_out));
+}
+int lb_pipeline_p2p_import(lb_context **ctxs, uint32_t n_seq, const void *downstream_handles, const void *upstream_handles) {
+    LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1, "nil argument");
+               std::vector<llama::Context *> v(n_seq);
+               for (uint32_t i = 0; i < n_seq; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+               pipe::p2p_import(v.data(), n_seq, downstream_handles, upstream_handles));
+}
+int lb_pipeline_p2p_disable(lb_context **ctxs, uint32_t n_seq) {
+    LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1, "nil argument");
+               std::vector<llama::Context *> v(n_seq);
+               for (uint32_t i = 0; i < n_seq; i++) { LB_CHECK(ctxs[i], "nil context"); v[i] = ctxs[i]->c; }
+               pipe::p2p_disable(v.data(), n_seq));
+}
 int lb_pipeline_prefill(lb_context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past) {
     LB_TRY_INT(LB_CHECK(ctxs && n_seq >= 1, "nil argument");
                std::vector<llama::Context *> v(n_seq);

@@ -103,8 +103,8 @@ size_t sample_top_p_top_k_smem(uint32_t V, uint32_t top_k);
 void sample_top_p_top_k(const float *logits, uint32_t V, const uint32_t *last_n_dev, uint32_t n_last, uint32_t top_k, float top_p,
                         float temp, float penalty, uint64_t seed, uint32_t *out_ids, float *out_probs, uint32_t *out_n_token,
                         cudaStream_t st);
-// state[0] (= past) += dp; state[1] (= step) += ds
-void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st);
+// state[0] (= past) += dp; state[1] (= step) += ds; if seq != nullptr, *seq += 1 (pipeline hand-off step counter)
+void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st, uint32_t *seq = nullptr);
 
 // ---- persistent single-token megakernel (kernels_mega.cu) ----
 struct MegaLayerHost {  // one per layer, array lives in device memory
@@ -127,6 +127,15 @@ struct MegaParamsHost {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx;
     void *trace = nullptr;            // optional uint64[n_layers*13] phase time stamps (profiling aid)
+    // ---- fused stage hand-off over NVLink peer memory (pipeline stages, kernels_ring.cu only; all optional) ----
+    // flags = this context's {in_flag, ack, seq, -} in LOCAL device memory: the upstream stage's kernel stores the
+    // residual into this context's x and then in_flag = step number; the downstream stage stores ack = step number once
+    // it has consumed what this stage sent; seq = steps this context has completed (advanced with the state).
+    uint32_t *p2p_flags = nullptr;
+    bool p2p_wait_in = false;         // wait for in_flag >= seq + 1 before touching x (stage > 0)
+    float *p2p_x_out = nullptr;       // peer-mapped x of the downstream stage's context: the last phase writes the residual there
+    uint32_t *p2p_flag_out = nullptr; // peer-mapped flags of the downstream context (its in_flag is [0])
+    uint32_t *p2p_ack_out = nullptr;  // peer-mapped flags of the upstream context (its ack is [1])
 };
 bool decode_mega_supported(uint32_t dim, uint32_t ff, uint32_t heads);
 bool decode_mega_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab);

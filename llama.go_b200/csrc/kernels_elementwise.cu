@@ -415,13 +415,14 @@ void get_rows_indirect(const float *table, uint32_t nc, const uint32_t *tokens, 
     LB_CHECK((nc & 3) == 0, "get_rows_indirect: row length must be a multiple of 4");
     launch_pdl(get_rows_indirect_kernel, dim3(nr), dim3(256), 0, st, table, nc, tokens, step_dev, dst);
 }
-__global__ void advance_state_kernel(uint32_t *state, uint32_t dp, uint32_t ds) {
+__global__ void advance_state_kernel(uint32_t *state, uint32_t dp, uint32_t ds, uint32_t *seq) {
     pdl_wait();
     state[0] += dp;
     state[1] += ds;
+    if (seq) *seq += 1;
 }
-void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st) {
-    launch_pdl(advance_state_kernel, dim3(1), dim3(1), 0, st, state, dp, ds);
+void advance_state(uint32_t *state, uint32_t dp, uint32_t ds, cudaStream_t st, uint32_t *seq) {
+    launch_pdl(advance_state_kernel, dim3(1), dim3(1), 0, st, state, dp, ds, seq);
 }
 
 // ---- greedy sampler on the device: the reference's SampleTopPTopK at temp -> 0

@@ -91,10 +91,16 @@ struct RingParams {
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
     unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0
+    // fused stage hand-off over NVLink peer memory (see MegaParamsHost)
+    uint32_t *p2p_flags;          // local {in_flag, ack, seq}
+    uint32_t p2p_wait_in;
+    float *p2p_x_out;
+    uint32_t *p2p_flag_out, *p2p_ack_out;
 };
 
 struct RingShared {
     unsigned long long full[RG_MAX_SLOTS], empty[RG_MAX_SLOTS];
+    unsigned epoch[RG_MAX_SLOTS];   // q / n_slots of the slot's current occupant (written by the producer before it arms full[])
     double red[RG_CWARPS];
     double rope_cs[64][2];
     float fred[2][RG_CWARPS / 2];
@@ -103,12 +109,29 @@ struct RingShared {
     float mrg_m[RG_MAX_ITEMS], mrg_l[RG_MAX_ITEMS], mrg_w[RG_MAX_ITEMS], mrg_inv[RG_MAX_HEADS];
 };
 
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin (one thread) until *flag >= want; traps after ~10 s instead of hanging the GPU if the peer stage died
+__device__ __forceinline__ void p2p_wait(const unsigned *flag, unsigned want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u32(flag) < want) {
+        if (clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+
 // ---- grid barrier among the consumer threads of all CTAs (the producer warps never take part)
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, bool sys = false) {
     target += nctas;
     ccsync();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (sys) __threadfence_system();   // this CTA's stores to the peer GPU are ordered before the hand-off flag
+        else __threadfence();
         atomicAdd(bar, 1u);
         const long long t0 = clock64();
         while (ld_acquire_u32(bar) < target) {
@@ -145,6 +168,8 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
                 const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
                 const uint32_t fb = smem_u32(&sh.full[slot]);
                 mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // the consumer warp of slot q - n_slots released it
+                *reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) = q / n_slots;
+                __threadfence_block();
                 mbar_expect_tx(fb, len * 4);
                 bulk_g2s(ring_base + slot * RG_SLOT, (m == 0 ? W : W3) + (size_t)row * K + k0, len * 4, fb);
                 q++;
@@ -176,6 +201,15 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs,
 #pragma unroll
             for (int m = 0; m < NM; m++, q++) {
                 const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
+                // A warp owns whole rows, so its next slot can be SEVERAL ring wraps ahead of what the entry holds now, and
+                // an mbarrier parity only tells consecutive phases apart: first wait until the producer has installed this
+                // wrap in the entry (it does so only after the previous occupant was released), then for the bytes.
+                {
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) != q / n_slots) {
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    }
+                }
                 mbar_wait(smem_u32(&sh.full[slot]), ph);
                 const float4 *w4 = reinterpret_cast<const float4 *>(ring + (size_t)slot * RG_SLOT);
                 float s0 = acc[m][0], s1 = acc[m][1];
@@ -430,6 +464,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         for (uint32_t s = 0; s < n_slots; s++) {
             mbar_init(smem_u32(&sh.full[s]), 1);
             mbar_init(smem_u32(&sh.empty[s]), 1);
+            sh.epoch[s] = 0xFFFFFFFFu;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -459,6 +494,19 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     }
     // ================= consumers =================
     unsigned target = 0;
+    // Pipeline stage hand-off (multi-GPU layer sharding) fused into this kernel: the upstream stage's kernel
+    // stored the residual stream straight into this context's x over NVLink and then raised in_flag; the producer warp
+    // above is already streaming this stage's weights while we wait.  Before this launch may overwrite the downstream
+    // context's x (in its last phase) the downstream stage must have consumed the previous step: ack >= seq.
+    unsigned p2p_seq = 0;
+    if (p.p2p_flags) {
+        p2p_seq = p.p2p_flags[2];
+        if (threadIdx.x == 0) {
+            if (p.p2p_wait_in) p2p_wait(p.p2p_flags + 0, p2p_seq + 1);
+            if (p.p2p_x_out) p2p_wait(p.p2p_flags + 1, p2p_seq);
+        }
+        ccsync();
+    }
     const float *xin = p.x;
     if (p.tok_embeddings) xin = p.tok_embeddings + (size_t)p.tokens[p.state[1]] * dim;  // GetRows, llama.go:244
     unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
@@ -497,17 +545,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
-        // ---- P5: w2 + residual (llama.go:363-366)
+        // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
         fill_plain(xs, p.act, ff);
-        consume<1, 1>(ff, dim, xs, p.x, p.y, pos, ring, sh, n_slots);
+        consume<1, 1>(ff, dim, xs, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, ring, sh, n_slots);
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers);
         stamp(li, 12);
         xin = p.x;
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         fill_norm(xs, xin, p.final_norm, dim, sh);
         consume<1, 0>(dim, p.vocab, xs, p.logits, nullptr, pos, ring, sh, n_slots);
+    }
+    if (p.p2p_flags && blockIdx.x == 0 && threadIdx.x == 0) {
+        // every CTA passed the last grid barrier (system-scope fences below) after storing its rows of the residual
+        __threadfence_system();
+        if (p.p2p_flag_out) st_release_sys_u32(p.p2p_flag_out + 0, p2p_seq + 1);   // downstream: your input for step seq+1 is there
+        if (p.p2p_ack_out) st_release_sys_u32(p.p2p_ack_out + 1, p2p_seq + 1);     // upstream: I am done with what you sent for step seq+1
     }
 }
 
@@ -577,6 +631,8 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
         if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
     }
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
+    p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
     const uint32_t hd = h.dim / h.heads;
     cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);

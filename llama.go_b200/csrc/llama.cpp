@@ -265,6 +265,9 @@ Context::~Context() {
     if (stream) cudaStreamSynchronize(stream);
     if (decode_graph) cudaGraphExecDestroy(decode_graph);
     if (stage_graph) cudaGraphExecDestroy(stage_graph);
+    if (p2p_x_out) cudaIpcCloseMemHandle(p2p_x_out);
+    if (p2p_flag_out) cudaIpcCloseMemHandle(p2p_flag_out);
+    if (p2p_ack_out) cudaIpcCloseMemHandle(p2p_ack_out);
     // buffers, events and the stream are released by `mem`
 }
 
@@ -317,6 +320,11 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.tickets = reinterpret_cast<unsigned *>(mp.part_ml + (size_t)H * 32 * 2);
         mp.barrier = mega_barrier;
         mp.trace = mega_trace;
+        if (p2p_on && use_ring) {
+            mp.p2p_flags = p2p_flags;
+            mp.p2p_wait_in = !model->has_embedding();
+            mp.p2p_x_out = p2p_x_out; mp.p2p_flag_out = p2p_flag_out; mp.p2p_ack_out = p2p_ack_out;
+        }
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
         if (use_ring_q8) k::decode_ring_q8(mp, q8_tmaps_ptr, st);
         else if (use_ring) k::decode_ring(mp, st);
@@ -408,9 +416,12 @@ void Context::ensure_stage_graph(cudaStream_t st) {
         cudaGraph_t g = nullptr;
         LB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
+            p2p_on = p2p_ready;   // the captured kernel waits for / raises the peer flags; the eager warm-up above did not
             forward(1, true, false, x, nullptr);
-            k::advance_state(state_dev, 1, 1, st);
+            k::advance_state(state_dev, 1, 1, st, p2p_on ? p2p_flags + 2 : nullptr);
+            p2p_on = false;
         } catch (...) {
+            p2p_on = false;
             cudaStreamEndCapture(st, &g);
             if (g) cudaGraphDestroy(g);
             throw;

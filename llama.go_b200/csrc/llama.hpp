@@ -103,6 +103,13 @@ struct Context {
     float *logits_host = nullptr;    // pinned staging [vocab]
     cudaGraphExec_t decode_graph = nullptr;
     cudaGraphExec_t stage_graph = nullptr;   // this stage's layers for one token (pipeline mode)
+    // fused stage hand-off over NVLink peer memory (pipeline.cpp p2p_export / p2p_import; kernels_ring.cu)
+    uint32_t *p2p_flags = nullptr;       // local {in_flag, ack, seq, -}
+    float *p2p_x_out = nullptr;          // downstream context's x, peer-mapped (cudaIpcOpenMemHandle)
+    uint32_t *p2p_flag_out = nullptr;    // downstream context's flags, peer-mapped
+    uint32_t *p2p_ack_out = nullptr;     // upstream context's flags, peer-mapped
+    bool p2p_ready = false;              // import done: the stage graph is captured with the hand-off fused in
+    bool p2p_on = false;                 // (set only while that graph is being captured)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t last_n = 0;
     bool use_graph = true;
@@ -185,6 +192,9 @@ void comm_destroy();
 int nccl_version();
 float pipeline_decode(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t steps, uint32_t past);
 void pipeline_prefill(llama::Context **ctxs, uint32_t n_seq, const uint32_t *tokens, uint32_t n, uint32_t past);
+void p2p_export(llama::Context **ctxs, uint32_t n_seq, void *out /* n_seq x 128 bytes */);
+void p2p_import(llama::Context **ctxs, uint32_t n_seq, const void *down /* n_seq x 128 or null */, const void *up /* or null */);
+void p2p_disable(llama::Context **ctxs, uint32_t n_seq);
 }  // namespace pipe
 namespace llama {
 // The context-swap rule of server.Do (pkg/server/server.go:158-172; main.go:190-200): when pastCount + len(embd)

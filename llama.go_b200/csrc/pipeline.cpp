@@ -97,6 +97,63 @@ int nccl_version() {
     return v;
 }
 
+// ---- fused stage hand-off over NVLink peer memory ---------------------------------------------------------------------
+// Instead of ncclRecv -> stage kernels -> ncclSend per (step, sequence) slot (two extra kernels and a rendezvous per slot:
+// ~60 us of a ~625 us slot at 8 GPUs), the stage's persistent kernel itself stores the residual into the next
+// stage's buffer (peer-mapped by CUDA IPC; one process per GPU) and raises a flag there; the next stage's kernel — already
+// streaming its weights — waits for that flag (kernels_ring.cu).  Back-pressure is a second flag going upstream.
+// export: per context 2 x 64 bytes (cudaIpcMemHandle of x, of the flags);  import: the handles of the downstream stage's
+// contexts (null on the last stage) and of the upstream stage's contexts (null on the first stage).
+void p2p_export(llama::Context **ctxs, uint32_t n_seq, void *out) {
+    LB_CHECK(ctxs && out && n_seq >= 1, "p2p_export: nil argument");
+    char *o = static_cast<char *>(out);
+    for (uint32_t s = 0; s < n_seq; s++) {
+        llama::Context *c = ctxs[s];
+        LB_CUDA(cudaSetDevice(c->model->device));
+        if (!c->p2p_flags) c->p2p_flags = c->mem.dmalloc<uint32_t>(4);
+        cudaIpcMemHandle_t hx, hf;
+        LB_CUDA(cudaIpcGetMemHandle(&hx, c->x));
+        LB_CUDA(cudaIpcGetMemHandle(&hf, c->p2p_flags));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(o + (size_t)s * 128, &hx, 64);
+        memcpy(o + (size_t)s * 128 + 64, &hf, 64);
+    }
+}
+
+void p2p_import(llama::Context **ctxs, uint32_t n_seq, const void *down, const void *up) {
+    LB_CHECK(ctxs && n_seq >= 1, "p2p_import: nil argument");
+    for (uint32_t s = 0; s < n_seq; s++) {
+        llama::Context *c = ctxs[s];
+        LB_CHECK(c->p2p_flags != nullptr, "p2p_import: call p2p_export first");
+        LB_CHECK(c->use_ring, "p2p_import: the fused hand-off needs the TMA-ring megakernel (unsupported shape or LB_NO_RING)");
+        LB_CHECK(!c->stage_graph, "p2p_import: the stage graph is already captured");
+        LB_CUDA(cudaSetDevice(c->model->device));
+        cudaIpcMemHandle_t h;
+        void *ptr = nullptr;
+        if (down) {
+            memcpy(&h, static_cast<const char *>(down) + (size_t)s * 128, 64);
+            LB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->p2p_x_out = static_cast<float *>(ptr);
+            memcpy(&h, static_cast<const char *>(down) + (size_t)s * 128 + 64, 64);
+            LB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->p2p_flag_out = static_cast<uint32_t *>(ptr);
+        }
+        if (up) {
+            memcpy(&h, static_cast<const char *>(up) + (size_t)s * 128 + 64, 64);
+            LB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->p2p_ack_out = static_cast<uint32_t *>(ptr);
+        }
+        c->p2p_ready = true;
+    }
+}
+
+void p2p_disable(llama::Context **ctxs, uint32_t n_seq) {
+    for (uint32_t s = 0; s < n_seq; s++) {
+        LB_CHECK(!ctxs[s]->stage_graph || !ctxs[s]->p2p_ready, "p2p_disable: the stage graph is already captured with the hand-off");
+        ctxs[s]->p2p_ready = false;
+    }
+}
+
 // Steady-state pipelined decode.  `ctxs[s]` = this stage's context of in-flight sequence s (its own
 // KV slabs and activations).  For step k = 0..steps-1 and sequence s = 0..S-1, in that order on ONE
 // stream:   [recv residual from stage-1]  ->  this stage's layers (CUDA-graph replay)  ->
@@ -112,13 +169,15 @@ float pipeline_decode(llama::Context **ctxs, uint32_t S, const uint32_t *tokens,
     const uint32_t d = m->hp.dim;
     const bool first = m->has_embedding(), last = m->has_head();
     const int world = (first && last) ? 1 : g_world;
-    if (world > 1) LB_CHECK(g_comm != nullptr, "pipeline_decode: call lb_comm_init first");
+    const bool p2p = c0->p2p_ready;   // fused hand-off over peer memory: no NCCL call on the decode path
+    if (world > 1 && !p2p) LB_CHECK(g_comm != nullptr, "pipeline_decode: call lb_comm_init first");
     LB_CHECK((uint64_t)past + steps <= c0->ctx_size, "pipeline_decode: past + steps exceeds the context size");
     LB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = c0->stream;
     for (uint32_t s = 0; s < S; s++) {
         llama::Context *c = ctxs[s];
         LB_CHECK(c->model == m, "pipeline_decode: contexts must share the stage model");
+        LB_CHECK(c->p2p_ready == p2p, "pipeline_decode: every context of the stage must use the same hand-off");
         LB_CHECK(steps <= c->tokens_cap, "pipeline_decode: too many steps");
         if (first) {
             LB_CHECK(tokens != nullptr, "pipeline_decode: stage 0 needs tokens");
@@ -137,10 +196,10 @@ float pipeline_decode(llama::Context **ctxs, uint32_t S, const uint32_t *tokens,
     for (uint32_t k = 0; k < steps; k++) {
         for (uint32_t s = 0; s < S; s++) {
             llama::Context *c = ctxs[s];
-            if (!first) LB_NCCL(g_nccl.Recv(c->x, d, ncclFloat32, g_rank - 1, g_comm, st));
+            if (!first && !p2p) LB_NCCL(g_nccl.Recv(c->x, d, ncclFloat32, g_rank - 1, g_comm, st));
             LB_CUDA(cudaGraphLaunch(c->stage_graph, st));
             count_launch(c->use_mega ? 2 : m->layers.size() * 8 + 4);
-            if (!last) LB_NCCL(g_nccl.Send(c->x, d, ncclFloat32, g_rank + 1, g_comm, st));
+            if (!last && !p2p) LB_NCCL(g_nccl.Send(c->x, d, ncclFloat32, g_rank + 1, g_comm, st));
         }
     }
     LB_CUDA(cudaEventRecord(c0->ev1, st));

@@ -57,6 +57,7 @@ class Stage:
             self.model.init_random(seed)
         self.ctxs = [llama.NewContext(self.model, ctx_size) for _ in range(n_seq)]
         self._arr = (C.c_void_p * n_seq)(*[c._h for c in self.ctxs])
+        self.p2p = False
 
     @property
     def is_first(self):
@@ -77,6 +78,43 @@ class Stage:
         ms = C.c_float(0)
         check(lib().lb_pipeline_decode(self._arr, len(self.ctxs), t.ctypes.data_as(_u32p), t.shape[1], past, C.byref(ms)))
         return ms.value
+
+    def enable_p2p(self, dist) -> bool:
+        """Fuse the stage hand-off into the stage kernels (NVLink peer stores + flags, lb_pipeline_p2p_*): exchange the CUDA
+        IPC handles of every rank's contexts and map the neighbours'.  All ranks switch together or not at all (any failure ->
+        NCCL send/recv as before).  LB_PIPE_NCCL=1 keeps NCCL.  Call before the first decode()."""
+        import os
+        import torch
+        if self.world == 1 or os.environ.get("LB_PIPE_NCCL"):
+            return False
+        n = len(self.ctxs)
+        ok, mine = 1.0, b""
+        try:
+            buf = (C.c_ubyte * (128 * n))()
+            check(lib().lb_pipeline_p2p_export(self._arr, n, buf))
+            mine = bytes(buf)
+        except Exception:
+            ok = 0.0
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine)
+        if ok and all(len(h) == 128 * n for h in allh):
+            try:
+                down = allh[self.rank + 1] if self.rank + 1 < self.world else None
+                up = allh[self.rank - 1] if self.rank > 0 else None
+                check(lib().lb_pipeline_p2p_import(self._arr, n, down, up))
+            except Exception:
+                ok = 0.0
+        else:
+            ok = 0.0
+        t = torch.tensor([ok])
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        self.p2p = bool(t.item() == 1.0)
+        if not self.p2p:
+            try:
+                lib().lb_pipeline_p2p_disable(self._arr, n)
+            except Exception:
+                pass
+        return self.p2p
 
     def logits(self, seq: int) -> np.ndarray:
         return llama.ReadLogits(self.ctxs[seq]).copy()

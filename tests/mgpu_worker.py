@@ -28,6 +28,8 @@ def main():
     S = 2  # two in-flight sequences, both fed the same tokens -> both must reproduce the golden logits
     stage = pipeline.Stage(hp, rank, world, local, rec["context"], S, seed=None, tensors=synth.synth_model(rec["seed"], hp))
     ids = g["prompt_ids"]
+    p2p = stage.enable_p2p(dist) if (len(sys.argv) > 2 and sys.argv[2] == "p2p") else False
+    print(f"[rank {rank}] hand-off: {'p2p-fused' if p2p else 'nccl'}", flush=True)
     stage.prefill(np.stack([ids] * S), 0)
     ok = True
     if stage.is_last:

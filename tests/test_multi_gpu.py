@@ -120,14 +120,18 @@ def test_pipeline_api_single_stage_equals_eval(synth):
 
 
 @pytest.mark.gpu
-def test_nccl_pipeline_two_gpus():
+@pytest.mark.parametrize("handoff", ["nccl", "p2p"])
+def test_pipeline_two_gpus(handoff):
+    """Two stages on two GPUs, one process each: golden logits through the NCCL send/recv hand-off and through the
+    hand-off fused into the stage kernels (NVLink peer stores + flags)."""
     import llama_go_b200  # noqa: F401
     from llama_go_b200 import _capi
     if _capi.lib().lb_device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     env = dict(os.environ)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"), "hd128"]
+           "--master-port", "29533" if handoff == "nccl" else "29534", os.path.join(ROOT, "tests", "mgpu_worker.py"), "hd128", handoff]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=env)
     out = p.stdout.decode("utf-8", "replace")
     assert p.returncode == 0 and "MGPU_OK" in out, out[-3000:]
+    assert ("hand-off: p2p-fused" in out) == (handoff == "p2p"), out[-3000:]

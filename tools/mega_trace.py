@@ -8,10 +8,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import llama_go_b200  # noqa
 from llama_go_b200 import _capi, llama, synth
 
-ap = argparse.ArgumentParser(); ap.add_argument("--past", type=int, default=448); ap.add_argument("--layers", type=int, default=32)
+ap = argparse.ArgumentParser(); ap.add_argument("--past", type=int, default=448); ap.add_argument("--layers", type=int, default=32); ap.add_argument("--q8", action="store_true")
 a = ap.parse_args()
 hp = synth.HParams(32000, 4096, 256, 32, a.layers)
-m = llama.Model(hp).init_random(0)
+m = llama.Model(hp, weight_type=llama.LB_TYPE_Q8_0 if a.q8 else llama.LB_TYPE_F32).init_random(0)
 c = llama.NewContext(m, 512)
 llama.Eval(c, [5, 6, 7, 8, 9, 10, 11, 12, 13], 0)
 for i in range(4):
@@ -25,6 +25,8 @@ arr = allv[a.layers * 13:].reshape(5, 148)
 d = np.diff(t, axis=1)[1:-1]          # skip first/last layer
 names = ["rms1", "gemv qkv", "barrier1", "attention", "barrier2", "gemv wo", "barrier3", "rms2", "gemv w1w3", "barrier4", "gemv w2", "barrier5"]
 ideal = {"gemv qkv": 201.4e6, "gemv wo": 67.2e6, "gemv w1w3": 360.8e6, "gemv w2": 180.4e6}
+if a.q8:
+    ideal = {k: v * 36 / 128 for k, v in ideal.items()}
 print("phase            mean_us   min_us   max_us   (CTA 0 view; ideal at 7.0 TB/s)")
 for i, nme in enumerate(names):
     extra = f"   ideal {ideal[nme] / 7.0e12 * 1e6:6.1f}" if nme in ideal else ""
