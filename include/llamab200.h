@@ -158,6 +158,8 @@ LB_API int       lb_batch_eval(lb_batch *b, const uint32_t *tokens, const uint32
 /* `steps` tokens per pod (tokens [n][steps], teacher-forced) enqueued back to back; ms_out = CUDA-event time */
 LB_API int       lb_batch_decode_resident(lb_batch *b, const uint32_t *tokens, uint32_t steps, const uint32_t *pasts, float *ms_out);
 LB_API int       lb_batch_read_logits(lb_batch *b, float *logits_out);    /* [n][vocab] of the last step */
+/* profiling aid, like lb_context_mega_trace: 13 globaltimer stamps per layer of the last pod-batch step (LB_MEGA_TRACE=1) */
+LB_API int       lb_batch_mega_trace(lb_batch *b, uint64_t *out, uint32_t n);
 
 /* ---- multi-GPU layer sharding: one process per GPU, NCCL send/recv of the residual stream ----
  * rank r owns the stage created with lb_model_create(hp, dev, r*L/G, (r+1)*L/G).  NCCL is bound at

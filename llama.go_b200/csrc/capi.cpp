@@ -217,6 +217,14 @@ int lb_batch_eval(lb_batch *b, const uint32_t *tokens, const uint32_t *pasts, fl
 int lb_batch_decode_resident(lb_batch *b, const uint32_t *tokens, uint32_t steps, const uint32_t *pasts, float *ms_out) {
     LB_TRY_INT(LB_CHECK(b, "nil batch"); float ms = b->b->decode_resident(tokens, steps, pasts); if (ms_out) *ms_out = ms);
 }
+int lb_batch_mega_trace(lb_batch *b, uint64_t *out, uint32_t n) {
+    LB_TRY_INT(LB_CHECK(b && out, "nil argument"); llama::PodBatch *x = b->b;
+               LB_CHECK(x->mega_trace != nullptr, "no trace buffer: create the batch with LB_MEGA_TRACE=1 in the environment");
+               LB_CHECK(n <= x->model->layers.size() * 13, "trace: n too large");
+               LB_CUDA(cudaSetDevice(x->model->device));
+               LB_CUDA(cudaStreamSynchronize(x->stream));
+               LB_CUDA(cudaMemcpy(out, x->mega_trace, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost)));
+}
 int lb_batch_read_logits(lb_batch *b, float *logits_out) { LB_TRY_INT(LB_CHECK(b && logits_out, "nil argument"); b->b->read_logits(logits_out)); }
 
 // ---- multi-GPU pipeline ----

@@ -176,6 +176,7 @@ struct MegaPodsParamsHost {
     float *part_o, *part_ml;
     unsigned *barrier;             // 2 counters, zeroed by the launcher
     const void *tmaps = nullptr;   // host pointer to the ring_pods_make_maps() blob (TMA-ring variant only)
+    void *trace = nullptr;         // optional uint64[n_layers * 13] phase time stamps (TMA-ring variant, profiling aid)
     uint32_t dim, ff, heads, vocab, ctx;
 };
 bool decode_mega_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);

@@ -129,6 +129,7 @@ struct RPParams {
     float *part_o, *part_ml;
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
+    unsigned long long *trace;   // optional: 13 globaltimer stamps per layer by consumer thread 0 of CTA 0 (profiling aid)
 };
 
 struct RPShared {
@@ -565,16 +566,30 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         return;
     }
     unsigned target = 0;
+    unsigned long long *tr = (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+    auto stamp = [&](uint32_t li, int i) {
+        if (tr) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            tr[li * 13 + i] = tt;
+        }
+    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayerHost L = p.layers[li];
         const size_t layer_off = (size_t)li * p.ctx * dim;
+        stamp(li, 0);
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         rms_scales(dim, B, sh);
+        stamp(li, 1);
         consume<1, 0, 1, HD>(dim, 3 * dim, nullptr, 0, L.attention_norm, p.qkv, 3 * dim, nullptr, 0, ph, pos, ring, xs, p, sh);
+        stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 3);
         // ---- P2: RoPE, KV store, attention (llama.go:274-333)
         attention_pods<HD>(p, layer_off, sh, scores);
+        stamp(li, 4);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 5);
         // ---- P3: wo + residual (llama.go:336-340)
         if (p.splits > 1) {
             merge_stats(p, sh);
@@ -582,16 +597,23 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         } else {
             consume<1, 1, 0, HD>(dim, dim, p.attn, dim, nullptr, p.y, dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         }
+        stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         if (threadIdx.x < RP_MAXB) sh.xrow[threadIdx.x] = threadIdx.x < B ? p.y + (size_t)threadIdx.x * dim : nullptr;
         ccsync();
         rms_scales(dim, B, sh);
+        stamp(li, 8);
         consume<2, 0, 1, HD>(dim, ff, nullptr, 0, L.ffn_norm, p.act, ff, nullptr, 0, ph, pos, ring, xs, p, sh);
+        stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366)
         consume<1, 1, 0, HD>(ff, dim, p.act, ff, nullptr, p.x, dim, p.y, dim, ph, pos, ring, xs, p, sh);
+        stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
+        stamp(li, 12);
         if (threadIdx.x < RP_MAXB) sh.xrow[threadIdx.x] = threadIdx.x < B ? p.x + (size_t)threadIdx.x * dim : nullptr;
         ccsync();
     }
@@ -662,6 +684,7 @@ void decode_ring_pods(const MegaPodsParamsHost &h, cudaStream_t st) {
     p.splits = pods_splits(h.B, h.heads);
     LB_CHECK(h.B * h.heads * p.splits <= (uint32_t)RP_MAX_ITEMS, "decode_ring_pods: too many attention items");
     p.chunk_cap = (h.ctx + p.splits - 1) / p.splits;
+    p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     size_t smem = 0;
     p.n_slots = pods_plan(&smem);
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));

@@ -171,6 +171,7 @@ struct PodBatch {
     unsigned *mega_barrier = nullptr;
     std::vector<uint8_t> tmaps;         // TMA tensor maps of the weight matrices (k::ring_pods_make_maps)
     const void *tmaps_ptr = nullptr;
+    void *mega_trace = nullptr;         // LB_MEGA_TRACE=1: per-phase globaltimer stamps of CTA 0 (TMA-ring variant)
 
     explicit PodBatch(const std::vector<Context *> &ctxs);
     ~PodBatch();

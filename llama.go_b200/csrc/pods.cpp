@@ -65,6 +65,7 @@ PodBatch::PodBatch(const std::vector<Context *> &cs) : ctxs(cs) {
         mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
         mega_barrier = mem.dmalloc<unsigned>(2);
+        if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13);
         if (use_ring) {
             tmaps.resize(k::ring_pods_maps_bytes() + 64);
             void *al = reinterpret_cast<void *>(((uintptr_t)tmaps.data() + 63) & ~(uintptr_t)63);
@@ -104,6 +105,7 @@ void PodBatch::forward() {
         mp.part_ml = attn_scratch + (size_t)B * H * 32 * hp.head_dim();
         mp.barrier = mega_barrier;
         mp.tmaps = tmaps_ptr;
+        mp.trace = mega_trace;
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
         if (use_ring) k::decode_ring_pods(mp, st);
         else k::decode_mega_pods(mp, st);

@@ -27,3 +27,7 @@ timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench_default_$TAG.json
 python -c "
 import json;d=json.load(open('$OUT/bench_default_$TAG.json'));print('headline',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'frac',d['roofline']['frac'],'repeats',d['repeats'],'cpu',d['cpu_baseline'] and d['cpu_baseline']['value'])
 for k,v in (d.get('configs') or {}).items(): print(' ',k, {kk:(round(vv,1) if isinstance(vv,float) else vv) for kk,vv in v.items() if kk in ('value','e2e','error')}, v.get('roofline',{}).get('frac'))" || tail -5 $OUT/bench_default_$TAG.err
+echo "=== pods trace + bench"
+timeout 200 python tools/pods_trace.py > $OUT/trace_pods8_$TAG.txt 2>&1; head -16 $OUT/trace_pods8_$TAG.txt
+timeout 300 python bench.py --pods 8 --steps 50 > $OUT/bench_pods8_$TAG.json 2> $OUT/bench_pods8_$TAG.err; rc=$?
+python -c "import json;d=json.load(open('$OUT/bench_pods8_$TAG.json'));print('[pods8] rc=$rc value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'frac',d['roofline']['frac'])" || tail -3 $OUT/bench_pods8_$TAG.err
