@@ -148,17 +148,13 @@ bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t v
 void decode_ring(const MegaParamsHost &p, cudaStream_t st);
 
 // ---- Q8_0 single-token decode on the TMA ring with the MulMat on the INT8 tensor cores (kernels_ring_q8.cu)
-struct RingQ8Planes {   // ROW-MAJOR planes (q8_to_row_major) of layer 0's wqkv, wo, w1, w3, w2 and of the lm_head ([5], may be null)
-    const int8_t *q[6];
-    const float *d[6];
-    uint64_t q_layer_stride;   // bytes between consecutive layers' planes (the same for every kind)
-    uint64_t d_layer_stride;   // floats
+struct RingQ8Layer {   // tile-major decode planes (q8_to_tile_major) of one layer's matrices; array lives in device memory
+    const uint8_t *wqkv, *wo, *w1, *w3, *w2;
 };
-void q8_to_row_major(const int8_t *q, const float *d, int8_t *q_rm, float *d_rm, uint32_t rows, uint32_t K, cudaStream_t st);
+size_t q8_tile_major_bytes(uint32_t rows, uint32_t K);
+void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t rows, uint32_t K, cudaStream_t st);
 bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
-size_t ring_q8_maps_bytes();
-void ring_q8_make_maps(const RingQ8Planes &pl, uint32_t n_layers, uint32_t dim, uint32_t ff, uint32_t vocab, void *maps_out);
-void decode_ring_q8(const MegaParamsHost &p, const void *tmaps, cudaStream_t st);
+void decode_ring_q8(const MegaParamsHost &p, const RingQ8Layer *planes_dev, const uint8_t *out_plane, cudaStream_t st);
 
 // ---- persistent pod-batch megakernel (kernels_mega_pods.cu): one decode step of B <= 8 pods, weights streamed once,
 //      B-column MulMat on the tensor cores (mma.sync tf32, 3xTF32 split in registers)

@@ -36,6 +36,7 @@ constexpr int RG_HALF = RG_CTHREADS / 2;
 constexpr uint32_t RG_SLOT_FLOATS = 4096;          // one slot = one row (or a K chunk of a longer row): ONE bulk copy of <= 16 KB
 constexpr uint32_t RG_SLOT = RG_SLOT_FLOATS * 4;
 constexpr int RG_MAX_SLOTS = 12;
+constexpr int RG_MAX_PHASES = 4 * 160 + 1;        // MulMat phases of a launch: 4 per layer + lm_head
 constexpr int RG_MAX_ITEMS = 2 * kNumSMs;
 constexpr int RG_MAX_HEADS = 256;
 
@@ -101,6 +102,8 @@ struct RingParams {
 struct RingShared {
     unsigned long long full[RG_MAX_SLOTS], empty[RG_MAX_SLOTS];
     unsigned epoch[RG_MAX_SLOTS];   // q / n_slots of the slot's current occupant (written by the producer before it arms full[])
+    unsigned jobrow[RG_MAX_SLOTS];  // the output row the slot's bytes belong to
+    unsigned short done_jobs[RG_MAX_PHASES];   // jobs of MulMat phase i of this launch (0xFFFF: the producer has not finished it)
     double red[RG_CWARPS];
     double rope_cs[64][2];
     float fred[2][RG_CWARPS / 2];
@@ -142,25 +145,30 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
     ccsync();
 }
 
-__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
-    r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
-    r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
-}
 
 // The stream is a sequence of slots numbered from the start of the launch: slot q lives in ring entry q % n_slots, its
 // mbarrier phase bit is (q / n_slots) & 1.  Both sides derive q from (phase base, row, chunk, matrix) — no shared cursor.
 __device__ __forceinline__ uint32_t chunk_floats(uint32_t K, uint32_t nch) { return ((K / 4 + nch - 1) / nch) * 4; }
 
+// Work of a MulMat phase = "jobs", one per output row (its nch K-chunks, both matrices of the SwiGLU pair: J slots).
+// 3/4 of the rows are dealt out statically (CTA c: a contiguous block), the rest is a pool handed out one row per ticket
+// (atomic counter per phase) — drawn by the PRODUCER as it runs ahead, so an SM that streams faster takes more rows and
+// all CTAs reach the grid barrier within about one row time (a purely static split left the fast CTAs waiting 5-12 us
+// per barrier for the slow ones: 203 vs 214 tok/s, profiles/README.md r02h).  Job j of the phase (in issue order) is
+// consumed by warp j % 16; its row number travels in sh.jobrow[]; the producer ends the phase by publishing the job count.
+constexpr unsigned RG_STATIC_NUM = 3, RG_STATIC_DEN = 4;
+
 // ---------------------------------------------------------------------------------------------------------
-// producer (one thread): rows [r0, r1) of W (and W3 for the SwiGLU pair) -> ring; one bulk copy per (row, chunk, matrix)
+// producer (one thread)
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t ring_base,
-                                        RingShared &sh, uint32_t n_slots) {
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
+__device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t phidx, unsigned *ticket,
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots) {
     const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
-    for (uint32_t row = r0; row < r1; row++) {
+    const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));   // static rows per CTA
+    const uint32_t pool0 = Q * gridDim.x;
+    uint32_t njobs = 0;
+    auto job = [&](uint32_t row) {
         for (uint32_t c = 0; c < nch; c++) {
             const uint32_t k0 = c * CH, len = min(CH, K - k0);
 #pragma unroll
@@ -168,6 +176,8 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
                 const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
                 const uint32_t fb = smem_u32(&sh.full[slot]);
                 mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // the consumer warp of slot q - n_slots released it
+                *reinterpret_cast<volatile unsigned *>(&sh.jobrow[slot]) = row;
+                __threadfence_block();
                 *reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) = q / n_slots;
                 __threadfence_block();
                 mbar_expect_tx(fb, len * 4);
@@ -175,36 +185,62 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
                 q++;
             }
         }
+        njobs++;
+    };
+    unsigned t = atomicAdd(ticket, 1u);                         // first ticket on its way while the static rows stream
+    for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
+    while ((uint64_t)pool0 + t < M) {
+        const uint32_t row = pool0 + t;
+        t = atomicAdd(ticket, 1u);                              // next ticket, overlapped with this row's copies
+        job(row);
     }
+    // end of phase: the job count for the consumers
+    *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]) = (unsigned short)njobs;
+    __threadfence_block();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// consumer: out[row] = epilogue(W[row] . x) for this CTA's rows of an M x K matrix; x in shared memory (xs).
-// Warp w owns rows r0 + w, r0 + w + 16, ... and consumes every slot of its rows by itself.
+// consumer: out[row] = epilogue(W[row] . x) for the rows this CTA's producer fetched; x in shared memory (xs).
+// Warp w consumes jobs w, w + 16, ... (every slot of a job by itself).
 // EPI: 0 none, 1 + res[row];  NM == 2: out[row] = silu(W1[row].x) * (W3[row].x)
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI>
-__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs, float *out, const float *res, uint32_t &qbase,
+__device__ __forceinline__ void consume(uint32_t K, const float *xs, float *out, const float *res, uint32_t &qbase, uint32_t phidx,
                                         const uint8_t *ring, RingShared &sh, uint32_t n_slots) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
-    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
-    for (uint32_t row = r0 + warp; row < r1; row += RG_CWARPS) {
+    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch), J = nch * NM;
+    uint32_t njobs = 0;
+    for (uint32_t j = warp;; j += RG_CWARPS) {
+        uint32_t q = qbase + j * J;
+        // Wait until the producer has installed job j's first slot in its ring entry — or has ended the phase with fewer
+        // jobs.  (A warp's next slot can be several ring wraps ahead of what the entry holds now, and an mbarrier parity
+        // only tells consecutive phases apart: the epoch check comes first, then the wait for the bytes.)
+        {
+            const uint32_t slot = q % n_slots;
+            const long long t0 = clock64();
+            bool have = false;
+            while (true) {
+                if (*reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) == q / n_slots) { have = true; break; }
+                const unsigned dj = *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]);
+                if (dj != 0xFFFFu) {
+                    njobs = dj;
+                    if (j >= njobs) break;
+                }
+                if (clock64() - t0 > 4000000000LL) __trap();
+            }
+            if (!have) break;
+        }
+        const uint32_t row = *reinterpret_cast<volatile unsigned *>(&sh.jobrow[q % n_slots]);
         float acc[NM][2];
 #pragma unroll
         for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
-        uint32_t q = qbase + (row - r0) * nch * NM;
         for (uint32_t c = 0; c < nch; c++) {
             const uint32_t k0 = c * CH, len4 = min(CH, K - k0) / 4;
             const float4 *x4 = reinterpret_cast<const float4 *>(xs + k0);
 #pragma unroll
             for (int m = 0; m < NM; m++, q++) {
                 const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
-                // A warp owns whole rows, so its next slot can be SEVERAL ring wraps ahead of what the entry holds now, and
-                // an mbarrier parity only tells consecutive phases apart: first wait until the producer has installed this
-                // wrap in the entry (it does so only after the previous occupant was released), then for the bytes.
-                {
+                if (c | m) {   // later slots of the job: same epoch rule
                     const long long t0 = clock64();
                     while (*reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) != q / n_slots) {
                         if (clock64() - t0 > 4000000000LL) __trap();
@@ -239,7 +275,7 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs,
             out[row] = v;
         }
     }
-    qbase += (r1 - r0) * nch * NM;
+    qbase += njobs * J;   // (every warp left the loop through the producer's end-of-phase word, so njobs is final)
 }
 
 // ---- activation vector of a phase -> shared memory -----------------------------------------------------------
@@ -247,12 +283,26 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs,
 __device__ __forceinline__ void fill_norm(float *xs, const float *x, const float *w, uint32_t K, RingShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4 *x4 = reinterpret_cast<float4 *>(xs);
+    constexpr int R = 4;   // float4 kept in registers per thread (covers K <= 8192); longer vectors take the shared-memory path for the rest
+    float4 v[R], ww[R];
     double acc = 0.0;
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) {
-        const float4 v = ldcg4(x + (size_t)f * 4);
-        x4[f] = v;
-        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
-        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t f = threadIdx.x + i * RG_CTHREADS;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ww[i] = v[i];
+        if (f < K / 4) {
+            v[i] = ldcg4(x + (size_t)f * 4);
+            ww[i] = __ldg(reinterpret_cast<const float4 *>(w) + f);
+        }
+        acc += (double)__fmul_rn(v[i].x, v[i].x); acc += (double)__fmul_rn(v[i].y, v[i].y);
+        acc += (double)__fmul_rn(v[i].z, v[i].z); acc += (double)__fmul_rn(v[i].w, v[i].w);
+    }
+    for (uint32_t f = threadIdx.x + R * RG_CTHREADS; f < K / 4; f += RG_CTHREADS) {
+        const float4 u = ldcg4(x + (size_t)f * 4);
+        x4[f] = u;
+        acc += (double)__fmul_rn(u.x, u.x); acc += (double)__fmul_rn(u.y, u.y);
+        acc += (double)__fmul_rn(u.z, u.z); acc += (double)__fmul_rn(u.w, u.w);
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.red[warp] = acc;
@@ -261,11 +311,18 @@ __device__ __forceinline__ void fill_norm(float *xs, const float *x, const float
 #pragma unroll
     for (int i = 0; i < RG_CWARPS; i++) t += sh.red[i];
     const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) {
-        const float4 v = x4[f];
-        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + f);
-        x4[f] = make_float4(__fmul_rn(ww.x, __fmul_rn(v.x, sc)), __fmul_rn(ww.y, __fmul_rn(v.y, sc)),
-                            __fmul_rn(ww.z, __fmul_rn(v.z, sc)), __fmul_rn(ww.w, __fmul_rn(v.w, sc)));
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t f = threadIdx.x + i * RG_CTHREADS;
+        if (f < K / 4)
+            x4[f] = make_float4(__fmul_rn(ww[i].x, __fmul_rn(v[i].x, sc)), __fmul_rn(ww[i].y, __fmul_rn(v[i].y, sc)),
+                                __fmul_rn(ww[i].z, __fmul_rn(v[i].z, sc)), __fmul_rn(ww[i].w, __fmul_rn(v[i].w, sc)));
+    }
+    for (uint32_t f = threadIdx.x + R * RG_CTHREADS; f < K / 4; f += RG_CTHREADS) {
+        const float4 u = x4[f];
+        const float4 wq = __ldg(reinterpret_cast<const float4 *>(w) + f);
+        x4[f] = make_float4(__fmul_rn(wq.x, __fmul_rn(u.x, sc)), __fmul_rn(wq.y, __fmul_rn(u.y, sc)),
+                            __fmul_rn(wq.z, __fmul_rn(u.z, sc)), __fmul_rn(wq.w, __fmul_rn(u.w, sc)));
     }
     ccsync();   // also orders sh.red against its next use
 }
@@ -466,6 +523,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
             mbar_init(smem_u32(&sh.empty[s]), 1);
             sh.epoch[s] = 0xFFFFFFFFu;
         }
+        for (int i = 0; i < RG_MAX_PHASES; i++) sh.done_jobs[i] = 0xFFFFu;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const uint32_t past = p.state[0];
@@ -482,18 +540,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         if (threadIdx.x != RG_CTHREADS) return;   // one thread drives the copy engine
         // ================= producer warp: the whole token's weights of this CTA, in schedule order =================
         const uint32_t ring_base = smem_u32(ring);
+        unsigned *tk = p.barrier + 2;   // one ticket counter per MulMat phase of the launch (zeroed with the barrier)
+        uint32_t phidx = 0;
         for (uint32_t li = 0; li < p.n_layers; li++) {
             const MegaLayerHost L = p.layers[li];
-            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, ring_base, sh, n_slots);
-            produce<1>(L.wo, nullptr, dim, dim, pos, ring_base, sh, n_slots);
-            produce<2>(L.w1, L.w3, dim, ff, pos, ring_base, sh, n_slots);
-            produce<1>(L.w2, nullptr, ff, dim, pos, ring_base, sh, n_slots);
+            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
+            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
+            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
+            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
         }
-        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots);
         return;
     }
     // ================= consumers =================
     unsigned target = 0;
+    uint32_t phidx = 0;   // MulMat phase number (same sequence as the producer's)
     // Pipeline stage hand-off (multi-GPU layer sharding) fused into this kernel: the upstream stage's kernel
     // stored the residual stream straight into this context's x over NVLink and then raised in_flag; the producer warp
     // above is already streaming this stage's weights while we wait.  Before this launch may overwrite the downstream
@@ -523,7 +584,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         fill_norm(xs, xin, L.attention_norm, dim, sh);
         stamp(li, 1);
-        consume<1, 0>(dim, 3 * dim, xs, p.qkv, nullptr, pos, ring, sh, n_slots);
+        consume<1, 0>(dim, xs, p.qkv, nullptr, pos, phidx++, ring, sh, n_slots);
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
@@ -534,20 +595,20 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         stamp(li, 5);
         // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
         fill_merge<HD>(xs, p, sh);
-        consume<1, 1>(dim, dim, xs, p.y, xin, pos, ring, sh, n_slots);
+        consume<1, 1>(dim, xs, p.y, xin, pos, phidx++, ring, sh, n_slots);
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         fill_norm(xs, p.y, L.ffn_norm, dim, sh);
         stamp(li, 8);
-        consume<2, 0>(dim, ff, xs, p.act, nullptr, pos, ring, sh, n_slots);
+        consume<2, 0>(dim, xs, p.act, nullptr, pos, phidx++, ring, sh, n_slots);
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
         fill_plain(xs, p.act, ff);
-        consume<1, 1>(ff, dim, xs, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, ring, sh, n_slots);
+        consume<1, 1>(ff, xs, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring, sh, n_slots);
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers);
         stamp(li, 12);
@@ -555,7 +616,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         fill_norm(xs, xin, p.final_norm, dim, sh);
-        consume<1, 0>(dim, p.vocab, xs, p.logits, nullptr, pos, ring, sh, n_slots);
+        consume<1, 0>(dim, xs, p.logits, nullptr, pos, phidx++, ring, sh, n_slots);
     }
     if (p.p2p_flags && blockIdx.x == 0 && threadIdx.x == 0) {
         // every CTA passed the last grid barrier (system-scope fences below) after storing its rows of the residual
@@ -605,6 +666,7 @@ static uint32_t ring_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ct
 
 bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
     if (heads == 0 || dim % heads || heads > (uint32_t)RG_MAX_HEADS) return false;
+    if (((uint64_t)(ff > vocab ? ff : vocab) > 3ull * dim ? (ff > vocab ? ff : vocab) : 3ull * dim) >= 65535ull * kNumSMs / 2) return false;   // job counts are 16-bit
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
     if (dim % 4 || ff % 4) return false;               // 16-byte bulk copies
@@ -633,7 +695,7 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
     p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
-    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
+    LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (3 + 4 * (size_t)h.n_layers), st));   // grid barrier + per-phase row tickets
     const uint32_t hd = h.dim / h.heads;
     cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);
     LB_CUDA(e);

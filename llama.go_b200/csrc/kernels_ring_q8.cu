@@ -5,9 +5,13 @@
 // a Q8 matrix is 4x smaller than its FP32 twin, so every kernel is one wave of resident warps, and the PRMT/FADD
 // dequantisation costs ~3.5 CUDA-core instructions per weight); a register-fed Q8 megakernel (173 / 290 tok/s) and an
 // int8-mma per-op GEMV (382 tok/s) were measured slower.  Here
-//   * the weight stream is decoupled from the consumers: a producer thread feeds a shared-memory ring with 3-D
-//     tensor-map TMA loads (slot = 16 rows x 1024 int8 + their 16 x 32 block scales), running ahead across tiles,
-//     phases and grid barriers (kernels_ring.cu);
+//   * the weight stream is decoupled from the consumers: a producer thread feeds a shared-memory ring with ONE bulk
+//     copy per slot (cp.async.bulk, 18 KB), running ahead across tiles, phases and grid barriers (kernels_ring.cu).
+//     The matrices are kept in a TILE-MAJOR "decode plane" (q8_to_tile_major): for every 16-row tile and every
+//     1024-column segment one contiguous record [32 blocks][16 rows][32 int8] + [32 blocks][16 rows] f32 scales —
+//     exactly the order a CTA streams them, and a shared-memory image in which the mma fragment reads are
+//     bank-conflict free (the first version streamed row-major planes through 3-D tensor maps: 4-way conflicts on
+//     the fragment loads and 8-way on the scales capped it below the per-op path, profiles/README.md);
 //   * the int8 weights are consumed AS STORED by mma.sync.m16n8k32.s8 (A = 16 rows x 32 k = one Q8 block per row);
 //     the FP32 activation block (32 values) enters as four balanced base-128 digit planes relative to the block's
 //     power-of-two scale s (x = s * (d0/2^6 + d1/2^13 + d2/2^20 + d3/2^27) +- s * 2^-28), four of the eight B columns;
@@ -17,7 +21,6 @@
 // only by summation order and the 2^-28 digit truncation.
 // Attention / RMSNorm / RoPE numerics: kernels_mega.cu.
 #include <cooperative_groups.h>
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,9 +37,10 @@ constexpr int RQ_THREADS = RQ_CTHREADS + 32;       // + the producer warp
 constexpr int RQ_HALF = RQ_CTHREADS / 2;
 constexpr uint32_t RQ_SEGK = 1024;                 // k per slot row
 constexpr uint32_t RQ_ROWS = 16;
-constexpr uint32_t RQ_QBYTES = RQ_ROWS * RQ_SEGK;              // 16 KB of int8
-constexpr uint32_t RQ_DBYTES = RQ_ROWS * (RQ_SEGK / 32) * 4;   // 2 KB of block scales
-constexpr uint32_t RQ_SLOT = RQ_QBYTES + RQ_DBYTES;            // 18432
+constexpr uint32_t RQ_BLKQ = RQ_ROWS * 32;                     // int8 bytes of one 32-column block of a tile: [16 rows][32]
+constexpr uint32_t RQ_BLKD = RQ_ROWS * 4;                      // its scales: [16 rows] f32
+constexpr uint32_t RQ_BLK = RQ_BLKQ + RQ_BLKD;                 // 576 bytes per (tile, block)
+constexpr uint32_t RQ_SLOT = (RQ_SEGK / 32) * RQ_BLK;          // 18432: a full segment record = [32][16][32] int8 | [32][16] f32
 constexpr int RQ_MAX_SLOTS = 10;
 constexpr int RQ_MAX_ITEMS = 2 * kNumSMs;
 constexpr int RQ_MAX_HEADS = 256;
@@ -75,11 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 // D(16x8, s32) = A(16x32, s8, row) * B(32x8, s8, col)
 __device__ __forceinline__ void mma_s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -89,12 +93,10 @@ __device__ __forceinline__ void mma_s8(int (&d)[4], uint32_t a0, uint32_t a1, ui
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
-struct RQMaps {   // per weight kind: q plane viewed as uint32 [layers][rows][K/4] (box 256 x 16 x 1), d plane [layers][rows][K/32] (box 32 x 16 x 1)
-    CUtensorMap q_wqkv, d_wqkv, q_wo, d_wo, q_w1, d_w1, q_w3, d_w3, q_w2, d_w2, q_out, d_out;
-};
-
 struct RQParams {
-    const MegaLayerHost *layers;      // norm vectors and the KV slabs (the matrices come through the tensor maps)
+    const MegaLayerHost *layers;      // norm vectors and the KV slabs
+    const RingQ8Layer *planes;        // [n_layers] tile-major decode planes of the layer's matrices
+    const uint8_t *out_plane;         // lm_head plane (nullptr: no lm_head on this stage)
     uint32_t n_layers;
     const float *tok_embeddings;
     const uint32_t *tokens;
@@ -155,24 +157,24 @@ struct RingPos {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// producer (one thread): for tile, for segment (, for matrix): the int8 box and its scale box into one slot
+// producer (one thread): for tile, for segment (, for matrix): one contiguous record of the tile-major plane per slot
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const CUtensorMap *qA, const CUtensorMap *dA, const CUtensorMap *qB, const CUtensorMap *dB, int layer,
-                                        uint32_t K, uint32_t M, uint32_t &ph, RingPos &pos, uint32_t ring_base, RQShared &sh, uint32_t n_slots) {
+__device__ __forceinline__ void produce(const uint8_t *PA, const uint8_t *PB, uint32_t K, uint32_t M, uint32_t &ph, RingPos &pos,
+                                        uint32_t ring_base, RQShared &sh, uint32_t n_slots) {
     uint32_t r0, r1;
     cta_tile_rows(M, ph++, r0, r1);
-    const uint32_t nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
+    const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
     for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
+        const size_t tbase = (size_t)(tile / RQ_ROWS) * nblk * RQ_BLK;
         for (uint32_t seg = 0; seg < nseg; seg++) {
+            const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
 #pragma unroll
             for (int m = 0; m < NM; m++) {
                 const uint32_t fb = smem_u32(&sh.full[pos.slot]);
                 mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
-                mbar_expect_tx(fb, RQ_SLOT);   // out-of-range rows / columns are zero-filled by the copy engine and still counted
-                const uint32_t dst = ring_base + pos.slot * RQ_SLOT;
-                tma_load_3d(dst, m == 0 ? qA : qB, fb, (int)(seg * (RQ_SEGK / 4)), (int)tile, layer);
-                tma_load_3d(dst + RQ_QBYTES, m == 0 ? dA : dB, fb, (int)(seg * (RQ_SEGK / 32)), (int)tile, layer);
+                mbar_expect_tx(fb, nb * RQ_BLK);
+                bulk_g2s(ring_base + pos.slot * RQ_SLOT, (m == 0 ? PA : PB) + tbase + (size_t)seg * RQ_SLOT, nb * RQ_BLK, fb);
                 pos.next(n_slots);
             }
         }
@@ -191,9 +193,10 @@ __device__ __forceinline__ void make_digits(float *xs, uint32_t K, uint32_t kp, 
         const uint32_t kk = b * 32 + lane;
         const float v = kk < K ? xs[kk] : 0.f;
         const float m = warp_max(fabsf(v));      // (also orders every lane's read of the block before the writes below)
-        int e = 0;
-        if (m > 0.f) frexpf(m, &e);                    // m = f * 2^e, f in [0.5, 1)  ->  |v| / 2^e < 1
-        const float s = ldexpf(1.0f, e), inv = ldexpf(1.0f, -e);
+        // block scale s = 2^e with max|v| / s in [0.5, 1): exponent arithmetic on the bits (frexpf / ldexpf cost ~2.5 us per
+        // phase here); a block whose maximum is zero or denormal is sent as zeros (|v| < 1.2e-38)
+        const uint32_t E = (__float_as_uint(m) >> 23) & 0xFFu;
+        const float s = E ? __uint_as_float((E + 1u) << 23) : 1.0f, inv = E ? __uint_as_float((253u - E) << 23) : 0.0f;
         float r = __fmul_rn(v, inv);                   // exact (power of two)
         int d[4];
         r = __fmul_rn(r, 64.0f);
@@ -223,7 +226,7 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     uint32_t r0, r1;
     cta_tile_rows(M, ph++, r0, r1);
-    const uint32_t nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
+    const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
     const int8_t *dig = reinterpret_cast<const int8_t *>(xs_dig);
     // digit weights of this lane's two D columns (2t, 2t + 1): digits 0..3 live in columns 0..3, columns 4..7 are zero planes
     const float w0 = t == 0 ? 0.015625f : (t == 1 ? 9.5367431640625e-07f : 0.f);            // 2^-6, 2^-20
@@ -246,15 +249,17 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs_
             for (int m = 0; m < NM; m++) {
                 mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase);
                 const uint8_t *sl = ring + (size_t)pos.slot * RQ_SLOT;
+                const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));   // blocks in this record (the last segment may be short)
                 uint2 qa[2], qb[2];
                 float da[2], db[2];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const uint32_t bl = warp * 2 + j;   // block inside the slot
-                    qa[j] = *reinterpret_cast<const uint2 *>(sl + g * RQ_SEGK + bl * 32 + t * 8);          // row g,     8 int8
-                    qb[j] = *reinterpret_cast<const uint2 *>(sl + (g + 8) * RQ_SEGK + bl * 32 + t * 8);    // row g + 8
-                    da[j] = *reinterpret_cast<const float *>(sl + RQ_QBYTES + (g * (RQ_SEGK / 32) + bl) * 4);
-                    db[j] = *reinterpret_cast<const float *>(sl + RQ_QBYTES + ((g + 8) * (RQ_SEGK / 32) + bl) * 4);
+                    const uint32_t bl = warp * 2 + j;   // block inside the record: [bl][row][32 int8], scales [bl][row] after the nb int8 blocks
+                    const bool live = bl < nb;
+                    qa[j] = live ? *reinterpret_cast<const uint2 *>(sl + bl * RQ_BLKQ + g * 32 + t * 8) : make_uint2(0u, 0u);          // row g, 8 int8
+                    qb[j] = live ? *reinterpret_cast<const uint2 *>(sl + bl * RQ_BLKQ + (g + 8) * 32 + t * 8) : make_uint2(0u, 0u);    // row g + 8
+                    da[j] = live ? *reinterpret_cast<const float *>(sl + nb * RQ_BLKQ + (bl * RQ_ROWS + g) * 4) : 0.f;
+                    db[j] = live ? *reinterpret_cast<const float *>(sl + nb * RQ_BLKQ + (bl * RQ_ROWS + g + 8) * 4) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
@@ -510,7 +515,7 @@ __device__ __forceinline__ void attention_phase(const RQParams &p, const MegaLay
 
 // dynamic shared memory: [ring: n_slots x RQ_SLOT][xs: kpad floats, digit planes in place][xsc: kpad/32 floats][scores][RQShared]
 template <int HD>
-__global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQParams p, const __grid_constant__ RQMaps maps) {
+__global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots, kpad = p.kpad;
     uint8_t *ring = smem_raw;
@@ -542,12 +547,13 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         if (threadIdx.x != RQ_CTHREADS) return;   // one thread drives the copy engine
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
-            produce<1>(&maps.q_wqkv, &maps.d_wqkv, nullptr, nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.q_wo, &maps.d_wo, nullptr, nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
-            produce<2>(&maps.q_w1, &maps.d_w1, &maps.q_w3, &maps.d_w3, (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.q_w2, &maps.d_w2, nullptr, nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
+            const RingQ8Layer P = p.planes[li];
+            produce<1>(P.wqkv, nullptr, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(P.wo, nullptr, dim, dim, ph, pos, ring_base, sh, n_slots);
+            produce<2>(P.w1, P.w3, dim, ff, ph, pos, ring_base, sh, n_slots);
+            produce<1>(P.w2, nullptr, ff, dim, ph, pos, ring_base, sh, n_slots);
         }
-        if (p.final_norm) produce<1>(&maps.q_out, &maps.d_out, nullptr, nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(p.out_plane, nullptr, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
         return;
     }
     unsigned target = 0;
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
 }
 
 template <int HD>
-static cudaError_t launch(const RQParams &p, const RQMaps &maps, size_t smem, cudaStream_t st) {
+static cudaError_t launch(const RQParams &p, size_t smem, cudaStream_t st) {
     static bool attr[64] = {};  // function attributes are per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -625,7 +631,7 @@ static cudaError_t launch(const RQParams &p, const RQMaps &maps, size_t smem, cu
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_ring_q8_kernel<HD>, p, maps);
+    return cudaLaunchKernelEx(&cfg, decode_ring_q8_kernel<HD>, p);
 }
 
 static uint32_t q8_splits(uint32_t heads) {
@@ -645,24 +651,41 @@ static uint32_t q8_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx,
     return n;
 }
 
-// ---- interleaved planes (kernels_q8.cu) -> the row-major planes this kernel streams ---------------------------------
-__global__ void q8_to_row_major_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, int8_t *__restrict__ q_rm,
-                                       float *__restrict__ d_rm, uint32_t rows, uint32_t K) {
-    const size_t n4 = (size_t)rows * (K / 4), stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const uint32_t r = (uint32_t)(i / (K / 4)), k4 = (uint32_t)(i % (K / 4));
-        // interleaved: ((r / 4) * (K / 4) + k4) * 16 + (r % 4) * 4 bytes
-        reinterpret_cast<uint32_t *>(q_rm)[i] = *reinterpret_cast<const uint32_t *>(q + ((size_t)(r >> 2) * (K >> 2) + k4) * 16 + (r & 3) * 4);
-        if ((k4 & 7) == 0) d_rm[(size_t)r * (K / 32) + (k4 >> 3)] = d[((size_t)(r >> 2) * (K >> 5) + (k4 >> 3)) * 4 + (r & 3)];
+// ---- interleaved planes (kernels_q8.cu) -> the tile-major decode plane this kernel streams ------------------------------
+// plane = for tile (16 rows), for block b (32 columns): [16 rows][32 int8]; then per (tile, segment of 32 blocks) the
+// scales [blocks of the segment][16 rows] f32 FOLLOW the segment's int8 blocks:  record(tile, seg) at
+// (tile * K/32 + seg * 32) * 576 bytes = [nb][16][32] int8 | [nb][16] f32.  Rows >= `rows` of the last tile are zero.
+__global__ void q8_to_tile_major_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, uint8_t *__restrict__ plane,
+                                        uint32_t rows, uint32_t K) {
+    const uint32_t nblk = K / 32, ntiles = (rows + RQ_ROWS - 1) / RQ_ROWS;
+    const size_t n = (size_t)ntiles * nblk * RQ_ROWS * 8, stride = (size_t)gridDim.x * blockDim.x;   // one thread per (tile, block, row, 4-byte group)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k4 = (uint32_t)(i & 7), r = (uint32_t)((i >> 3) % RQ_ROWS);
+        const size_t tb = i / (8 * RQ_ROWS);
+        const uint32_t b = (uint32_t)(tb % nblk), tile = (uint32_t)(tb / nblk);
+        const uint32_t row = tile * RQ_ROWS + r, seg = b / (RQ_SEGK / 32), bl = b % (RQ_SEGK / 32);
+        const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
+        uint8_t *rec = plane + ((size_t)tile * nblk + (size_t)seg * (RQ_SEGK / 32)) * RQ_BLK;
+        uint32_t w = 0;
+        float sc = 0.f;
+        if (row < rows) {
+            const uint32_t kcol = b * 32 + k4 * 4;
+            w = *reinterpret_cast<const uint32_t *>(q + ((size_t)(row >> 2) * (K >> 2) + (kcol >> 2)) * 16 + (row & 3) * 4);
+            sc = d[((size_t)(row >> 2) * (K >> 5) + b) * 4 + (row & 3)];
+        }
+        *reinterpret_cast<uint32_t *>(rec + bl * RQ_BLKQ + r * 32 + k4 * 4) = w;
+        if (k4 == 0) *reinterpret_cast<float *>(rec + nb * RQ_BLKQ + (bl * RQ_ROWS + r) * 4) = sc;
     }
 }
 
 }  // namespace
 
-void q8_to_row_major(const int8_t *q, const float *d, int8_t *q_rm, float *d_rm, uint32_t rows, uint32_t K, cudaStream_t st) {
-    LB_CHECK(K % 32 == 0 && rows % 4 == 0, "q8_to_row_major: K must be a multiple of 32 and the row count a multiple of 4");
+size_t q8_tile_major_bytes(uint32_t rows, uint32_t K) { return (size_t)((rows + RQ_ROWS - 1) / RQ_ROWS) * (K / 32) * RQ_BLK; }
+
+void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t rows, uint32_t K, cudaStream_t st) {
+    LB_CHECK(K % 32 == 0 && rows % 4 == 0, "q8_to_tile_major: K must be a multiple of 32 and the row count a multiple of 4");
     if (!rows) return;
-    q8_to_row_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, q_rm, d_rm, rows, K);
+    q8_to_tile_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, plane, rows, K);
     LB_LAUNCH_CHECK();
 }
 
@@ -670,62 +693,17 @@ bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_
     if (heads == 0 || dim % heads || heads > (uint32_t)RQ_MAX_HEADS) return false;
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
-    if (dim % 32 || ff % 32 || dim < 256) return false;
-    (void)vocab;
+    if (dim % 32 || ff % 32 || dim < 256 || vocab % 16) return false;   // whole 16-row tiles, 32-column blocks
     return q8_plan(dim, ff, heads, ctx, nullptr, nullptr) >= 3;
 }
 
-static CUtensorMap q8_map(const void *base, CUtensorMapDataType dt, uint64_t inner, uint64_t rows, uint64_t layers, uint64_t layer_stride_elems,
-                          uint32_t box_inner) {
-    typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                            const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static PFN fn = nullptr;
-    if (!fn) {
-        void *pfn = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        LB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qr));
-        LB_CHECK(pfn != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-        fn = reinterpret_cast<PFN>(pfn);
-    }
-    CUtensorMap m;
-    cuuint64_t dims[3] = {inner, rows, layers};
-    cuuint64_t strides[2] = {inner * 4, (layers > 1 ? layer_stride_elems : inner * rows) * 4};
-    cuuint32_t box[3] = {box_inner, RQ_ROWS, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(&m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    LB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-    return m;
-}
-
-size_t ring_q8_maps_bytes() { return sizeof(RQMaps); }
-
-// q_rm / d_rm: row-major planes of layer 0's matrices in the order wqkv, wo, w1, w3, w2 (+ output); q/d layer strides in bytes / floats
-void ring_q8_make_maps(const RingQ8Planes &pl, uint32_t n_layers, uint32_t dim, uint32_t ff, uint32_t vocab, void *maps_out) {
-    LB_CHECK(maps_out && n_layers >= 1, "ring_q8_make_maps: nil argument");
-    LB_CHECK(pl.q_layer_stride % 4 == 0, "ring_q8_make_maps: q layer stride must be a multiple of 4 bytes");
-    RQMaps m;
-    auto qm = [&](const int8_t *q, uint64_t K, uint64_t rows, bool per_layer) {
-        return q8_map(q, CU_TENSOR_MAP_DATA_TYPE_UINT32, K / 4, rows, per_layer ? n_layers : 1, pl.q_layer_stride / 4, RQ_SEGK / 4);
-    };
-    auto dm = [&](const float *d, uint64_t K, uint64_t rows, bool per_layer) {
-        return q8_map(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, K / 32, rows, per_layer ? n_layers : 1, pl.d_layer_stride, RQ_SEGK / 32);
-    };
-    m.q_wqkv = qm(pl.q[0], dim, 3ull * dim, true); m.d_wqkv = dm(pl.d[0], dim, 3ull * dim, true);
-    m.q_wo = qm(pl.q[1], dim, dim, true);          m.d_wo = dm(pl.d[1], dim, dim, true);
-    m.q_w1 = qm(pl.q[2], dim, ff, true);           m.d_w1 = dm(pl.d[2], dim, ff, true);
-    m.q_w3 = qm(pl.q[3], dim, ff, true);           m.d_w3 = dm(pl.d[3], dim, ff, true);
-    m.q_w2 = qm(pl.q[4], ff, dim, true);           m.d_w2 = dm(pl.d[4], ff, dim, true);
-    if (pl.q[5]) { m.q_out = qm(pl.q[5], dim, vocab, false); m.d_out = dm(pl.d[5], dim, vocab, false); }
-    else { m.q_out = m.q_wo; m.d_out = m.d_wo; }
-    memcpy(maps_out, &m, sizeof(RQMaps));
-}
-
-void decode_ring_q8(const MegaParamsHost &h, const void *tmaps, cudaStream_t st) {
+void decode_ring_q8(const MegaParamsHost &h, const RingQ8Layer *planes_dev, const uint8_t *out_plane, cudaStream_t st) {
     LB_CHECK(decode_ring_q8_supported(h.dim, h.ff, h.heads, h.vocab, h.ctx), "decode_ring_q8: unsupported shape");
-    LB_CHECK(tmaps != nullptr, "decode_ring_q8: tensor maps missing (ring_q8_make_maps)");
+    LB_CHECK(planes_dev != nullptr, "decode_ring_q8: decode planes missing");
     RQParams p;
     p.layers = h.layers_dev;
+    p.planes = planes_dev;
+    p.out_plane = out_plane;
     p.n_layers = h.n_layers;
     p.tok_embeddings = h.tok_embeddings; p.tokens = h.tokens; p.state = h.state;
     p.final_norm = h.final_norm;
@@ -738,9 +716,8 @@ void decode_ring_q8(const MegaParamsHost &h, const void *tmaps, cudaStream_t st)
     p.n_slots = q8_plan(h.dim, h.ff, h.heads, h.ctx, &p.kpad, &smem);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
-    const RQMaps &maps = *static_cast<const RQMaps *>(tmaps);
     const uint32_t hd = h.dim / h.heads;
-    cudaError_t e = hd == 128 ? launch<128>(p, maps, smem, st) : hd == 64 ? launch<64>(p, maps, smem, st) : launch<32>(p, maps, smem, st);
+    cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);
     LB_CUDA(e);
     count_launch();
 }

@@ -44,7 +44,7 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     struct MOff { size_t f, q, d; };
     auto reserve_mat = [&](size_t n) {
         MOff o{0, 0, 0};
-        if (q8()) { o.q = qtotal; qtotal += align_up(n, 256); o.d = dtotal; dtotal += align_up(n / 32, A); }
+        if (q8()) { o.q = qtotal; qtotal += align_up(n, 512); o.d = dtotal; dtotal += align_up(n / 32, A); }   // 512 = one 16 x 32 tile block (tile-major plane offsets)
         else o.f = reserve(n);
         return o;
     };
@@ -64,15 +64,14 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
     if (q8()) {
         qslab = mem.dmalloc<int8_t>(qtotal);
         dslab = mem.dmalloc<float>(dtotal);
-        qslab_rm = mem.dmalloc<int8_t>(qtotal);
-        dslab_rm = mem.dmalloc<float>(dtotal);
+        tmslab = mem.dmalloc<uint8_t>(qtotal / 512 * 576 + 256);   // every matrix: (rows / 16) x (K / 32) records of 576 bytes
     }
     auto fptr = [&](const MOff &o) { return q8() ? nullptr : slab + o.f; };
     auto qmat = [&](const MOff &o, size_t row_off_elems = 0) {
         Q8Mat m;
         if (q8()) {
             m.q = qslab + o.q + row_off_elems; m.d = dslab + o.d + row_off_elems / 32;
-            m.q_rm = qslab_rm + o.q + row_off_elems; m.d_rm = dslab_rm + o.d + row_off_elems / 32;
+            m.tm = tmslab + (o.q + row_off_elems) / 512 * 576;   // (o.q and row offsets are multiples of 512 elements: 16 rows x 32 columns)
         }
         return m;
     };
@@ -135,7 +134,7 @@ void Model::set_tensor(const std::string &name, int dtype, const void *host, siz
     }
     if (quant) {
         k::quantize_q8(dst, e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
-        k::q8_to_row_major(e.q8.q, e.q8.d, e.q8.q_rm, e.q8.d_rm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+        if ((e.nelem / e.cols) % 16 == 0) k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
     }
     LB_CUDA(cudaDeviceSynchronize());
     if (tmp16) cudaFree(tmp16);
@@ -173,7 +172,7 @@ void Model::init_random(uint64_t seed) {
         if (e.q8.q) {
             k::init_random(static_cast<float *>(tmp), e.nelem, seed, e.tid, e.mean, sscale, 0);
             k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
-            k::q8_to_row_major(e.q8.q, e.q8.d, e.q8.q_rm, e.q8.d_rm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+            if ((e.nelem / e.cols) % 16 == 0) k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
         } else {
             k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
         }
@@ -239,23 +238,16 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
         }
         mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
-        mega_barrier = mem.dmalloc<unsigned>(2 + 4 * nl);  // grid barrier + per-phase ticket counters
+        mega_barrier = mem.dmalloc<unsigned>(4 + 4 * nl);  // grid barrier + per-phase ticket counters
         if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13 + 5 * 148);
         if (use_ring_q8) {
-            const Layer &L0 = m->layers[0];
-            k::RingQ8Planes pl = {};
-            const Q8Mat *mats[5] = {&L0.wqkv8, &L0.wo8, &L0.w18, &L0.w38, &L0.w28};
-            for (int i = 0; i < 5; i++) { pl.q[i] = mats[i]->q_rm; pl.d[i] = mats[i]->d_rm; }
-            pl.q[5] = m->has_head() ? m->output8.q_rm : nullptr;
-            pl.d[5] = m->has_head() ? m->output8.d_rm : nullptr;
-            if (nl > 1) {
-                pl.q_layer_stride = (uint64_t)(m->layers[1].wqkv8.q_rm - L0.wqkv8.q_rm);
-                pl.d_layer_stride = (uint64_t)(m->layers[1].wqkv8.d_rm - L0.wqkv8.d_rm);
+            std::vector<k::RingQ8Layer> pl(nl);
+            for (size_t i = 0; i < nl; i++) {
+                const Layer &L = m->layers[i];
+                pl[i] = {L.wqkv8.tm, L.wo8.tm, L.w18.tm, L.w38.tm, L.w28.tm};
             }
-            q8_tmaps.resize(k::ring_q8_maps_bytes() + 64);
-            void *al = reinterpret_cast<void *>(((uintptr_t)q8_tmaps.data() + 63) & ~(uintptr_t)63);
-            k::ring_q8_make_maps(pl, (uint32_t)nl, hp.dim, hp.ff(), hp.vocab, al);
-            q8_tmaps_ptr = al;
+            q8_planes_dev = mem.dmalloc<k::RingQ8Layer>(nl, false);
+            LB_CUDA(cudaMemcpy(q8_planes_dev, pl.data(), nl * sizeof(k::RingQ8Layer), cudaMemcpyHostToDevice));
         }
     }
 }
@@ -326,7 +318,7 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
             mp.p2p_x_out = p2p_x_out; mp.p2p_flag_out = p2p_flag_out; mp.p2p_ack_out = p2p_ack_out;
         }
         mp.dim = d; mp.ff = ff; mp.heads = H; mp.vocab = V; mp.ctx = ctx_size;
-        if (use_ring_q8) k::decode_ring_q8(mp, q8_tmaps_ptr, st);
+        if (use_ring_q8) k::decode_ring_q8(mp, static_cast<const k::RingQ8Layer *>(q8_planes_dev), model->has_head() ? model->output8.tm : nullptr, st);
         else if (use_ring) k::decode_ring(mp, st);
         else k::decode_mega(mp, st);
         if (hidden_out && hidden_out != x)

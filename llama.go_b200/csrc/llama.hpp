@@ -19,12 +19,11 @@ struct HParams {  // llama.go:149-158
     uint32_t head_dim() const { return dim / heads; }
 };
 
-struct Q8Mat {  // Q8_0 planes of one matrix: 4-row-interleaved (kernels_q8.cu: per-op GEMV, tcgen05 GEMM) and a
-                // row-major copy q_rm[M][K] int8, d_rm[M][K/32] float streamed by the decode ring (kernels_ring_q8.cu)
+struct Q8Mat {  // Q8_0 planes of one matrix: 4-row-interleaved q / d (kernels_q8.cu: per-op GEMV, tcgen05 GEMM) and the
+                // tile-major decode plane streamed by the ring megakernel (kernels_ring_q8.cu: q8_to_tile_major)
     int8_t *q = nullptr;
     float *d = nullptr;
-    int8_t *q_rm = nullptr;
-    float *d_rm = nullptr;
+    uint8_t *tm = nullptr;
 };
 
 struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] matrix
@@ -52,8 +51,7 @@ struct Model {
     Q8Mat output8;
     int8_t *qslab = nullptr;  // Q8_0: int8 plane of every MulMat matrix of the stage
     float *dslab = nullptr;   //       and the per-block scales
-    int8_t *qslab_rm = nullptr;  // the same planes row-major (decode ring)
-    float *dslab_rm = nullptr;
+    uint8_t *tmslab = nullptr;   // the same matrices as tile-major decode planes (ring megakernel)
     std::vector<Layer> layers;  // index = global layer - layer_begin
     bool q8() const { return weight_type == 16; }
 
@@ -87,8 +85,7 @@ struct Context {
     bool use_mega = false;             // single-token forward = one persistent cooperative kernel
     bool use_ring = false;             // ... the TMA-ring variant (kernels_ring.cu) instead of the register-fed one
     bool use_ring_q8 = false;          // Q8_0 weights: TMA ring + int8 tensor cores (kernels_ring_q8.cu)
-    std::vector<uint8_t> q8_tmaps;     // its tensor maps (k::ring_q8_make_maps)
-    const void *q8_tmaps_ptr = nullptr;
+    void *q8_planes_dev = nullptr;     // k::RingQ8Layer[local layers]
     float *logits = nullptr;       // [vocab] (last row)
     float *all_logits = nullptr;   // [max_batch][vocab], allocated on first use
     uint32_t *tokens_dev = nullptr;  // [max_batch + resident window]
