@@ -157,6 +157,7 @@ __device__ __forceinline__ uint32_t chunk_floats(uint32_t K, uint32_t nch) { ret
 // per barrier for the slow ones: 203 vs 214 tok/s, profiles/README.md r02h).  Job j of the phase (in issue order) is
 // consumed by warp j % 16; its row number travels in sh.jobrow[]; the producer ends the phase by publishing the job count.
 constexpr unsigned RG_STATIC_NUM = 3, RG_STATIC_DEN = 4;
+constexpr unsigned RG_TICKET_ROWS = 4;   // rows per ticket; two tickets are kept in flight (an L2 atomic round trip is ~4 row times)
 
 // ---------------------------------------------------------------------------------------------------------
 // producer (one thread)
@@ -187,12 +188,13 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
         }
         njobs++;
     };
-    unsigned t = atomicAdd(ticket, 1u);                         // first ticket on its way while the static rows stream
+    unsigned ta = atomicAdd(ticket, 1u), tb = atomicAdd(ticket, 1u);   // two tickets on their way while the static rows stream
     for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
-    while ((uint64_t)pool0 + t < M) {
-        const uint32_t row = pool0 + t;
-        t = atomicAdd(ticket, 1u);                              // next ticket, overlapped with this row's copies
-        job(row);
+    while ((uint64_t)pool0 + (uint64_t)ta * RG_TICKET_ROWS < M) {
+        const uint32_t rb = pool0 + ta * RG_TICKET_ROWS, re = min(M, rb + RG_TICKET_ROWS);
+        ta = tb;
+        tb = atomicAdd(ticket, 1u);                             // next ticket, overlapped with these rows' copies
+        for (uint32_t row = rb; row < re; row++) job(row);
     }
     // end of phase: the job count for the consumers
     *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]) = (unsigned short)njobs;
@@ -220,12 +222,15 @@ __device__ __forceinline__ void consume(uint32_t K, const float *xs, float *out,
             const long long t0 = clock64();
             bool have = false;
             while (true) {
-                if (*reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) == q / n_slots) { have = true; break; }
+                const bool inst = *reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) == q / n_slots;
+                // (read AFTER the epoch: the producer publishes a phase's job count before it installs anything of the next
+                //  phase, so an installed slot number q that belongs to the NEXT phase is always seen together with the count)
                 const unsigned dj = *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]);
                 if (dj != 0xFFFFu) {
                     njobs = dj;
                     if (j >= njobs) break;
                 }
+                if (inst) { have = true; break; }
                 if (clock64() - t0 > 4000000000LL) __trap();
             }
             if (!have) break;

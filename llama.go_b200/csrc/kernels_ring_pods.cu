@@ -46,7 +46,7 @@ constexpr int RP_MAX_SLOTS = 8;
 constexpr uint32_t RP_PASS_SEGS = 8;               // segments per K pass
 constexpr uint32_t RP_XS_F4 = RP_PASS_SEGS * 16 * 32;   // float4 slots of the activation stage (64 KB): [chunk][pod][t]
 constexpr int RP_MAX_ITEMS = 2 * kNumSMs + 64;
-constexpr int RP_MAX_TILES = 20;                   // 16-row tiles of a CTA per matrix (x2 for the w1/w3 pair)
+constexpr int RP_MAX_TILES = 16;                   // 16-row tiles of a CTA per matrix (x2 for the w1/w3 pair)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ccsync() { asm volatile("bar.sync 1, %0;" ::"n"(RP_CTHREADS) : "memory"); }   // consumers only
@@ -110,21 +110,22 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// one map per weight kind and box height: dims {K, rows, layers} with the model's layer stride; box {256, h, 1}, h = 1 << i.
-// A CTA's row block (balanced to one row) is fetched as full 16-row boxes plus the binary decomposition of the rest, so no
-// box ever brings rows the CTA does not use and no CTA owns more than one row more than another.
+// one map per weight kind: dims {K, rows, layers} with the model's layer stride; box {256, 16, 1}
 enum { RPK_WQKV = 0, RPK_WO, RPK_W1, RPK_W3, RPK_W2, RPK_OUT, RPK_KINDS };
 struct RPMaps {
-    CUtensorMap m[RPK_KINDS][5];
+    CUtensorMap m[RPK_KINDS];
 };
-// height of the next box of the row range [r, r1): 16 while at least 16 rows remain, then descending powers of two
-__device__ __forceinline__ uint32_t box_rows(uint32_t r, uint32_t r1) {
-    const uint32_t left = r1 - r;
-    return left >= RP_ROWS ? RP_ROWS : (1u << (31 - __clz(left)));
-}
-__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t &r0, uint32_t &r1) {
-    r0 = (uint32_t)(((uint64_t)M * blockIdx.x) / gridDim.x);
-    r1 = (uint32_t)(((uint64_t)M * (blockIdx.x + 1)) / gridDim.x);
+// Rows of an M-row matrix owned by this CTA in MulMat phase number `ph`: whole 16-row tiles (a TMA box never fetches rows
+// the CTA does not use — contiguous balanced row ranges wasted ~11 % of the stream on ragged last tiles), ceil(M/16) tiles
+// dealt out evenly; which CTAs get the extra tile rotates with the phase number, and the ring's run-ahead lets a CTA that
+// is short one tile start on the next phase's weights while the others finish.
+// (Measured and rejected, r02i: balanced-to-a-row ranges fetched as 16 + 8 + 4 + 2 + 1-row boxes — every box costs a full
+//  slot cycle whatever its height, the small ones made the short phases 2x slower: 941 vs 1239 tok/s at B = 8.)
+__device__ __forceinline__ void cta_tile_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
+    const uint32_t ntiles = (M + RP_ROWS - 1) / RP_ROWS;
+    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
+    r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RP_ROWS);
+    r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RP_ROWS);
 }
 
 struct RPParams {
@@ -186,26 +187,24 @@ struct RingPos {
 // producer: for K pass, for tile, for segment of the pass (, for matrix): one slot
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, RingPos &pos,
-                                        uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
+__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, uint32_t &ph,
+                                        RingPos &pos, uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
     uint32_t r0, r1;
-    cta_rows(M, r0, r1);
+    cta_tile_rows(M, ph++, r0, r1);
     const uint32_t nseg = K / RP_SEG;
     for (uint32_t s0 = 0; s0 < nseg; s0 += RP_PASS_SEGS) {
         const uint32_t s1 = min(s0 + RP_PASS_SEGS, nseg);
-        for (uint32_t tile = r0; tile < r1;) {
-            const uint32_t h = box_rows(tile, r1), hi = 31 - __clz(h);
+        for (uint32_t tile = r0; tile < r1; tile += RP_ROWS) {
             for (uint32_t seg = s0; seg < s1; seg++) {
 #pragma unroll
                 for (int m = 0; m < NM; m++) {
                     const uint32_t fb = smem_u32(&sh.full[pos.slot]);
                     mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
-                    mbar_expect_tx(fb, h * RP_PITCH);
-                    tma_load_3d(ring_base + pos.slot * RP_SLOT, (m == 0 ? mapA : mapB) + hi, fb, (int)(seg * RP_SEG), (int)tile, layer);
+                    mbar_expect_tx(fb, RP_SLOT);   // rows past the matrix end are zero-filled by the copy engine and still counted
+                    tma_load_3d(ring_base + pos.slot * RP_SLOT, m == 0 ? mapA : mapB, fb, (int)(seg * RP_SEG), (int)tile, layer);
                     pos.next(n_slots);
                 }
             }
-            tile += h;
         }
     }
 }
@@ -309,12 +308,12 @@ __device__ __forceinline__ void merge_stats(const RPParams &p, RPShared &sh) {
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI, int XMODE, int HD>
 __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsrc, uint32_t ldx, const float *wnorm,
-                                        float *out, uint32_t ldo, const float *res, uint32_t ldr, RingPos &pos,
+                                        float *out, uint32_t ldo, const float *res, uint32_t ldr, uint32_t &ph, RingPos &pos,
                                         const uint8_t *ring, float4 *xs, const RPParams &p, RPShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint32_t n_slots = p.n_slots, B = p.B;
     uint32_t r0, r1;
-    cta_rows(M, r0, r1);
+    cta_tile_rows(M, ph++, r0, r1);
     const uint32_t nseg = K / RP_SEG;
     const uint32_t npass = (nseg + RP_PASS_SEGS - 1) / RP_PASS_SEGS;
     const uint32_t wofs = (uint32_t)g * RP_PITCH + (uint32_t)warp * 64 + (uint32_t)t * 16;   // this lane's 16 B of row g inside a slot
@@ -323,8 +322,7 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsr
         const uint32_t s0 = ps * RP_PASS_SEGS, s1 = min(s0 + RP_PASS_SEGS, nseg);
         fill_pass<XMODE, HD>(xs, xsrc, ldx, wnorm, s0 * RP_SEG, (s1 - s0) * 16, p, sh);
         uint32_t tj = 0;
-        for (uint32_t tile = r0; tile < r1; tj++) {
-            const uint32_t bh = box_rows(tile, r1);   // rows of this box; the MMAs run on all 16 rows of the slot, rows >= bh are stale bytes
+        for (uint32_t tile = r0; tile < r1; tile += RP_ROWS, tj++) {
             float hh[NM][4], lh[NM][4], hl[NM][4];
 #pragma unroll
             for (int m = 0; m < NM; m++)
@@ -379,7 +377,7 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsr
                         if (NM == 2) sh.acc[RP_MAX_TILES + tj][threadIdx.x] = s3v;
                     }
                 }
-                if (ps + 1 == npass && (threadIdx.x >> 3) < bh && pod < B) {
+                if (ps + 1 == npass && row < r1 && pod < B) {
                     float v;
                     if (NM == 2) v = __fmul_rn(silu_ref(s1v), s3v);
                     else if (EPI == 1) v = __fadd_rn(s1v, __ldcg((res ? res + (size_t)pod * ldr : sh.xrow[pod]) + row));
@@ -389,7 +387,6 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsr
             }
             if (NM == 2) ccsync();   // single-buffered partials in the two-matrix phase
             else buf ^= 1;
-            tile += bh;
         }
         if (ps + 1 < npass) ccsync();   // every warp is done with this pass's activation stage before it is refilled
     }
@@ -558,16 +555,17 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
 
     RingPos pos;
     pos.slot = 0; pos.phase = 0;
+    uint32_t ph = 0;   // MulMat phase counter (rotates the tile assignment; identical on both sides)
     if (producer) {
         if (threadIdx.x != RP_CTHREADS) return;   // one thread drives the copy engine
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
-            produce<1>(maps.m[RPK_WQKV], nullptr, (int)li, dim, 3 * dim, pos, ring_base, sh, n_slots);
-            produce<1>(maps.m[RPK_WO], nullptr, (int)li, dim, dim, pos, ring_base, sh, n_slots);
-            produce<2>(maps.m[RPK_W1], maps.m[RPK_W3], (int)li, dim, ff, pos, ring_base, sh, n_slots);
-            produce<1>(maps.m[RPK_W2], nullptr, (int)li, ff, dim, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_WQKV], nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_WO], nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
+            produce<2>(&maps.m[RPK_W1], &maps.m[RPK_W3], (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_W2], nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
         }
-        if (p.final_norm) produce<1>(maps.m[RPK_OUT], nullptr, 0, dim, p.vocab, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(&maps.m[RPK_OUT], nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
         return;
     }
     unsigned target = 0;
@@ -586,7 +584,7 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         rms_scales(dim, B, sh);
         stamp(li, 1);
-        consume<1, 0, 1, HD>(dim, 3 * dim, nullptr, 0, L.attention_norm, p.qkv, 3 * dim, nullptr, 0, pos, ring, xs, p, sh);
+        consume<1, 0, 1, HD>(dim, 3 * dim, nullptr, 0, L.attention_norm, p.qkv, 3 * dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
@@ -598,9 +596,9 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         // ---- P3: wo + residual (llama.go:336-340)
         if (p.splits > 1) {
             merge_stats(p, sh);
-            consume<1, 1, 2, HD>(dim, dim, nullptr, 0, nullptr, p.y, dim, nullptr, 0, pos, ring, xs, p, sh);
+            consume<1, 1, 2, HD>(dim, dim, nullptr, 0, nullptr, p.y, dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         } else {
-            consume<1, 1, 0, HD>(dim, dim, p.attn, dim, nullptr, p.y, dim, nullptr, 0, pos, ring, xs, p, sh);
+            consume<1, 1, 0, HD>(dim, dim, p.attn, dim, nullptr, p.y, dim, nullptr, 0, ph, pos, ring, xs, p, sh);
         }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
@@ -610,12 +608,12 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         ccsync();
         rms_scales(dim, B, sh);
         stamp(li, 8);
-        consume<2, 0, 1, HD>(dim, ff, nullptr, 0, L.ffn_norm, p.act, ff, nullptr, 0, pos, ring, xs, p, sh);
+        consume<2, 0, 1, HD>(dim, ff, nullptr, 0, L.ffn_norm, p.act, ff, nullptr, 0, ph, pos, ring, xs, p, sh);
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366)
-        consume<1, 1, 0, HD>(ff, dim, p.act, ff, nullptr, p.x, dim, p.y, dim, pos, ring, xs, p, sh);
+        consume<1, 1, 0, HD>(ff, dim, p.act, ff, nullptr, p.x, dim, p.y, dim, ph, pos, ring, xs, p, sh);
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 12);
@@ -624,7 +622,7 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         rms_scales(dim, B, sh);
-        consume<1, 0, 1, HD>(dim, p.vocab, nullptr, 0, p.final_norm, p.logits, p.vocab, nullptr, 0, pos, ring, xs, p, sh);
+        consume<1, 0, 1, HD>(dim, p.vocab, nullptr, 0, p.final_norm, p.logits, p.vocab, nullptr, 0, ph, pos, ring, xs, p, sh);
     }
 }
 
@@ -669,7 +667,7 @@ bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint3
     if (hd != 128 && hd != 64 && hd != 32) return false;
     if (dim % RP_SEG || ff % RP_SEG) return false;
     const uint32_t max_m = (ff > vocab ? ff : vocab) > 3 * dim ? (ff > vocab ? ff : vocab) : 3 * dim;
-    if ((max_m / kNumSMs + 1) / RP_ROWS + 5 > (uint32_t)RP_MAX_TILES) return false;   // boxes of a CTA per matrix (acc[] rows)
+    if (((max_m + RP_ROWS - 1) / RP_ROWS + kNumSMs - 1) / kNumSMs > (uint32_t)RP_MAX_TILES) return false;   // acc[] rows
     if ((size_t)2 * ctx * sizeof(float) > (size_t)RP_XS_F4 * 16) return false;             // attention scores overlay the stage
     return pods_plan(nullptr) >= 3;
 }
@@ -705,7 +703,7 @@ void decode_ring_pods(const MegaPodsParamsHost &h, cudaStream_t st) {
 typedef CUresult (*PFN_encodeTiled_rp)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats, uint32_t box_h) {
+static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats) {
     static PFN_encodeTiled_rp fn = nullptr;
     if (!fn) {
         void *pfn = nullptr;
@@ -717,7 +715,7 @@ static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t
     CUtensorMap m;
     cuuint64_t dims[3] = {K, rows, layers};
     cuuint64_t strides[2] = {K * 4, (layers > 1 ? layer_stride_floats : K * rows) * 4};
-    cuuint32_t box[3] = {RP_SEG, box_h, 1};
+    cuuint32_t box[3] = {RP_SEG, RP_ROWS, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -739,15 +737,12 @@ void ring_pods_make_maps(const MegaLayerHost *L, uint32_t n_layers, uint32_t dim
     }
     LB_CHECK(stride >= 0 && (stride % 4) == 0, "ring_pods_make_maps: bad layer stride");
     RPMaps m;
-    for (int i = 0; i < 5; i++) {
-        const uint32_t h = 1u << i;
-        m.m[RPK_WQKV][i] = rp_map(L[0].wqkv, dim, 3ull * dim, n_layers, (uint64_t)stride, h);
-        m.m[RPK_WO][i] = rp_map(L[0].wo, dim, dim, n_layers, (uint64_t)stride, h);
-        m.m[RPK_W1][i] = rp_map(L[0].w1, dim, ff, n_layers, (uint64_t)stride, h);
-        m.m[RPK_W3][i] = rp_map(L[0].w3, dim, ff, n_layers, (uint64_t)stride, h);
-        m.m[RPK_W2][i] = rp_map(L[0].w2, ff, dim, n_layers, (uint64_t)stride, h);
-        m.m[RPK_OUT][i] = output ? rp_map(output, dim, vocab, 1, 0, h) : m.m[RPK_WO][i];
-    }
+    m.m[RPK_WQKV] = rp_map(L[0].wqkv, dim, 3ull * dim, n_layers, (uint64_t)stride);
+    m.m[RPK_WO] = rp_map(L[0].wo, dim, dim, n_layers, (uint64_t)stride);
+    m.m[RPK_W1] = rp_map(L[0].w1, dim, ff, n_layers, (uint64_t)stride);
+    m.m[RPK_W3] = rp_map(L[0].w3, dim, ff, n_layers, (uint64_t)stride);
+    m.m[RPK_W2] = rp_map(L[0].w2, ff, dim, n_layers, (uint64_t)stride);
+    m.m[RPK_OUT] = output ? rp_map(output, dim, vocab, 1, 0) : m.m[RPK_WO];
     memcpy(maps_out, &m, sizeof(RPMaps));
 }
 

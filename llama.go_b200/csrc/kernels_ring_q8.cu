@@ -182,36 +182,112 @@ __device__ __forceinline__ void produce(const uint8_t *PA, const uint8_t *PB, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// activation vector (FP32, in xs) -> IN PLACE digit planes: block b's 32 floats (128 bytes) become its four digit planes
-// dig[(b * 4 + plane) * 32 + k % 32] (the same 128 bytes), block scales in xsc[b]; blocks up to kp/32, columns >= K are zero.
-// One warp per block, one lane per element.
+// Activation vector -> digit planes.  A 32-value block of x becomes four int8 planes relative to the block's power-of-two
+// scale s = 2^e (max|x| / s in [0.5, 1)):  x = s * (d0/2^6 + d1/2^13 + d2/2^20 + d3/2^27) +- s * 2^-28, |d_i| <= 64.
+// dig[(b * 4 + plane) * 32 + k % 32], xsc[b] = s.  One warp per block, one lane per element, everything in registers
+// (the first version staged the FP32 vector in shared memory and converted it in a second sweep: ~4 us per phase).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void make_digits(float *xs, uint32_t K, uint32_t kp, float *xsc) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int8_t *dig = reinterpret_cast<int8_t *>(xs);
-    for (uint32_t b = warp; b < kp / 32; b += RQ_CWARPS) {
-        const uint32_t kk = b * 32 + lane;
-        const float v = kk < K ? xs[kk] : 0.f;
-        const float m = warp_max(fabsf(v));      // (also orders every lane's read of the block before the writes below)
-        // block scale s = 2^e with max|v| / s in [0.5, 1): exponent arithmetic on the bits (frexpf / ldexpf cost ~2.5 us per
-        // phase here); a block whose maximum is zero or denormal is sent as zeros (|v| < 1.2e-38)
-        const uint32_t E = (__float_as_uint(m) >> 23) & 0xFFu;
-        const float s = E ? __uint_as_float((E + 1u) << 23) : 1.0f, inv = E ? __uint_as_float((253u - E) << 23) : 0.0f;
-        float r = __fmul_rn(v, inv);                   // exact (power of two)
-        int d[4];
-        r = __fmul_rn(r, 64.0f);
-        d[0] = __float2int_rn(r); r = __fsub_rn(r, (float)d[0]);
-#pragma unroll
-        for (int i = 1; i < 4; i++) {
-            r = __fmul_rn(r, 128.0f);
-            d[i] = __float2int_rn(r);
-            r = __fsub_rn(r, (float)d[i]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; i++) dig[(b * 4 + i) * 32 + lane] = (int8_t)d[i];
-        if (lane == 0) xsc[b] = s;
+__device__ __forceinline__ void emit_block(uint32_t b, float v, int lane, int8_t *dig, float *xsc) {
+    const float m = warp_max(fabsf(v));
+    // exponent arithmetic on the bits; a block whose maximum is zero or denormal is sent as zeros (|v| < 1.2e-38)
+    const uint32_t E = (__float_as_uint(m) >> 23) & 0xFFu;
+    const float s = E ? __uint_as_float((E + 1u) << 23) : 1.0f, inv = E ? __uint_as_float((253u - E) << 23) : 0.0f;
+    float r = __fmul_rn(__fmul_rn(v, inv), 64.0f);   // exact (powers of two)
+    int d0 = __float2int_rn(r); r = __fsub_rn(r, (float)d0);
+    r = __fmul_rn(r, 128.0f);
+    int d1 = __float2int_rn(r); r = __fsub_rn(r, (float)d1);
+    r = __fmul_rn(r, 128.0f);
+    int d2 = __float2int_rn(r); r = __fsub_rn(r, (float)d2);
+    r = __fmul_rn(r, 128.0f);
+    int d3 = __float2int_rn(r);
+    int8_t *o = dig + (size_t)b * 128 + lane;
+    o[0] = (int8_t)d0; o[32] = (int8_t)d1; o[64] = (int8_t)d2; o[96] = (int8_t)d3;
+    if (lane == 0) xsc[b] = s;
+}
+__device__ __forceinline__ void zero_blocks(uint32_t b0, uint32_t b1, int8_t *dig, float *xsc) {   // padding columns of the last segment
+    for (uint32_t i = b0 * 32 + threadIdx.x; i < b1 * 32; i += RQ_CTHREADS) {
+        reinterpret_cast<uint32_t *>(dig)[i] = 0u;
+        if ((i & 31) == 0) xsc[i >> 5] = 1.0f;
     }
+}
+// digits of  w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
+__device__ __forceinline__ void norm_digits(const float *x, const float *w, uint32_t K, uint32_t kp, int8_t *dig, float *xsc, RQShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NB = 16;   // blocks per warp kept in registers (K <= 8192); the rest is re-read
+    const uint32_t nblk = K / 32;
+    float v[NB];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const uint32_t b = warp + i * RQ_CWARPS;
+        v[i] = b < nblk ? __ldcg(x + (size_t)b * 32 + lane) : 0.f;
+        acc += (double)__fmul_rn(v[i], v[i]);
+    }
+    for (uint32_t b = warp + NB * RQ_CWARPS; b < nblk; b += RQ_CWARPS) {
+        const float u = __ldcg(x + (size_t)b * 32 + lane);
+        acc += (double)__fmul_rn(u, u);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sh.red[warp] = acc;
+    ccsync();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RQ_CWARPS; i++) t += sh.red[i];
+    const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const uint32_t b = warp + i * RQ_CWARPS;
+        if (b < nblk) emit_block(b, __fmul_rn(__ldg(w + (size_t)b * 32 + lane), __fmul_rn(v[i], sc)), lane, dig, xsc);
+    }
+    for (uint32_t b = warp + NB * RQ_CWARPS; b < nblk; b += RQ_CWARPS)
+        emit_block(b, __fmul_rn(__ldg(w + (size_t)b * 32 + lane), __fmul_rn(__ldcg(x + (size_t)b * 32 + lane), sc)), lane, dig, xsc);
+    zero_blocks(nblk, kp / 32, dig, xsc);
+    ccsync();   // also orders sh.red against its next use
+}
+__device__ __forceinline__ void plain_digits(const float *x, uint32_t K, uint32_t kp, int8_t *dig, float *xsc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nblk = K / 32;
+    for (uint32_t b = warp; b < nblk; b += RQ_CWARPS) emit_block(b, __ldcg(x + (size_t)b * 32 + lane), lane, dig, xsc);
+    zero_blocks(nblk, kp / 32, dig, xsc);
+    ccsync();
+}
+// digits of the merged attention output (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
+template <int HD>
+__device__ __forceinline__ void merge_digits(const RQParams &p, uint32_t kp, int8_t *dig, float *xsc, RQShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = p.splits, items = p.heads * S;
+    for (uint32_t i = threadIdx.x; i < items; i += RQ_CTHREADS) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
+        sh.mrg_m[i] = ml.x;
+        sh.mrg_l[i] = ml.y;
+    }
+    ccsync();
+    for (uint32_t h = threadIdx.x; h < p.heads; h += RQ_CTHREADS) {
+        float M = -INFINITY;
+        for (uint32_t s2 = 0; s2 < S; s2++) M = fmaxf(M, sh.mrg_m[h * S + s2]);
+        float Lsum = 0.f;
+        for (uint32_t s2 = 0; s2 < S; s2++) {
+            const float l = sh.mrg_l[h * S + s2];
+            float wgt = 0.f;
+            if (l > 0.f) {
+                wgt = expf(__fsub_rn(sh.mrg_m[h * S + s2], M));
+                Lsum = fmaf(l, wgt, Lsum);
+            }
+            sh.mrg_w[h * S + s2] = wgt;
+        }
+        sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
+    }
+    ccsync();
+    const uint32_t nblk = p.dim / 32;
+    for (uint32_t b = warp; b < nblk; b += RQ_CWARPS) {
+        const uint32_t e = b * 32 + lane, h = e / HD, d = e % HD;   // a 32-element block never straddles heads (HD >= 32)
+        const float *po = p.part_o + (size_t)h * S * HD + d;
+        float o = 0.f;
+        for (uint32_t s2 = 0; s2 < S; s2++)
+            if (sh.mrg_l[h * S + s2] > 0.f) o = fmaf(__ldcg(po + (size_t)s2 * HD), sh.mrg_w[h * S + s2], o);
+        emit_block(b, __fmul_rn(o, sh.mrg_inv[h]), lane, dig, xsc);
+    }
+    zero_blocks(nblk, kp / 32, dig, xsc);
     ccsync();
 }
 
@@ -221,13 +297,12 @@ __device__ __forceinline__ void make_digits(float *xs, uint32_t K, uint32_t kp, 
 // across the 16 warps per tile in a fixed order.
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI>
-__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs_dig, const float *xsc, float *out, const float *res,
+__device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *dig, const float *xsc, float *out, const float *res,
                                         uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     uint32_t r0, r1;
     cta_tile_rows(M, ph++, r0, r1);
     const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
-    const int8_t *dig = reinterpret_cast<const int8_t *>(xs_dig);
     // digit weights of this lane's two D columns (2t, 2t + 1): digits 0..3 live in columns 0..3, columns 4..7 are zero planes
     const float w0 = t == 0 ? 0.015625f : (t == 1 ? 9.5367431640625e-07f : 0.f);            // 2^-6, 2^-20
     const float w1 = t == 0 ? 1.220703125e-04f : (t == 1 ? 7.450580596923828e-09f : 0.f);   // 2^-13, 2^-27
@@ -304,89 +379,6 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xs_
         }
         ccsync();   // part[] is reused by the next tile
     }
-}
-
-// ---- activation vector of a phase -> shared memory -----------------------------------------------------------
-// y = w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
-__device__ __forceinline__ void fill_norm(float *xs, const float *x, const float *w, uint32_t K, RQShared &sh) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    double acc = 0.0;
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) {
-        const float4 v = ldcg4(x + (size_t)f * 4);
-        x4[f] = v;
-        acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
-        acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) sh.red[warp] = acc;
-    ccsync();
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < RQ_CWARPS; i++) t += sh.red[i];
-    const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) {
-        const float4 v = x4[f];
-        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + f);
-        x4[f] = make_float4(__fmul_rn(ww.x, __fmul_rn(v.x, sc)), __fmul_rn(ww.y, __fmul_rn(v.y, sc)),
-                            __fmul_rn(ww.z, __fmul_rn(v.z, sc)), __fmul_rn(ww.w, __fmul_rn(v.w, sc)));
-    }
-    ccsync();   // also orders sh.red against its next use
-}
-__device__ __forceinline__ void fill_plain(float *xs, const float *x, uint32_t K) {
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RQ_CTHREADS) x4[f] = ldcg4(x + (size_t)f * 4);
-    ccsync();
-}
-// merge of the attention splits (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
-template <int HD>
-__device__ __forceinline__ void fill_merge(float *xs, const RQParams &p, RQShared &sh) {
-    const uint32_t S = p.splits, items = p.heads * S;
-    for (uint32_t i = threadIdx.x; i < items; i += RQ_CTHREADS) {
-        const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
-        sh.mrg_m[i] = ml.x;
-        sh.mrg_l[i] = ml.y;
-    }
-    ccsync();
-    for (uint32_t h = threadIdx.x; h < p.heads; h += RQ_CTHREADS) {
-        float M = -INFINITY;
-        for (uint32_t s = 0; s < S; s++) M = fmaxf(M, sh.mrg_m[h * S + s]);
-        float Lsum = 0.f;
-        for (uint32_t s = 0; s < S; s++) {
-            const float l = sh.mrg_l[h * S + s];
-            float wgt = 0.f;
-            if (l > 0.f) {
-                wgt = expf(__fsub_rn(sh.mrg_m[h * S + s], M));
-                Lsum = fmaf(l, wgt, Lsum);
-            }
-            sh.mrg_w[h * S + s] = wgt;
-        }
-        sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
-    }
-    ccsync();
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    constexpr int MB = 12;
-    for (uint32_t f = threadIdx.x; f < p.dim / 4; f += RQ_CTHREADS) {
-        const uint32_t e = f * 4, h = e / HD, d = e % HD;
-        const float *po = p.part_o + (size_t)h * S * HD + d;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t s0 = 0; s0 < S; s0 += MB) {
-            float4 pv[MB];
-#pragma unroll
-            for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < MB; u++) {
-                if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
-                    const float wgt = sh.mrg_w[h * S + s0 + u];
-                    o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
-                    o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
-                }
-            }
-        }
-        const float inv = sh.mrg_inv[h];
-        x4[f] = make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv));
-    }
-    ccsync();
 }
 
 // ---- attention phase: identical to kernels_mega.cu::attention_phase (items (head, split), two per CTA at a time)
@@ -520,7 +512,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots, kpad = p.kpad;
     uint8_t *ring = smem_raw;
     float *xs = reinterpret_cast<float *>(smem_raw + (size_t)n_slots * RQ_SLOT);
+    int8_t *dig = reinterpret_cast<int8_t *>(xs);   // digit planes: 4 bytes per column, [block][plane][32]
     float *xsc = xs + kpad;
+    const uint32_t kp_dim = (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, kp_ff = (ff + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK;
     float *scores = xsc + kpad / 32;
     RQShared &sh = *reinterpret_cast<RQShared *>(scores + 2 * (size_t)((p.chunk_cap + 3) & ~3u));
     const bool producer = threadIdx.x >= RQ_CTHREADS;
@@ -571,10 +565,9 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         const MegaLayerHost L = p.layers[li];
         stamp(li, 0);
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
-        fill_norm(xs, xin, L.attention_norm, dim, sh);
-        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        norm_digits(xin, L.attention_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 1);
-        consume<1, 0>(dim, 3 * dim, xs, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots);
+        consume<1, 0>(dim, 3 * dim, dig, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots);
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
@@ -584,33 +577,29 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 5);
         // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
-        fill_merge<HD>(xs, p, sh);
-        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
-        consume<1, 1>(dim, dim, xs, xsc, p.y, xin, ph, pos, ring, sh, n_slots);
+        merge_digits<HD>(p, kp_dim, dig, xsc, sh);
+        consume<1, 1>(dim, dim, dig, xsc, p.y, xin, ph, pos, ring, sh, n_slots);
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
-        fill_norm(xs, p.y, L.ffn_norm, dim, sh);
-        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
+        norm_digits(p.y, L.ffn_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 8);
-        consume<2, 0>(dim, ff, xs, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots);
+        consume<2, 0>(dim, ff, dig, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots);
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366)
-        fill_plain(xs, p.act, ff);
-        make_digits(xs, ff, (ff + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
-        consume<1, 1>(ff, dim, xs, xsc, p.x, p.y, ph, pos, ring, sh, n_slots);
+        plain_digits(p.act, ff, kp_ff, dig, xsc);
+        consume<1, 1>(ff, dim, dig, xsc, p.x, p.y, ph, pos, ring, sh, n_slots);
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 12);
         xin = p.x;
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
-        fill_norm(xs, xin, p.final_norm, dim, sh);
-        make_digits(xs, dim, (dim + RQ_SEGK - 1) / RQ_SEGK * RQ_SEGK, xsc);
-        consume<1, 0>(dim, p.vocab, xs, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots);
+        norm_digits(xin, p.final_norm, dim, kp_dim, dig, xsc, sh);
+        consume<1, 0>(dim, p.vocab, dig, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots);
     }
 }
 
