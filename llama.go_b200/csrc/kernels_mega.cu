@@ -63,42 +63,63 @@ struct MegaShared {
     float mrg_m[MG_MAX_ITEMS], mrg_l[MG_MAX_ITEMS], mrg_w[MG_MAX_ITEMS], mrg_inv[MG_MAX_HEADS];
 };
 
-// ---- L2 prefetch of the rows this CTA will stream first in an upcoming GEMV phase (its static block starts at
-// row blockIdx.x * Q, see gemv_phase).  Issued by warp 1 BETWEEN the arrival and the wait of a grid barrier: HBM is
-// idle while the grid synchronises, and the prefetch must come after the arrival — thread 0's __threadfence()
-// before the arrival atomic waits for its warp's outstanding memory operations, so anything issued earlier delays
-// the arrival of this CTA and with it every other CTA (why the round-1 attempts showed no gain).
-struct MegaPrefetch {
-    const float *W = nullptr, *W3 = nullptr;
-    uint32_t M = 0, K = 0, bytes = 0;  // bytes: budget per matrix and CTA
-    bool all_static = false;           // the phase uses the contiguous M/grid split (gemv_phase all_static)
+// ---- shared-memory head start of the NEXT MulMat phase (round 2) ---------------------------------------------
+// HBM idles while the grid synchronises (~2 us per barrier + the RMSNorm prologue, ~8 us around the attention phase):
+// nothing the CTA has in flight survives a phase boundary.  Weights do not depend on anything computed in the
+// launch, so when a CTA has finished a phase, one thread issues cp.async.bulk copies (TMA engine, completion on an
+// mbarrier) of the first rows of the CTA's static block of the NEXT phase into the otherwise unused shared memory
+// (~190 KB: 12 rows of a 7B wq/wk/wv/wo, 2 x 6 rows of w1|w3, 4 rows of w2).  The copies are in flight during the
+// barrier, the attention phase and the prologue; the next phase consumes those rows from shared memory (same
+// K-slices, same arithmetic, LDS instead of LDG) at the END of its static part, so it never waits for them.
+// (L2 prefetch hints at the same place measured no gain, profiles/README.md r02a: the async proxy is not held up by
+// the polling thread's fences, and the bytes land where the consumer reads them at shared-memory speed.)
+struct MegaPre {
+    uint32_t buf;      // shared-memory address of the buffer (0: feature off)
+    uint32_t bar;      // shared-memory address of its mbarrier
+    uint32_t cap;      // bytes
 };
-__device__ __forceinline__ void l2_prefetch_rows(const MegaPrefetch &pf) {
-    if (!pf.W || threadIdx.x < 32 || threadIdx.x >= 64) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t Q = ((uint32_t)(((uint64_t)pf.M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
-    uint32_t first = blockIdx.x * Q;
-    if (pf.all_static) {
-        first = (uint32_t)(((uint64_t)pf.M * blockIdx.x) / gridDim.x);
-        Q = (uint32_t)(((uint64_t)pf.M * (blockIdx.x + 1)) / gridDim.x) - first;
+__device__ __forceinline__ uint32_t mg_static_rows(uint32_t M) {   // static rows per CTA of a phase (see gemv_phase)
+    return ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;
+}
+__device__ __forceinline__ uint32_t mg_pre_rows(const MegaPre &pre, uint32_t M, uint32_t K, uint32_t NM) {
+    if (!pre.buf) return 0;
+    uint32_t n = pre.cap / (K * 4u * NM);
+    const uint32_t Q = mg_static_rows(M);
+    if (n > Q) n = Q;
+    return n > (uint32_t)MG_ROWBLK ? (uint32_t)MG_ROWBLK : n;
+}
+// one thread: start the copies of the next phase's head rows (rows are adjacent in HBM: one copy per matrix row keeps
+// every copy <= 88 KB; >= 8 KB copies run at the full HBM rate from a single issuing thread, profiles/README.md r02f)
+__device__ __forceinline__ void mg_pre_issue(const MegaPre &pre, const float *W, const float *W3, uint32_t M, uint32_t K) {
+    const uint32_t NM = W3 ? 2u : 1u, n = mg_pre_rows(pre, M, K, NM);
+    if (!n) return;
+    const uint32_t r0 = blockIdx.x * mg_static_rows(M), rb = K * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pre.bar), "r"(n * rb * NM) : "memory");
+    for (uint32_t m = 0; m < NM; m++) {
+        const float *src = (m ? W3 : W) + (size_t)r0 * K;
+        for (uint32_t r = 0; r < n; r++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(pre.buf + (m * n + r) * rb), "l"(src + (size_t)r * K), "r"(rb), "r"(pre.bar) : "memory");
     }
-    const uint32_t row_bytes = pf.K * 4;
-    uint32_t rows = pf.bytes / row_bytes;
-    if (rows > Q) rows = Q;
-    const size_t total = (size_t)rows * row_bytes;  // contiguous: rows are row-major and adjacent
-    constexpr uint32_t CH = 8192;                    // bytes per prefetch instruction
-    const char *b1 = reinterpret_cast<const char *>(pf.W + (size_t)first * pf.K);
-    const char *b3 = pf.W3 ? reinterpret_cast<const char *>(pf.W3 + (size_t)first * pf.K) : nullptr;
-    for (size_t off = (size_t)lane * CH; off < total; off += 32 * CH) {
-        const uint32_t n = (uint32_t)(total - off < CH ? total - off : CH);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b1 + off), "r"(n) : "memory");
-        if (b3) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b3 + off), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mg_pre_wait(const MegaPre &pre, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(pre.bar), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: never hang the GPU
     }
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
 }
 
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr,
-                                             const MegaPrefetch &pf = MegaPrefetch()) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr) {
     target += nctas;
     csync();
     if (threadIdx.x == 0) {
@@ -110,7 +131,6 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
         __threadfence();
         atomicAdd(bar, 1u);
     }
-    l2_prefetch_rows(pf);  // warp 1; warp 0 polls
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_u32(bar) < target) {
@@ -190,33 +210,39 @@ __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ?
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
                                            const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr,
-                                           bool all_static = false) {
+                                           const MegaPre &pre, uint32_t &pre_parity) {
     constexpr int NM = SWIGLU ? 2 : 1;
     constexpr int RB = mg_rb(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t KS = K / MG_WARPS;
     const float *w1 = W + (size_t)warp * KS + lane * 4;
     const float *w3 = SWIGLU ? W3 + (size_t)warp * KS + lane * 4 : nullptr;
-    // all_static (experiment LB_MEGA_WO_STATIC, short phases): contiguous M/grid rows per CTA, no ticket pool — a
-    // 4-row ticket block is load -> wait -> compute -> sync with only 64 KB in flight (~56 % of the SM's HBM share),
-    // which costs a 10 us phase more than the ~7 % arrival skew of a static split.
-    const uint32_t Q = ((uint32_t)(((uint64_t)M * 4) / (5 * gridDim.x)) / MG_DYN_ROWS) * MG_DYN_ROWS;  // static rows per CTA
-    const uint32_t pool0 = all_static ? M : Q * gridDim.x;
-    if (threadIdx.x == 0) sh.ticket_slot[0] = all_static ? 0u : atomicAdd(ctr, 1u);  // latency hidden behind the static part
+    const uint32_t Q = mg_static_rows(M);  // static rows per CTA
+    const uint32_t pool0 = Q * gridDim.x;
+    const uint32_t npre = mg_pre_rows(pre, M, K, NM);   // the first npre static rows are (on their way) in shared memory
+    if (threadIdx.x == 0) sh.ticket_slot[0] = atomicAdd(ctr, 1u);  // latency hidden behind the static part
     int buf = 0;
-    // rows [rb, rb+nrb) -> partials -> combine -> out
-    auto do_block = [&](uint32_t rb, uint32_t nrb) {
+    // rows [rb, rb+nrb) -> partials -> combine -> out;  SM: the rows come from the head-start buffer (row rb = its row 0)
+    auto do_block = [&](auto from_smem, uint32_t rb, uint32_t nrb) {
+        constexpr bool SM = decltype(from_smem)::value;
+        const uint32_t s1 = pre.buf + ((uint32_t)warp * KS + lane * 4) * 4u, s3 = s1 + npre * K * 4u;
         for (uint32_t r = 0; r < nrb; r += RB) {
             float4 a[RB][NM][V];
 #pragma unroll
             for (int i = 0; i < RB; i++) {
                 const bool rok = r + i < nrb;
                 const size_t off = (size_t)(rb + r + i) * K;
+                const uint32_t soff = (r + i) * K * 4u;
 #pragma unroll
                 for (int j = 0; j < V; j++) {
                     const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
-                    a[i][0][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (SM) {
+                        a[i][0][j] = ok ? lds_f4(s1 + soff + j * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (SWIGLU) a[i][NM - 1][j] = ok ? lds_f4(s3 + soff + j * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        a[i][0][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (SWIGLU) a[i][NM - 1][j] = ok ? ld_stream_f4(w3 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
             }
 #pragma unroll
@@ -250,10 +276,15 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
         }
         buf ^= 1;  // the other partial buffer is used next; this one is reused only after the next csync
     };
-    // static part
-    uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
-    if (all_static) cta_rows(M, r0, r1);
-    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) do_block(rb, min((uint32_t)MG_ROWBLK, r1 - rb));
+    // static part: the rows that stream from HBM first, the head-start rows last (their copies have had the whole
+    // barrier + prologue + this loop to land)
+    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    for (uint32_t rb = r0 + npre; rb < r1; rb += MG_ROWBLK) do_block(std::false_type{}, rb, min((uint32_t)MG_ROWBLK, r1 - rb));
+    if (npre) {
+        mg_pre_wait(pre, pre_parity);
+        pre_parity ^= 1u;
+        do_block(std::true_type{}, r0, npre);   // its csync: every warp is done reading the buffer -> it may be refilled
+    }
     // dynamic pool
     int slot = 0;
     csync();  // ticket_slot[0] written by thread 0 is visible
@@ -261,75 +292,9 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
     while ((uint64_t)pool0 + (uint64_t)t * MG_DYN_ROWS < M) {
         const uint32_t rb = pool0 + t * MG_DYN_ROWS;
         if (threadIdx.x == 0) sh.ticket_slot[slot ^ 1] = atomicAdd(ctr, 1u);  // next ticket, overlapped with this block
-        do_block(rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
+        do_block(std::false_type{}, rb, min((uint32_t)MG_DYN_ROWS, M - rb));  // contains a csync after the loads: the slot write is visible after it
         slot ^= 1;
         t = sh.ticket_slot[slot];
-    }
-}
-
-// EXPERIMENT (LB_MEGA_WO_STATIC=2): a short single-matrix phase with the contiguous static split, software-pipelined:
-// two half-batches of rows live in registers, the loads of half-batch i+1 are issued before the arithmetic of
-// half-batch i, so 64-128 KB per SM are in flight at all times instead of a 128 KB burst followed by a bubble.
-// Same K-slices, same per-row arithmetic and the same combine as gemv_phase: identical results.
-template <int V>
-__device__ __forceinline__ void gemv_phase_static_pipelined(const float *__restrict__ W, uint32_t M, uint32_t K,
-                                                            const float4 (&xs)[V], float *out, const float *res, MegaShared &sh) {
-    constexpr int RBH = mg_rb(V, 1) >= 8 ? 3 : (mg_rb(V, 1) >= 2 ? mg_rb(V, 1) / 2 : 1);  // 4 rows x 2 buffers spill at the 128-register cap
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t KS = K / MG_WARPS;
-    const float *w1 = W + (size_t)warp * KS + lane * 4;
-    uint32_t r0, r1;
-    cta_rows(M, r0, r1);
-    float4 a[2][RBH][V];
-    auto issue = [&](auto bc, uint32_t row, uint32_t n) {
-        constexpr int b = decltype(bc)::value;
-#pragma unroll
-        for (int i = 0; i < RBH; i++) {
-            const bool rok = (uint32_t)i < n;
-            const size_t off = (size_t)(row + i) * K;
-#pragma unroll
-            for (int j = 0; j < V; j++) {
-                const bool ok = rok && (uint32_t)((j * 32 + lane) * 4) < KS;
-                a[b][i][j] = ok ? ld_stream_f4(w1 + off + j * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-    };
-    auto consume = [&](auto bc, uint32_t rel, uint32_t n, int buf) {
-        constexpr int b = decltype(bc)::value;
-#pragma unroll
-        for (int i = 0; i < RBH; i++) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < V; j++) {
-                acc = fmaf(a[b][i][j].x, xs[j].x, acc); acc = fmaf(a[b][i][j].y, xs[j].y, acc);
-                acc = fmaf(a[b][i][j].z, xs[j].z, acc); acc = fmaf(a[b][i][j].w, xs[j].w, acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0 && (uint32_t)i < n) sh.part[buf][0][rel + i][warp] = acc;
-        }
-    };
-    using B0 = std::integral_constant<int, 0>;
-    using B1 = std::integral_constant<int, 1>;
-    auto cnt = [](uint32_t total, uint32_t at) { return total > at ? (total - at < (uint32_t)RBH ? total - at : (uint32_t)RBH) : 0u; };
-    int buf = 0;
-    for (uint32_t rb = r0; rb < r1; rb += MG_ROWBLK) {
-        const uint32_t nrb = min((uint32_t)MG_ROWBLK, r1 - rb);
-        issue(B0{}, rb, cnt(nrb, 0));
-        for (uint32_t r = 0; r < nrb; r += 2 * RBH) {
-            if (r + RBH < nrb) issue(B1{}, rb + r + RBH, cnt(nrb, r + RBH));
-            consume(B0{}, r, cnt(nrb, r), buf);
-            if (r + 2 * RBH < nrb) issue(B0{}, rb + r + 2 * RBH, cnt(nrb, r + 2 * RBH));
-            if (r + RBH < nrb) consume(B1{}, r + RBH, cnt(nrb, r + RBH), buf);
-        }
-        csync();
-        if (threadIdx.x < nrb) {
-            float s1 = 0.f;
-#pragma unroll
-            for (int wv = 0; wv < MG_WARPS; wv++) s1 += sh.part[buf][0][threadIdx.x][wv];
-            const uint32_t row = rb + threadIdx.x;
-            out[row] = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
-        }
-        buf ^= 1;
     }
 }
 
@@ -353,8 +318,7 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
-    uint32_t prefetch;          // LB_MEGA_PF: L2 prefetch across grid barriers (A/B switch)
-    uint32_t wo_static;         // LB_MEGA_WO_STATIC: the wo phase uses the contiguous static split (A/B switch)
+    uint32_t pre_bytes;         // shared-memory head start of the next MulMat phase: buffer size (0: off, LB_MEGA_NO_PRE)
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -552,10 +516,12 @@ __device__ __forceinline__ void merged_attention_slice(const MegaParams &p, floa
     }
 }
 
+// dynamic shared memory: [scores: 2 x chunk_cap floats, padded to 128 B][head-start buffer: pre_bytes]
 template <int VD, int VF, int HD>
 __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
-    extern __shared__ float scores[];  // [2][chunk_cap]
+    extern __shared__ __align__(128) float scores[];  // [2][chunk_cap]
     __shared__ MegaShared sh;
+    __shared__ __align__(8) unsigned long long pre_bar;
     const uint32_t dim = p.dim, ff = p.ff;
     unsigned target = 0;
     const uint32_t past = p.state[0];
@@ -581,26 +547,32 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         sh.rope_cs[threadIdx.x][0] = cs;
         sh.rope_cs[threadIdx.x][1] = sn;
     }
+    MegaPre pre;
+    pre.cap = p.pre_bytes;
+    pre.bar = (uint32_t)__cvta_generic_to_shared(&pre_bar);
+    pre.buf = p.pre_bytes ? (uint32_t)__cvta_generic_to_shared(scores) + (((2 * p.chunk_cap * 4u) + 127u) & ~127u) : 0u;
+    uint32_t pre_parity = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pre.bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     csync();
+    // thread 32 (warp 1; thread 0 fences and polls in the grid barriers) starts the head-start copies
+    const bool pre_thread = threadIdx.x == 32;
+    if (pre_thread && p.n_layers) mg_pre_issue(pre, p.layers[0].wqkv, nullptr, 3 * dim, dim);
     unsigned *sched = p.barrier + 1;  // [n_layers * 4 + 1] ticket counters, zeroed with the barrier
-    const float *L_wo = nullptr;  // the current layer's wo (for the prefetch of an all-static wo phase)
-    auto pf = [&](const float *W, const float *W3, uint32_t M, uint32_t K, uint32_t bytes) {
-        MegaPrefetch f;
-        if (p.prefetch && W) { f.W = W; f.W3 = W3; f.M = M; f.K = K; f.bytes = bytes; f.all_static = p.wo_static && W == L_wo; }
-        return f;
-    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayer L = p.layers[li];
-        L_wo = L.wo;
         stamp(li, 0);
         {   // ---- P1: rmsnorm * attention_norm, then [wq;wk;wv] (llama.go:255-265)
             float4 xs[VD];
             rms_slice<VD>(xin, L.attention_norm, dim, xs, sh);
             stamp(li, 1);
-            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0);
+            gemv_phase<VD, false>(L.wqkv, nullptr, 3 * dim, dim, xs, p.qkv, nullptr, sh, sched + li * 4 + 0, pre, pre_parity);
         }
+        if (pre_thread) mg_pre_issue(pre, L.wo, nullptr, dim, dim);   // in flight under barrier 1, the attention phase, barrier 2
         stamp(li, 2);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0), pf(L.wo, nullptr, dim, dim, 512u << 10));  // all of wo's static rows, under the attention phase
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 0));
         stamp(li, 3);
         // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
@@ -610,37 +582,40 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[VD];
             merged_attention_slice<VD, HD>(p, xs, sh);
-            if (p.wo_static == 2) gemv_phase_static_pipelined<VD>(L.wo, dim, dim, xs, p.y, xin, sh);
-            else gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, p.wo_static != 0);
+            gemv_phase<VD, false>(L.wo, nullptr, dim, dim, xs, p.y, xin, sh, sched + li * 4 + 1, pre, pre_parity);
         }
+        if (pre_thread) mg_pre_issue(pre, L.w1, L.w3, ff, dim);
         stamp(li, 6);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2), pf(L.w1, L.w3, ff, dim, 64u << 10));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 2));
         stamp(li, 7);
         {   // ---- P4: rmsnorm * ffn_norm, silu(w1·)·(w3·) (llama.go:346-361)
             float4 xs[VD];
             rms_slice<VD>(p.y, L.ffn_norm, dim, xs, sh);
             stamp(li, 8);
-            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2);
+            gemv_phase<VD, true>(L.w1, L.w3, ff, dim, xs, p.act, nullptr, sh, sched + li * 4 + 2, pre, pre_parity);
         }
+        if (pre_thread) mg_pre_issue(pre, L.w2, nullptr, dim, ff);
         stamp(li, 9);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3), pf(L.w2, nullptr, dim, ff, 136u << 10));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 3));
         stamp(li, 10);
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
-            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3);
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3, pre, pre_parity);
+        }
+        if (pre_thread) {
+            if (li + 1 < p.n_layers) mg_pre_issue(pre, p.layers[li + 1].wqkv, nullptr, 3 * dim, dim);
+            else if (p.final_norm) mg_pre_issue(pre, p.output, nullptr, p.vocab, dim);
         }
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4),
-                     li + 1 < p.n_layers ? pf(p.layers[li + 1].wqkv, nullptr, 3 * dim, dim, 128u << 10)
-                                         : pf(p.output, nullptr, p.vocab, dim, 128u << 10));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
         stamp(li, 12);
         xin = p.x;
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384), row N-1 = the only row
         float4 xs[VD];
         rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
-        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4);
+        gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4, pre, pre_parity);
     }
 }
 
@@ -906,8 +881,23 @@ static bool pick_variant(uint32_t dim, uint32_t ff, uint32_t hd, int &vd, int &v
     return true;
 }
 
+template <int VD, int VF, int HD>
+static cudaError_t raise_smem_limit(size_t smem) {
+    static size_t set_for[64] = {};  // function attributes are per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || set_for[dev] < smem) {
+        e = cudaFuncSetAttribute(decode_mega_kernel<VD, VF, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) set_for[dev] = smem;
+    }
+    return cudaSuccess;
+}
 template <int VD, int VF>
 static cudaError_t launch_hd(const MegaParams &p, uint32_t hd, size_t smem, cudaStream_t st) {
+    cudaError_t ea = hd == 128 ? raise_smem_limit<VD, VF, 128>(smem) : hd == 64 ? raise_smem_limit<VD, VF, 64>(smem) : raise_smem_limit<VD, VF, 32>(smem);
+    if (ea != cudaSuccess) return ea;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNumSMs); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -979,12 +969,22 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     int vd, vf;
     const uint32_t hd = h.dim / h.heads;
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
-    const size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
+    size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
-    static const bool mega_pf = getenv("LB_MEGA_PF") != nullptr;  // round-2 experiment: A/B in one run
-    p.prefetch = mega_pf ? 1u : 0u;
-    static const uint32_t mega_wo_static = getenv("LB_MEGA_WO_STATIC") ? (uint32_t)atoi(getenv("LB_MEGA_WO_STATIC")) : 0u;
-    p.wo_static = mega_wo_static;  // 1: contiguous static split, 2: + software-pipelined half-batches
+    // head-start buffer: what is left of the SM's 227 KB next to the static shared memory (MegaShared) and the scores
+    static const bool no_pre = getenv("LB_MEGA_NO_PRE") != nullptr;   // A/B switch
+    static const uint32_t pre_kb = getenv("LB_MEGA_PRE_KB") ? (uint32_t)atoi(getenv("LB_MEGA_PRE_KB")) : 0u;   // profiling aid: smaller buffer
+    p.pre_bytes = 0;
+    if (!h.q8 && !no_pre) {
+        const size_t scores_pad = (smem + 127) & ~(size_t)127;
+        const size_t budget = 227 * 1024 - (sizeof(MegaShared) + 256);
+        if (scores_pad + 32 * 1024 <= budget) {
+            size_t pb = (budget - scores_pad) & ~(size_t)1023;
+            if (pre_kb && (size_t)pre_kb * 1024 < pb) pb = (size_t)pre_kb * 1024;
+            p.pre_bytes = (uint32_t)pb;
+            smem = scores_pad + pb;
+        }
+    }
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (2 + 4 * (size_t)h.n_layers), st));  // barrier + ticket counters
     cudaError_t e;
     if (h.q8) {  // experiment: Q8 megakernel (int8 tensor cores)

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int RG_CWARPS = 16;                      // consumer warps
 constexpr int RG_CTHREADS = RG_CWARPS * 32;        // 512
-constexpr int RG_THREADS = RG_CTHREADS + 32;       // + the producer warp
+constexpr int RG_THREADS = RG_CTHREADS + 64;       // + the producer warp + the L2 look-ahead warp
 constexpr int RG_HALF = RG_CTHREADS / 2;
 constexpr uint32_t RG_SLOT_FLOATS = 4096;          // one slot = one row (or a K chunk of a longer row): ONE bulk copy of <= 16 KB
 constexpr uint32_t RG_SLOT = RG_SLOT_FLOATS * 4;
@@ -91,6 +91,7 @@ struct RingParams {
     float *part_o, *part_ml;
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
+    uint32_t pf_bytes;            // L2 look-ahead of the prefetch warp beyond the ring, bytes per CTA (0: off)
     unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0
     // fused stage hand-off over NVLink peer memory (see MegaParamsHost)
     uint32_t *p2p_flags;          // local {in_flag, ack, seq}
@@ -103,6 +104,7 @@ struct RingShared {
     unsigned long long full[RG_MAX_SLOTS], empty[RG_MAX_SLOTS];
     unsigned epoch[RG_MAX_SLOTS];   // q / n_slots of the slot's current occupant (written by the producer before it arms full[])
     unsigned jobrow[RG_MAX_SLOTS];  // the output row the slot's bytes belong to
+    unsigned copied;                // nominal stream position of the producer (bytes of this CTA's share copied so far), read by the look-ahead warp
     unsigned short done_jobs[RG_MAX_PHASES];   // jobs of MulMat phase i of this launch (0xFFFF: the producer has not finished it)
     double red[RG_CWARPS];
     double rope_cs[64][2];
@@ -162,9 +164,12 @@ constexpr unsigned RG_TICKET_ROWS = 4;   // rows per ticket; two tickets are kep
 // ---------------------------------------------------------------------------------------------------------
 // producer (one thread)
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t phase_share_bytes(uint32_t K, uint32_t M, int NM) {   // one CTA's nominal share of a MulMat phase
+    return (uint32_t)(((uint64_t)M * K * 4ull * (uint64_t)NM) / gridDim.x);
+}
 template <int NM>
 __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t phidx, unsigned *ticket,
-                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots) {
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t &stream_pos) {
     const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
     const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));   // static rows per CTA
     const uint32_t pool0 = Q * gridDim.x;
@@ -187,6 +192,7 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
             }
         }
         njobs++;
+        *reinterpret_cast<volatile unsigned *>(&sh.copied) = stream_pos + njobs * K * 4u * (uint32_t)NM;
     };
     unsigned ta = atomicAdd(ticket, 1u), tb = atomicAdd(ticket, 1u);   // two tickets on their way while the static rows stream
     for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
@@ -199,6 +205,47 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
     // end of phase: the job count for the consumers
     *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]) = (unsigned short)njobs;
     __threadfence_block();
+    stream_pos += phase_share_bytes(K, M, NM);
+    *reinterpret_cast<volatile unsigned *>(&sh.copied) = stream_pos;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// L2 look-ahead (one thread of a second helper warp): walks the same schedule as the producer and keeps the next
+// pf_bytes of this CTA's share of the stream on their way from HBM into L2 (cp.async.bulk.prefetch.L2), beyond what
+// the ring can hold.  The ring covers ~3 us of stream; a grid barrier + the attention phase + the next barrier stop the
+// consumers for ~10 us, so without this HBM idles while the ring is full.  The prefetch stream of CTA c = its static
+// rows + the c-th share of the phase's ticket pool (whoever draws those rows later finds them in L2).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+template <int NM>
+__device__ __forceinline__ void lookahead(const float *W, const float *W3, uint32_t K, uint32_t M, RingShared &sh, uint32_t ring_bytes,
+                                          uint32_t pf_bytes, uint32_t &stream_pos) {
+    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
+    const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));
+    const uint32_t pool0 = Q * gridDim.x, P = M - pool0;
+    const uint32_t ps = pool0 + (uint32_t)(((uint64_t)P * blockIdx.x) / gridDim.x), pe = pool0 + (uint32_t)(((uint64_t)P * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t jb = K * 4u * (uint32_t)NM;
+    uint32_t pos = stream_pos;
+    auto job = [&](uint32_t row) {
+        pos += jb;
+        const long long t0 = clock64();
+        int32_t ahead;
+        while ((ahead = (int32_t)(pos - *reinterpret_cast<volatile unsigned *>(&sh.copied))) > (int32_t)pf_bytes) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        if (ahead <= (int32_t)ring_bytes) return;   // the copy engine is about to fetch (or has fetched) this row itself
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t k0 = c * CH, len = min(CH, K - k0);
+#pragma unroll
+            for (int m = 0; m < NM; m++) l2_prefetch((m == 0 ? W : W3) + (size_t)row * K + k0, len * 4);
+        }
+    };
+    for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
+    for (uint32_t row = ps; row < pe; row++) job(row);
+    stream_pos += phase_share_bytes(K, M, NM);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -528,6 +575,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
             mbar_init(smem_u32(&sh.empty[s]), 1);
             sh.epoch[s] = 0xFFFFFFFFu;
         }
+        sh.copied = 0;
         for (int i = 0; i < RG_MAX_PHASES; i++) sh.done_jobs[i] = 0xFFFFu;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -542,19 +590,34 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
 
     uint32_t pos = 0;   // slot counter (producer: next slot to fill; consumers: first slot of the current phase)
     if (producer) {
+        if (threadIdx.x == RG_CTHREADS + 32 && p.pf_bytes) {
+            // ================= look-ahead warp =================
+            const uint32_t ring_bytes = 2 * RG_SLOT;   // closer than this to the copy cursor: not worth a prefetch
+            uint32_t sp = 0;
+            for (uint32_t li = 0; li < p.n_layers; li++) {
+                const MegaLayerHost L = p.layers[li];
+                lookahead<1>(L.wqkv, nullptr, dim, 3 * dim, sh, ring_bytes, p.pf_bytes, sp);
+                lookahead<1>(L.wo, nullptr, dim, dim, sh, ring_bytes, p.pf_bytes, sp);
+                lookahead<2>(L.w1, L.w3, dim, ff, sh, ring_bytes, p.pf_bytes, sp);
+                lookahead<1>(L.w2, nullptr, ff, dim, sh, ring_bytes, p.pf_bytes, sp);
+            }
+            if (p.final_norm) lookahead<1>(p.output, nullptr, dim, p.vocab, sh, ring_bytes, p.pf_bytes, sp);
+            return;
+        }
         if (threadIdx.x != RG_CTHREADS) return;   // one thread drives the copy engine
+        uint32_t stream_pos = 0;
         // ================= producer warp: the whole token's weights of this CTA, in schedule order =================
         const uint32_t ring_base = smem_u32(ring);
         unsigned *tk = p.barrier + 2;   // one ticket counter per MulMat phase of the launch (zeroed with the barrier)
         uint32_t phidx = 0;
         for (uint32_t li = 0; li < p.n_layers; li++) {
             const MegaLayerHost L = p.layers[li];
-            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
-            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
-            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
-            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots); phidx++;
+            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
+            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
+            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
+            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
         }
-        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos);
         return;
     }
     // ================= consumers =================
@@ -697,6 +760,8 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
         const uint32_t n = (uint32_t)atoi(e);
         if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
     }
+    static const uint32_t pf_kb = getenv("LB_RING_PF_KB") ? (uint32_t)atoi(getenv("LB_RING_PF_KB")) : 0u;   // L2 look-ahead per SM
+    p.pf_bytes = pf_kb * 1024u;
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
     p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
