@@ -185,7 +185,7 @@ int lb_context_read_hidden(lb_context *c, uint32_t n, float *out) {
 }
 int lb_context_mega_trace(lb_context *c, uint64_t *out, uint32_t n) {
     LB_TRY_INT(LB_CHECK(c && out, "nil argument"); LB_CHECK(c->c->mega_trace != nullptr, "no trace (set LB_MEGA_TRACE=1 before creating the context)");
-               LB_CHECK(n <= c->c->model->layers.size() * 13 + 5 * 148, "trace: n too large");
+               LB_CHECK(n <= c->c->model->layers.size() * 13 + 13 * 148, "trace: n too large");
                LB_CUDA(cudaSetDevice(c->c->model->device)); LB_CUDA(cudaStreamSynchronize(c->c->stream));
                LB_CUDA(cudaMemcpy(out, c->c->mega_trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost)));
 }

@@ -152,7 +152,8 @@ struct RingQ8Layer {   // tile-major decode planes (q8_to_tile_major) of one lay
     const uint8_t *wqkv, *wo, *w1, *w3, *w2;
 };
 size_t q8_tile_major_bytes(uint32_t rows, uint32_t K);
-void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t rows, uint32_t K, cudaStream_t st);
+// rows [row0, row0 + nrows) of an M-row matrix (q/d: the 4-row-interleaved planes of THOSE rows) into the matrix's decode plane
+void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t M, uint32_t row0, uint32_t nrows, uint32_t K, cudaStream_t st);
 bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
 void decode_ring_q8(const MegaParamsHost &p, const RingQ8Layer *planes_dev, const uint8_t *out_plane, cudaStream_t st);
 

@@ -971,16 +971,17 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
-    // head-start buffer: what is left of the SM's 227 KB next to the static shared memory (MegaShared) and the scores
-    static const bool no_pre = getenv("LB_MEGA_NO_PRE") != nullptr;   // A/B switch
-    static const uint32_t pre_kb = getenv("LB_MEGA_PRE_KB") ? (uint32_t)atoi(getenv("LB_MEGA_PRE_KB")) : 0u;   // profiling aid: smaller buffer
+    // head-start buffer (opt-in, LB_MEGA_PRE_KB=<KB>): measured SLOWER than no buffer (profiles/README.md r02j: 180 tok/s with
+    // 196 KB, 217 with 96 KB, 221.5 without) — every MulMat phase streams slower once the shared-memory carve-out
+    // shrinks the L1 that the 128 KB of LDGs in flight per SM pass through, and the barriers grow with the copy traffic.
+    static const uint32_t pre_kb = getenv("LB_MEGA_PRE_KB") ? (uint32_t)atoi(getenv("LB_MEGA_PRE_KB")) : 0u;
     p.pre_bytes = 0;
-    if (!h.q8 && !no_pre) {
+    if (!h.q8 && pre_kb) {
         const size_t scores_pad = (smem + 127) & ~(size_t)127;
         const size_t budget = 227 * 1024 - (sizeof(MegaShared) + 256);
         if (scores_pad + 32 * 1024 <= budget) {
             size_t pb = (budget - scores_pad) & ~(size_t)1023;
-            if (pre_kb && (size_t)pre_kb * 1024 < pb) pb = (size_t)pre_kb * 1024;
+            if ((size_t)pre_kb * 1024 < pb) pb = (size_t)pre_kb * 1024;
             p.pre_bytes = (uint32_t)pb;
             smem = scores_pad + pb;
         }

@@ -131,10 +131,15 @@ __device__ __forceinline__ void p2p_wait(const unsigned *flag, unsigned want) {
 }
 
 // ---- grid barrier among the consumer threads of all CTAs (the producer warps never take part)
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, bool sys = false) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, bool sys = false, unsigned long long *arrive = nullptr) {
     target += nctas;
     ccsync();
     if (threadIdx.x == 0) {
+        if (arrive) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            arrive[blockIdx.x] = t;
+        }
         if (sys) __threadfence_system();   // this CTA's stores to the peer GPU are ordered before the hand-off flag
         else __threadfence();
         atomicAdd(bar, 1u);
@@ -169,7 +174,9 @@ __device__ __forceinline__ uint32_t phase_share_bytes(uint32_t K, uint32_t M, in
 }
 template <int NM>
 __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t phidx, unsigned *ticket,
-                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t &stream_pos) {
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t &stream_pos,
+                                        unsigned long long *pstat = nullptr) {
+    unsigned long long stall = 0;   // profiling aid (pstat != nullptr): ns this producer spent waiting for a free ring entry
     const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
     const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));   // static rows per CTA
     const uint32_t pool0 = Q * gridDim.x;
@@ -181,6 +188,13 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
             for (int m = 0; m < NM; m++) {
                 const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
                 const uint32_t fb = smem_u32(&sh.full[slot]);
+                if (pstat) {
+                    unsigned long long ta, tb;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ta));
+                    mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
+                    stall += tb - ta;
+                } else
                 mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // the consumer warp of slot q - n_slots released it
                 *reinterpret_cast<volatile unsigned *>(&sh.jobrow[slot]) = row;
                 __threadfence_block();
@@ -207,6 +221,7 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
     __threadfence_block();
     stream_pos += phase_share_bytes(K, M, NM);
     *reinterpret_cast<volatile unsigned *>(&sh.copied) = stream_pos;
+    if (pstat) { pstat[blockIdx.x] = stall; pstat[4 * gridDim.x + blockIdx.x] = njobs; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -612,10 +627,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         uint32_t phidx = 0;
         for (uint32_t li = 0; li < p.n_layers; li++) {
             const MegaLayerHost L = p.layers[li];
-            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
-            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
-            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
-            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos); phidx++;
+            // profiling aid: layer 5's producer stall time and job count per CTA and phase (after the 13 stamps per layer and the 5 x grid arrival stamps)
+            unsigned long long *ps = (p.trace && li == 5 && p.n_layers > 6) ? p.trace + (size_t)p.n_layers * 13 + 5 * (size_t)gridDim.x : nullptr;
+            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps); phidx++;
+            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + gridDim.x : nullptr); phidx++;
+            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + 2 * gridDim.x : nullptr); phidx++;
+            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + 3 * gridDim.x : nullptr); phidx++;
         }
         if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos);
         return;
@@ -646,6 +663,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
             tr[li * 13 + i] = t;
         }
     };
+    auto arr = [&](uint32_t li, int b) -> unsigned long long * {   // profiling aid: arrival time of every CTA at each of layer 5's barriers
+        return (p.trace && li == 5 && p.n_layers > 6) ? p.trace + (size_t)p.n_layers * 13 + (size_t)b * gridDim.x : nullptr;
+    };
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayerHost L = p.layers[li];
         stamp(li, 0);
@@ -654,31 +674,31 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         stamp(li, 1);
         consume<1, 0>(dim, xs, p.qkv, nullptr, pos, phidx++, ring, sh, n_slots);
         stamp(li, 2);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 0));
         stamp(li, 3);
         // ---- P2: RoPE, KV store, split attention partials (llama.go:274-333)
         attention_phase<HD>(p, L, past, sh, scores);
         stamp(li, 4);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 1));
         stamp(li, 5);
         // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
         fill_merge<HD>(xs, p, sh);
         consume<1, 1>(dim, xs, p.y, xin, pos, phidx++, ring, sh, n_slots);
         stamp(li, 6);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 2));
         stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         fill_norm(xs, p.y, L.ffn_norm, dim, sh);
         stamp(li, 8);
         consume<2, 0>(dim, xs, p.act, nullptr, pos, phidx++, ring, sh, n_slots);
         stamp(li, 9);
-        grid_barrier(p.barrier, target, gridDim.x);
+        grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 3));
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
         fill_plain(xs, p.act, ff);
         consume<1, 1>(ff, xs, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring, sh, n_slots);
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers);
+        grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers, arr(li, 4));
         stamp(li, 12);
         xin = p.x;
     }

@@ -110,22 +110,50 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// one map per weight kind: dims {K, rows, layers} with the model's layer stride; box {256, 16, 1}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// two maps per weight kind:
+//   m[]  dims {K, rows, layers} with the model's layer stride, box {256, 16, 1} — bounded by the matrix: rows past M are zero-filled;
+//   mc[] dims {K, R, nfull, layers}: the matrix seen as nfull chunks of R = ceil(M / 148) consecutive rows, box {256, 16, 1, 1} —
+//        bounded by the CHUNK: a box that hangs over the end of a CTA's chunk fetches only the chunk's rows (the copy engine
+//        zero-fills the rest without reading it), so a CTA can own a row range that is not a multiple of 16.
 enum { RPK_WQKV = 0, RPK_WO, RPK_W1, RPK_W3, RPK_W2, RPK_OUT, RPK_KINDS };
 struct RPMaps {
     CUtensorMap m[RPK_KINDS];
+    CUtensorMap mc[RPK_KINDS];
 };
-// Rows of an M-row matrix owned by this CTA in MulMat phase number `ph`: whole 16-row tiles (a TMA box never fetches rows
-// the CTA does not use — contiguous balanced row ranges wasted ~11 % of the stream on ragged last tiles), ceil(M/16) tiles
-// dealt out evenly; which CTAs get the extra tile rotates with the phase number, and the ring's run-ahead lets a CTA that
-// is short one tile start on the next phase's weights while the others finish.
-// (Measured and rejected, r02i: balanced-to-a-row ranges fetched as 16 + 8 + 4 + 2 + 1-row boxes — every box costs a full
-//  slot cycle whatever its height, the small ones made the short phases 2x slower: 941 vs 1239 tok/s at B = 8.)
-__device__ __forceinline__ void cta_tile_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
-    const uint32_t ntiles = (M + RP_ROWS - 1) / RP_ROWS;
+// Rows of an M-row matrix owned by this CTA in MulMat phase number `ph`.
+// Round-2 history (profiles/README.md): (1) contiguous balanced row ranges through the matrix-bounded map wasted ~11 % of the
+// stream on ragged last tiles (a box fetches all 16 rows); (2) whole 16-row tiles dealt out evenly fetch nothing twice, but
+// ceil vs mean is a whole tile per CTA and phase — 256 KB .. 700 KB, more than the ring can run ahead — and showed up as
+// 5-12 us of barrier wait per phase (r02i trace: 36 of 198 us per layer); (3) 16 + 8 + 4 + 2 + 1-row boxes: every box costs a
+// full slot cycle, 941 vs 1239 tok/s.  Now: every CTA owns R = ceil(M / grid) consecutive rows (balanced to one row), fetched
+// as 16-row boxes through the chunk-bounded map: the last box of a chunk reads only the rows that exist in the chunk.
+// The chunk -> CTA assignment rotates with the phase number (the one or two short chunks at the end move around).
+// Matrices with fewer than 16 rows per CTA (test models) keep the whole-tile split.
+struct RowPlan {
+    uint32_t r0, r1;      // rows [r0, r1)
+    uint32_t chunk;       // >= 0: index into the chunked map; 0xFFFFFFFF: use the matrix-bounded map with absolute rows
+};
+__device__ __forceinline__ RowPlan cta_rows_plan(uint32_t M, uint32_t ph) {
+    RowPlan rp;
     const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
-    r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RP_ROWS);
-    r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RP_ROWS);
+    if (M >= RP_ROWS * gridDim.x) {
+        const uint32_t R = (M + gridDim.x - 1) / gridDim.x, nfull = M / R;
+        rp.r0 = min(M, c * R);
+        rp.r1 = min(M, rp.r0 + R);
+        rp.chunk = c < nfull ? c : 0xFFFFFFFFu;
+    } else {
+        const uint32_t ntiles = (M + RP_ROWS - 1) / RP_ROWS;
+        rp.r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RP_ROWS);
+        rp.r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RP_ROWS);
+        rp.chunk = 0xFFFFFFFFu;
+    }
+    return rp;
 }
 
 struct RPParams {
@@ -187,10 +215,11 @@ struct RingPos {
 // producer: for K pass, for tile, for segment of the pass (, for matrix): one slot
 // ---------------------------------------------------------------------------------------------------------
 template <int NM>
-__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, int layer, uint32_t K, uint32_t M, uint32_t &ph,
+__device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorMap *mapB, const CUtensorMap *chunkA, const CUtensorMap *chunkB,
+                                        int layer, uint32_t K, uint32_t M, uint32_t &ph,
                                         RingPos &pos, uint32_t ring_base, RPShared &sh, uint32_t n_slots) {
-    uint32_t r0, r1;
-    cta_tile_rows(M, ph++, r0, r1);
+    const RowPlan rp = cta_rows_plan(M, ph++);
+    const uint32_t r0 = rp.r0, r1 = rp.r1;
     const uint32_t nseg = K / RP_SEG;
     for (uint32_t s0 = 0; s0 < nseg; s0 += RP_PASS_SEGS) {
         const uint32_t s1 = min(s0 + RP_PASS_SEGS, nseg);
@@ -201,7 +230,10 @@ __device__ __forceinline__ void produce(const CUtensorMap *mapA, const CUtensorM
                     const uint32_t fb = smem_u32(&sh.full[pos.slot]);
                     mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
                     mbar_expect_tx(fb, RP_SLOT);   // rows past the matrix end are zero-filled by the copy engine and still counted
-                    tma_load_3d(ring_base + pos.slot * RP_SLOT, m == 0 ? mapA : mapB, fb, (int)(seg * RP_SEG), (int)tile, layer);
+                    if (rp.chunk != 0xFFFFFFFFu)
+                        tma_load_4d(ring_base + pos.slot * RP_SLOT, m == 0 ? chunkA : chunkB, fb, (int)(seg * RP_SEG), (int)(tile - r0), (int)rp.chunk, layer);
+                    else
+                        tma_load_3d(ring_base + pos.slot * RP_SLOT, m == 0 ? mapA : mapB, fb, (int)(seg * RP_SEG), (int)tile, layer);
                     pos.next(n_slots);
                 }
             }
@@ -312,8 +344,8 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const float *xsr
                                         const uint8_t *ring, float4 *xs, const RPParams &p, RPShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const uint32_t n_slots = p.n_slots, B = p.B;
-    uint32_t r0, r1;
-    cta_tile_rows(M, ph++, r0, r1);
+    const RowPlan rp = cta_rows_plan(M, ph++);
+    const uint32_t r0 = rp.r0, r1 = rp.r1;
     const uint32_t nseg = K / RP_SEG;
     const uint32_t npass = (nseg + RP_PASS_SEGS - 1) / RP_PASS_SEGS;
     const uint32_t wofs = (uint32_t)g * RP_PITCH + (uint32_t)warp * 64 + (uint32_t)t * 16;   // this lane's 16 B of row g inside a slot
@@ -560,12 +592,12 @@ __global__ void __launch_bounds__(RP_ALL_THREADS, 1) decode_ring_pods_kernel(con
         if (threadIdx.x != RP_CTHREADS) return;   // one thread drives the copy engine
         const uint32_t ring_base = smem_u32(ring);
         for (uint32_t li = 0; li < p.n_layers; li++) {
-            produce<1>(&maps.m[RPK_WQKV], nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.m[RPK_WO], nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
-            produce<2>(&maps.m[RPK_W1], &maps.m[RPK_W3], (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
-            produce<1>(&maps.m[RPK_W2], nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_WQKV], nullptr, &maps.mc[RPK_WQKV], nullptr, (int)li, dim, 3 * dim, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_WO], nullptr, &maps.mc[RPK_WO], nullptr, (int)li, dim, dim, ph, pos, ring_base, sh, n_slots);
+            produce<2>(&maps.m[RPK_W1], &maps.m[RPK_W3], &maps.mc[RPK_W1], &maps.mc[RPK_W3], (int)li, dim, ff, ph, pos, ring_base, sh, n_slots);
+            produce<1>(&maps.m[RPK_W2], nullptr, &maps.mc[RPK_W2], nullptr, (int)li, ff, dim, ph, pos, ring_base, sh, n_slots);
         }
-        if (p.final_norm) produce<1>(&maps.m[RPK_OUT], nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
+        if (p.final_norm) produce<1>(&maps.m[RPK_OUT], nullptr, &maps.mc[RPK_OUT], nullptr, 0, dim, p.vocab, ph, pos, ring_base, sh, n_slots);
         return;
     }
     unsigned target = 0;
@@ -667,7 +699,8 @@ bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint3
     if (hd != 128 && hd != 64 && hd != 32) return false;
     if (dim % RP_SEG || ff % RP_SEG) return false;
     const uint32_t max_m = (ff > vocab ? ff : vocab) > 3 * dim ? (ff > vocab ? ff : vocab) : 3 * dim;
-    if (((max_m + RP_ROWS - 1) / RP_ROWS + kNumSMs - 1) / kNumSMs > (uint32_t)RP_MAX_TILES) return false;   // acc[] rows
+    if (((max_m + RP_ROWS - 1) / RP_ROWS + kNumSMs - 1) / kNumSMs > (uint32_t)RP_MAX_TILES ||
+        ((max_m + kNumSMs - 1) / kNumSMs + RP_ROWS - 1) / RP_ROWS > (uint32_t)RP_MAX_TILES) return false;   // acc[] rows (either row split)
     if ((size_t)2 * ctx * sizeof(float) > (size_t)RP_XS_F4 * 16) return false;             // attention scores overlay the stage
     return pods_plan(nullptr) >= 3;
 }
@@ -703,7 +736,7 @@ void decode_ring_pods(const MegaPodsParamsHost &h, cudaStream_t st) {
 typedef CUresult (*PFN_encodeTiled_rp)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats) {
+static PFN_encodeTiled_rp rp_encode_fn() {
     static PFN_encodeTiled_rp fn = nullptr;
     if (!fn) {
         void *pfn = nullptr;
@@ -712,6 +745,26 @@ static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t
         LB_CHECK(pfn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
         fn = reinterpret_cast<PFN_encodeTiled_rp>(pfn);
     }
+    return fn;
+}
+// the matrix as nfull chunks of R = ceil(rows / 148) rows (cta_rows_plan): dims {K, R, nfull, layers}, box {256, 16, 1, 1}
+static CUtensorMap rp_map_chunked(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats) {
+    PFN_encodeTiled_rp fn = rp_encode_fn();
+    const uint64_t R = (rows + kNumSMs - 1) / kNumSMs, nfull = rows / R;
+    CUtensorMap m;
+    memset(&m, 0, sizeof(m));
+    if (rows < (uint64_t)RP_ROWS * kNumSMs) return m;   // never used: such a matrix keeps the whole-tile split (cta_rows_plan)
+    cuuint64_t dims[4] = {K, R, nfull ? nfull : 1, layers};
+    cuuint64_t strides[3] = {K * 4, R * K * 4, (layers > 1 ? layer_stride_floats : K * rows) * 4};
+    cuuint32_t box[4] = {RP_SEG, RP_ROWS, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (chunked) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+static CUtensorMap rp_map(const float *base, uint64_t K, uint64_t rows, uint64_t layers, uint64_t layer_stride_floats) {
+    PFN_encodeTiled_rp fn = rp_encode_fn();
     CUtensorMap m;
     cuuint64_t dims[3] = {K, rows, layers};
     cuuint64_t strides[2] = {K * 4, (layers > 1 ? layer_stride_floats : K * rows) * 4};
@@ -743,6 +796,12 @@ void ring_pods_make_maps(const MegaLayerHost *L, uint32_t n_layers, uint32_t dim
     m.m[RPK_W3] = rp_map(L[0].w3, dim, ff, n_layers, (uint64_t)stride);
     m.m[RPK_W2] = rp_map(L[0].w2, ff, dim, n_layers, (uint64_t)stride);
     m.m[RPK_OUT] = output ? rp_map(output, dim, vocab, 1, 0) : m.m[RPK_WO];
+    m.mc[RPK_WQKV] = rp_map_chunked(L[0].wqkv, dim, 3ull * dim, n_layers, (uint64_t)stride);
+    m.mc[RPK_WO] = rp_map_chunked(L[0].wo, dim, dim, n_layers, (uint64_t)stride);
+    m.mc[RPK_W1] = rp_map_chunked(L[0].w1, dim, ff, n_layers, (uint64_t)stride);
+    m.mc[RPK_W3] = rp_map_chunked(L[0].w3, dim, ff, n_layers, (uint64_t)stride);
+    m.mc[RPK_W2] = rp_map_chunked(L[0].w2, ff, dim, n_layers, (uint64_t)stride);
+    m.mc[RPK_OUT] = output ? rp_map_chunked(output, dim, vocab, 1, 0) : m.mc[RPK_WO];
     memcpy(maps_out, &m, sizeof(RPMaps));
 }
 

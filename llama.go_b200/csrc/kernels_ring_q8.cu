@@ -142,11 +142,25 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
 // rows the CTA does not use), ceil(M/16) tiles dealt out evenly; WHICH CTAs get the extra tile rotates with the phase
 // number, and the run-ahead of the ring lets a CTA that is short one tile in this phase start on the next phase's
 // weights while the others finish — the per-phase imbalance averages out over a layer.
-__device__ __forceinline__ void cta_tile_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
-    const uint32_t ntiles = (M + RQ_ROWS - 1) / RQ_ROWS;
-    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
-    r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RQ_ROWS);
-    r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RQ_ROWS);
+// Row grouping of an M-row matrix — shared by the decode plane's layout (q8_to_tile_major) and the work split:
+//   M >= 16 rows per CTA: the matrix is cut into grid-many chunks of R = ceil(M / grid) consecutive rows (balanced to one row; a
+//   whole-tile split left ceil-vs-mean = one 16-row tile per CTA and phase, 72 .. 200 KB, as barrier wait: r02k trace, 21 of 67 us
+//   per layer); inside a chunk: 16-row tiles and one short last tile.  Smaller matrices (test models): plain 16-row tiles.
+// A tile of rt rows starting at row g0 is stored compactly: record(g0, seg) at (g0 * K/32 + seg * 32 * rt) * 36 bytes =
+// [nb blocks][rt rows][32 int8] | [nb][rt] f32 scales — one contiguous bulk copy per slot, whatever rt is.
+__host__ __device__ __forceinline__ uint32_t rq_chunk_rows(uint32_t M, uint32_t grid) {   // 0: plain 16-row tiles
+    return M >= RQ_ROWS * grid ? (M + grid - 1) / grid : 0u;
+}
+__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
+    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x, R = rq_chunk_rows(M, gridDim.x);
+    if (R) {
+        r0 = min(M, c * R);
+        r1 = min(M, r0 + R);
+    } else {
+        const uint32_t ntiles = (M + RQ_ROWS - 1) / RQ_ROWS;
+        r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RQ_ROWS);
+        r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RQ_ROWS);
+    }
 }
 
 struct RingPos {
@@ -163,18 +177,20 @@ template <int NM>
 __device__ __forceinline__ void produce(const uint8_t *PA, const uint8_t *PB, uint32_t K, uint32_t M, uint32_t &ph, RingPos &pos,
                                         uint32_t ring_base, RQShared &sh, uint32_t n_slots) {
     uint32_t r0, r1;
-    cta_tile_rows(M, ph++, r0, r1);
+    cta_rows(M, ph++, r0, r1);
     const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
     for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
-        const size_t tbase = (size_t)(tile / RQ_ROWS) * nblk * RQ_BLK;
+        const uint32_t rt = min((uint32_t)RQ_ROWS, r1 - tile);
+        const size_t tbase = (size_t)tile * nblk * 36u;
         for (uint32_t seg = 0; seg < nseg; seg++) {
             const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
+            const uint32_t bytes = nb * rt * 36u;
 #pragma unroll
             for (int m = 0; m < NM; m++) {
                 const uint32_t fb = smem_u32(&sh.full[pos.slot]);
                 mbar_wait(smem_u32(&sh.empty[pos.slot]), pos.phase ^ 1);
-                mbar_expect_tx(fb, nb * RQ_BLK);
-                bulk_g2s(ring_base + pos.slot * RQ_SLOT, (m == 0 ? PA : PB) + tbase + (size_t)seg * RQ_SLOT, nb * RQ_BLK, fb);
+                mbar_expect_tx(fb, bytes);
+                bulk_g2s(ring_base + pos.slot * RQ_SLOT, (m == 0 ? PA : PB) + tbase + (size_t)seg * (RQ_SEGK / 32) * rt * 36u, bytes, fb);
                 pos.next(n_slots);
             }
         }
@@ -187,22 +203,38 @@ __device__ __forceinline__ void produce(const uint8_t *PA, const uint8_t *PB, ui
 // dig[(b * 4 + plane) * 32 + k % 32], xsc[b] = s.  One warp per block, one lane per element, everything in registers
 // (the first version staged the FP32 vector in shared memory and converted it in a second sweep: ~4 us per phase).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_block(uint32_t b, float v, int lane, int8_t *dig, float *xsc) {
-    const float m = warp_max(fabsf(v));
+// Lane layout: a thread holds 4 consecutive elements (one float4) of block f / 8, f = the float4's index in the vector;
+// the 8 lanes of a block sit next to each other in the warp (f = threadIdx.x + i * 512 keeps f % 8 == lane % 8).
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return ((uint32_t)a & 0xFFu) | (((uint32_t)b & 0xFFu) << 8) | (((uint32_t)c & 0xFFu) << 16) | ((uint32_t)d << 24);
+}
+__device__ __forceinline__ void emit4(uint32_t f, float4 v, int8_t *dig, float *xsc) {
+    float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    const uint32_t grp = 0xFFu << (threadIdx.x & 24u);   // the block's 8 lanes (a warp's other blocks may be past the end of the vector)
+    m = fmaxf(m, __shfl_xor_sync(grp, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(grp, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(grp, m, 4));
     // exponent arithmetic on the bits; a block whose maximum is zero or denormal is sent as zeros (|v| < 1.2e-38)
     const uint32_t E = (__float_as_uint(m) >> 23) & 0xFFu;
     const float s = E ? __uint_as_float((E + 1u) << 23) : 1.0f, inv = E ? __uint_as_float((253u - E) << 23) : 0.0f;
-    float r = __fmul_rn(__fmul_rn(v, inv), 64.0f);   // exact (powers of two)
-    int d0 = __float2int_rn(r); r = __fsub_rn(r, (float)d0);
-    r = __fmul_rn(r, 128.0f);
-    int d1 = __float2int_rn(r); r = __fsub_rn(r, (float)d1);
-    r = __fmul_rn(r, 128.0f);
-    int d2 = __float2int_rn(r); r = __fsub_rn(r, (float)d2);
-    r = __fmul_rn(r, 128.0f);
-    int d3 = __float2int_rn(r);
-    int8_t *o = dig + (size_t)b * 128 + lane;
-    o[0] = (int8_t)d0; o[32] = (int8_t)d1; o[64] = (int8_t)d2; o[96] = (int8_t)d3;
-    if (lane == 0) xsc[b] = s;
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    int d[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float r = __fmul_rn(__fmul_rn(in[i], inv), 64.0f);   // exact (powers of two)
+        d[0][i] = __float2int_rn(r); r = __fsub_rn(r, (float)d[0][i]);
+        r = __fmul_rn(r, 128.0f);
+        d[1][i] = __float2int_rn(r); r = __fsub_rn(r, (float)d[1][i]);
+        r = __fmul_rn(r, 128.0f);
+        d[2][i] = __float2int_rn(r); r = __fsub_rn(r, (float)d[2][i]);
+        r = __fmul_rn(r, 128.0f);
+        d[3][i] = __float2int_rn(r);
+    }
+    const uint32_t b = f >> 3, sub = f & 7u;
+    uint32_t *o = reinterpret_cast<uint32_t *>(dig + (size_t)b * 128) + sub;
+#pragma unroll
+    for (int pl = 0; pl < 4; pl++) o[pl * 8] = pack4(d[pl][0], d[pl][1], d[pl][2], d[pl][3]);
+    if (sub == 0) xsc[b] = s;
 }
 __device__ __forceinline__ void zero_blocks(uint32_t b0, uint32_t b1, int8_t *dig, float *xsc) {   // padding columns of the last segment
     for (uint32_t i = b0 * 32 + threadIdx.x; i < b1 * 32; i += RQ_CTHREADS) {
@@ -211,21 +243,31 @@ __device__ __forceinline__ void zero_blocks(uint32_t b0, uint32_t b1, int8_t *di
     }
 }
 // digits of  w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
+// One L2/HBM round trip: the residual stream and the norm weights are requested together, as float4 per thread.
 __device__ __forceinline__ void norm_digits(const float *x, const float *w, uint32_t K, uint32_t kp, int8_t *dig, float *xsc, RQShared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NB = 16;   // blocks per warp kept in registers (K <= 8192); the rest is re-read
-    const uint32_t nblk = K / 32;
-    float v[NB];
+    constexpr int R = 4;   // float4 per thread kept in registers (K <= 8192); the rest is re-read
+    float4 v[R], g[R];
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const uint32_t b = warp + i * RQ_CWARPS;
-        v[i] = b < nblk ? __ldcg(x + (size_t)b * 32 + lane) : 0.f;
-        acc += (double)__fmul_rn(v[i], v[i]);
+    for (int i = 0; i < R; i++) {
+        const uint32_t f = threadIdx.x + i * RQ_CTHREADS;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[i] = v[i];
+        if (f < K / 4) {
+            v[i] = ldcg4(x + (size_t)f * 4);
+            g[i] = __ldg(reinterpret_cast<const float4 *>(w) + f);
+        }
     }
-    for (uint32_t b = warp + NB * RQ_CWARPS; b < nblk; b += RQ_CWARPS) {
-        const float u = __ldcg(x + (size_t)b * 32 + lane);
-        acc += (double)__fmul_rn(u, u);
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        acc += (double)__fmul_rn(v[i].x, v[i].x); acc += (double)__fmul_rn(v[i].y, v[i].y);
+        acc += (double)__fmul_rn(v[i].z, v[i].z); acc += (double)__fmul_rn(v[i].w, v[i].w);
+    }
+    for (uint32_t f = threadIdx.x + R * RQ_CTHREADS; f < K / 4; f += RQ_CTHREADS) {
+        const float4 u = ldcg4(x + (size_t)f * 4);
+        acc += (double)__fmul_rn(u.x, u.x); acc += (double)__fmul_rn(u.y, u.y);
+        acc += (double)__fmul_rn(u.z, u.z); acc += (double)__fmul_rn(u.w, u.w);
     }
     acc = warp_sum(acc);
     if (lane == 0) sh.red[warp] = acc;
@@ -234,27 +276,41 @@ __device__ __forceinline__ void norm_digits(const float *x, const float *w, uint
 #pragma unroll
     for (int i = 0; i < RQ_CWARPS; i++) t += sh.red[i];
     const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
+    auto nrm = [&](float4 u, float4 q) {
+        return make_float4(__fmul_rn(q.x, __fmul_rn(u.x, sc)), __fmul_rn(q.y, __fmul_rn(u.y, sc)),
+                           __fmul_rn(q.z, __fmul_rn(u.z, sc)), __fmul_rn(q.w, __fmul_rn(u.w, sc)));
+    };
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const uint32_t b = warp + i * RQ_CWARPS;
-        if (b < nblk) emit_block(b, __fmul_rn(__ldg(w + (size_t)b * 32 + lane), __fmul_rn(v[i], sc)), lane, dig, xsc);
+    for (int i = 0; i < R; i++) {
+        const uint32_t f = threadIdx.x + i * RQ_CTHREADS;
+        if (f < K / 4) emit4(f, nrm(v[i], g[i]), dig, xsc);   // (f < K/4 is uniform over the 8 lanes of a block: K % 32 == 0)
     }
-    for (uint32_t b = warp + NB * RQ_CWARPS; b < nblk; b += RQ_CWARPS)
-        emit_block(b, __fmul_rn(__ldg(w + (size_t)b * 32 + lane), __fmul_rn(__ldcg(x + (size_t)b * 32 + lane), sc)), lane, dig, xsc);
-    zero_blocks(nblk, kp / 32, dig, xsc);
+    for (uint32_t f = threadIdx.x + R * RQ_CTHREADS; f < K / 4; f += RQ_CTHREADS)
+        emit4(f, nrm(ldcg4(x + (size_t)f * 4), __ldg(reinterpret_cast<const float4 *>(w) + f)), dig, xsc);
+    zero_blocks(K / 32, kp / 32, dig, xsc);
     ccsync();   // also orders sh.red against its next use
 }
 __device__ __forceinline__ void plain_digits(const float *x, uint32_t K, uint32_t kp, int8_t *dig, float *xsc) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t nblk = K / 32;
-    for (uint32_t b = warp; b < nblk; b += RQ_CWARPS) emit_block(b, __ldcg(x + (size_t)b * 32 + lane), lane, dig, xsc);
-    zero_blocks(nblk, kp / 32, dig, xsc);
+    constexpr int PB = 6;   // float4 per thread per batch of loads: one L2 round trip per 12288 elements
+    for (uint32_t f0 = threadIdx.x; f0 < K / 4; f0 += PB * RQ_CTHREADS) {
+        float4 v[PB];
+#pragma unroll
+        for (int i = 0; i < PB; i++) {
+            const uint32_t f = f0 + i * RQ_CTHREADS;
+            v[i] = f < K / 4 ? ldcg4(x + (size_t)f * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < PB; i++) {
+            const uint32_t f = f0 + i * RQ_CTHREADS;
+            if (f < K / 4) emit4(f, v[i], dig, xsc);
+        }
+    }
+    zero_blocks(K / 32, kp / 32, dig, xsc);
     ccsync();
 }
 // digits of the merged attention output (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
 template <int HD>
 __device__ __forceinline__ void merge_digits(const RQParams &p, uint32_t kp, int8_t *dig, float *xsc, RQShared &sh) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t S = p.splits, items = p.heads * S;
     for (uint32_t i = threadIdx.x; i < items; i += RQ_CTHREADS) {
         const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
@@ -278,16 +334,28 @@ __device__ __forceinline__ void merge_digits(const RQParams &p, uint32_t kp, int
         sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
     }
     ccsync();
-    const uint32_t nblk = p.dim / 32;
-    for (uint32_t b = warp; b < nblk; b += RQ_CWARPS) {
-        const uint32_t e = b * 32 + lane, h = e / HD, d = e % HD;   // a 32-element block never straddles heads (HD >= 32)
+    constexpr int MB = 12;   // splits per batch of loads (a per-split loop of L2 reads costs one round trip per split)
+    for (uint32_t f = threadIdx.x; f < p.dim / 4; f += RQ_CTHREADS) {
+        const uint32_t e = f * 4, h = e / HD, d = e % HD;
         const float *po = p.part_o + (size_t)h * S * HD + d;
-        float o = 0.f;
-        for (uint32_t s2 = 0; s2 < S; s2++)
-            if (sh.mrg_l[h * S + s2] > 0.f) o = fmaf(__ldcg(po + (size_t)s2 * HD), sh.mrg_w[h * S + s2], o);
-        emit_block(b, __fmul_rn(o, sh.mrg_inv[h]), lane, dig, xsc);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t s0 = 0; s0 < S; s0 += MB) {
+            float4 pv[MB];
+#pragma unroll
+            for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < MB; u++) {
+                if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
+                    const float wgt = sh.mrg_w[h * S + s0 + u];
+                    o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
+                    o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+                }
+            }
+        }
+        const float inv = sh.mrg_inv[h];
+        emit4(f, make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv)), dig, xsc);
     }
-    zero_blocks(nblk, kp / 32, dig, xsc);
+    zero_blocks(p.dim / 32, kp / 32, dig, xsc);
     ccsync();
 }
 
@@ -301,12 +369,14 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
                                         uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     uint32_t r0, r1;
-    cta_tile_rows(M, ph++, r0, r1);
+    cta_rows(M, ph++, r0, r1);
     const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
     // digit weights of this lane's two D columns (2t, 2t + 1): digits 0..3 live in columns 0..3, columns 4..7 are zero planes
     const float w0 = t == 0 ? 0.015625f : (t == 1 ? 9.5367431640625e-07f : 0.f);            // 2^-6, 2^-20
     const float w1 = t == 0 ? 1.220703125e-04f : (t == 1 ? 7.450580596923828e-09f : 0.f);   // 2^-13, 2^-27
     for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
+        const uint32_t rt = min((uint32_t)RQ_ROWS, r1 - tile);   // rows of this tile (the chunk's last tile may be short)
+        const bool lo_row = (uint32_t)g < rt, hi_row = (uint32_t)g + 8 < rt;
         float acc[NM][2];
 #pragma unroll
         for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
@@ -329,12 +399,12 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
                 float da[2], db[2];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const uint32_t bl = warp * 2 + j;   // block inside the record: [bl][row][32 int8], scales [bl][row] after the nb int8 blocks
+                    const uint32_t bl = warp * 2 + j;   // block inside the record: [bl][row < rt][32 int8], scales [bl][row] after the nb int8 blocks
                     const bool live = bl < nb;
-                    qa[j] = live ? *reinterpret_cast<const uint2 *>(sl + bl * RQ_BLKQ + g * 32 + t * 8) : make_uint2(0u, 0u);          // row g, 8 int8
-                    qb[j] = live ? *reinterpret_cast<const uint2 *>(sl + bl * RQ_BLKQ + (g + 8) * 32 + t * 8) : make_uint2(0u, 0u);    // row g + 8
-                    da[j] = live ? *reinterpret_cast<const float *>(sl + nb * RQ_BLKQ + (bl * RQ_ROWS + g) * 4) : 0.f;
-                    db[j] = live ? *reinterpret_cast<const float *>(sl + nb * RQ_BLKQ + (bl * RQ_ROWS + g + 8) * 4) : 0.f;
+                    qa[j] = live && lo_row ? *reinterpret_cast<const uint2 *>(sl + (bl * rt + g) * 32 + t * 8) : make_uint2(0u, 0u);        // row g, 8 int8
+                    qb[j] = live && hi_row ? *reinterpret_cast<const uint2 *>(sl + (bl * rt + g + 8) * 32 + t * 8) : make_uint2(0u, 0u);    // row g + 8
+                    da[j] = live && lo_row ? *reinterpret_cast<const float *>(sl + nb * rt * 32 + (bl * rt + g) * 4) : 0.f;
+                    db[j] = live && hi_row ? *reinterpret_cast<const float *>(sl + nb * rt * 32 + (bl * rt + g + 8) * 4) : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
@@ -645,36 +715,50 @@ static uint32_t q8_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx,
 // scales [blocks of the segment][16 rows] f32 FOLLOW the segment's int8 blocks:  record(tile, seg) at
 // (tile * K/32 + seg * 32) * 576 bytes = [nb][16][32] int8 | [nb][16] f32.  Rows >= `rows` of the last tile are zero.
 __global__ void q8_to_tile_major_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, uint8_t *__restrict__ plane,
-                                        uint32_t rows, uint32_t K) {
-    const uint32_t nblk = K / 32, ntiles = (rows + RQ_ROWS - 1) / RQ_ROWS;
-    const size_t n = (size_t)ntiles * nblk * RQ_ROWS * 8, stride = (size_t)gridDim.x * blockDim.x;   // one thread per (tile, block, row, 4-byte group)
+                                        uint32_t M, uint32_t row0, uint32_t nrows, uint32_t K, uint32_t R) {
+    const uint32_t nblk = K / 32;
+    const size_t n = (size_t)nrows * nblk * 8, stride = (size_t)gridDim.x * blockDim.x;   // one thread per (row, block, 4-byte group)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k4 = (uint32_t)(i & 7), r = (uint32_t)((i >> 3) % RQ_ROWS);
-        const size_t tb = i / (8 * RQ_ROWS);
-        const uint32_t b = (uint32_t)(tb % nblk), tile = (uint32_t)(tb / nblk);
-        const uint32_t row = tile * RQ_ROWS + r, seg = b / (RQ_SEGK / 32), bl = b % (RQ_SEGK / 32);
-        const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
-        uint8_t *rec = plane + ((size_t)tile * nblk + (size_t)seg * (RQ_SEGK / 32)) * RQ_BLK;
-        uint32_t w = 0;
-        float sc = 0.f;
-        if (row < rows) {
-            const uint32_t kcol = b * 32 + k4 * 4;
-            w = *reinterpret_cast<const uint32_t *>(q + ((size_t)(row >> 2) * (K >> 2) + (kcol >> 2)) * 16 + (row & 3) * 4);
-            sc = d[((size_t)(row >> 2) * (K >> 5) + b) * 4 + (row & 3)];
+        const uint32_t k4 = (uint32_t)(i & 7);
+        const size_t rb = i >> 3;
+        const uint32_t b = (uint32_t)(rb % nblk), lr = (uint32_t)(rb / nblk);   // lr: row inside q/d (the tensor's own planes)
+        const uint32_t row = row0 + lr;                                           // row inside the whole matrix
+        // the tile this row belongs to (rq_chunk_rows / cta_rows): first row g0, height rt
+        uint32_t g0, rt;
+        if (R) {
+            const uint32_t c = row / R, cend = min(M, (c + 1) * R);
+            g0 = c * R + ((row - c * R) / RQ_ROWS) * RQ_ROWS;
+            rt = min((uint32_t)RQ_ROWS, cend - g0);
+        } else {
+            g0 = (row / RQ_ROWS) * RQ_ROWS;
+            rt = min((uint32_t)RQ_ROWS, M - g0);
         }
-        *reinterpret_cast<uint32_t *>(rec + bl * RQ_BLKQ + r * 32 + k4 * 4) = w;
-        if (k4 == 0) *reinterpret_cast<float *>(rec + nb * RQ_BLKQ + (bl * RQ_ROWS + r) * 4) = sc;
+        const uint32_t r = row - g0, seg = b / (RQ_SEGK / 32), bl = b % (RQ_SEGK / 32);
+        const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
+        uint8_t *rec = plane + ((size_t)g0 * nblk + (size_t)seg * (RQ_SEGK / 32) * rt) * 36u;
+        const uint32_t kcol = b * 32 + k4 * 4;
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(q + ((size_t)(lr >> 2) * (K >> 2) + (kcol >> 2)) * 16 + (lr & 3) * 4);
+        *reinterpret_cast<uint32_t *>(rec + (bl * rt + r) * 32 + k4 * 4) = w;
+        if (k4 == 0) *reinterpret_cast<float *>(rec + nb * rt * 32 + (bl * rt + r) * 4) = d[((size_t)(lr >> 2) * (K >> 5) + b) * 4 + (lr & 3)];
     }
 }
 
 }  // namespace
 
-size_t q8_tile_major_bytes(uint32_t rows, uint32_t K) { return (size_t)((rows + RQ_ROWS - 1) / RQ_ROWS) * (K / 32) * RQ_BLK; }
+size_t q8_tile_major_bytes(uint32_t rows, uint32_t K) { return (size_t)rows * (K / 32) * 36u; }
 
-void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t rows, uint32_t K, cudaStream_t st) {
-    LB_CHECK(K % 32 == 0 && rows % 4 == 0, "q8_to_tile_major: K must be a multiple of 32 and the row count a multiple of 4");
-    if (!rows) return;
-    q8_to_tile_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, plane, rows, K);
+// every record must start on and span a multiple of 16 bytes (bulk copy): K % 128 == 0 makes that true for any tile height;
+// matrices that keep plain 16-row tiles only need whole tiles
+static bool rq_layout_ok(uint32_t M, uint32_t K) {
+    if (K % 32 || M % 4) return false;
+    return rq_chunk_rows(M, kNumSMs) ? K % 128 == 0 : M % RQ_ROWS == 0;
+}
+
+void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t M, uint32_t row0, uint32_t nrows, uint32_t K, cudaStream_t st) {
+    if (!rq_layout_ok(M, K)) return;   // shapes the ring megakernel does not take (decode_ring_q8_supported): no decode plane
+    LB_CHECK(row0 % 4 == 0 && nrows % 4 == 0 && row0 + nrows <= M, "q8_to_tile_major: bad row range");
+    if (!nrows) return;
+    q8_to_tile_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, plane, M, row0, nrows, K, rq_chunk_rows(M, kNumSMs));
     LB_LAUNCH_CHECK();
 }
 
@@ -682,7 +766,8 @@ bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_
     if (heads == 0 || dim % heads || heads > (uint32_t)RQ_MAX_HEADS) return false;
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
-    if (dim % 32 || ff % 32 || dim < 256 || vocab % 16) return false;   // whole 16-row tiles, 32-column blocks
+    if (dim % 32 || ff % 32 || dim < 256) return false;
+    if (!rq_layout_ok(3 * dim, dim) || !rq_layout_ok(dim, dim) || !rq_layout_ok(ff, dim) || !rq_layout_ok(dim, ff) || !rq_layout_ok(vocab, dim)) return false;
     return q8_plan(dim, ff, heads, ctx, nullptr, nullptr) >= 3;
 }
 

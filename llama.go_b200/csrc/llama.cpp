@@ -67,11 +67,13 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
         tmslab = mem.dmalloc<uint8_t>(qtotal / 512 * 576 + 256);   // every matrix: (rows / 16) x (K / 32) records of 576 bytes
     }
     auto fptr = [&](const MOff &o) { return q8() ? nullptr : slab + o.f; };
-    auto qmat = [&](const MOff &o, size_t row_off_elems = 0) {
+    // (matrix offsets o.q are multiples of 512 elements; the decode plane holds 36 bytes per 32 elements, k::q8_tile_major_bytes)
+    auto qmat = [&](const MOff &o, size_t rows_total, size_t cols, size_t row_off = 0) {
         Q8Mat m;
         if (q8()) {
-            m.q = qslab + o.q + row_off_elems; m.d = dslab + o.d + row_off_elems / 32;
-            m.tm = tmslab + (o.q + row_off_elems) / 512 * 576;   // (o.q and row offsets are multiples of 512 elements: 16 rows x 32 columns)
+            m.q = qslab + o.q + row_off * cols; m.d = dslab + o.d + row_off * cols / 32;
+            m.tm = tmslab + o.q / 512 * 576;
+            m.tm_row0 = (uint32_t)row_off; m.tm_rows = (uint32_t)rows_total;
         }
         return m;
     };
@@ -81,7 +83,7 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
         tensors["tok_embeddings.weight"] = {tok_embeddings, V * d, 1, 0.f, 1.f, Q8Mat()};
     }
     if (has_head()) {
-        norm = slab + o_norm; output = fptr(o_out); output8 = qmat(o_out);
+        norm = slab + o_norm; output = fptr(o_out); output8 = qmat(o_out, V, d);
         tensors["norm.weight"] = {norm, d, 2, 1.f, 0.1f, Q8Mat()};
         tensors["output.weight"] = {output, V * d, 3, 0.f, sdd, output8, (uint32_t)d};
     }
@@ -90,15 +92,15 @@ Model::Model(const HParams &h, int dev, uint32_t lb_, uint32_t le_, int wt) : hp
         Layer &L = layers[i];
         L.attention_norm = slab + lo[i].an; L.ffn_norm = slab + lo[i].fn;
         L.wqkv = fptr(lo[i].qkv); L.wo = fptr(lo[i].wo); L.w1 = fptr(lo[i].w1); L.w3 = fptr(lo[i].w3); L.w2 = fptr(lo[i].w2);
-        L.wqkv8 = qmat(lo[i].qkv); L.wo8 = qmat(lo[i].wo); L.w18 = qmat(lo[i].w1); L.w38 = qmat(lo[i].w3); L.w28 = qmat(lo[i].w2);
+        L.wqkv8 = qmat(lo[i].qkv, 3 * d, d); L.wo8 = qmat(lo[i].wo, d, d); L.w18 = qmat(lo[i].w1, ff, d); L.w38 = qmat(lo[i].w3, ff, d); L.w28 = qmat(lo[i].w2, d, ff);
         uint32_t il = layer_begin + (uint32_t)i;
         std::string p = "layers." + std::to_string(il) + ".";
         uint64_t base = 16ull * (il + 1);
         auto fq = [&](size_t rows_off) { return q8() ? nullptr : L.wqkv + rows_off; };
         tensors[p + "attention_norm.weight"] = {L.attention_norm, d, base + 0, 1.f, 0.1f, Q8Mat()};
-        tensors[p + "attention.wq.weight"] = {fq(0), d * d, base + 1, 0.f, sdd, qmat(lo[i].qkv, 0), (uint32_t)d};
-        tensors[p + "attention.wk.weight"] = {fq(d * d), d * d, base + 2, 0.f, sdd, qmat(lo[i].qkv, d * d), (uint32_t)d};
-        tensors[p + "attention.wv.weight"] = {fq(2 * d * d), d * d, base + 3, 0.f, sdd, qmat(lo[i].qkv, 2 * d * d), (uint32_t)d};
+        tensors[p + "attention.wq.weight"] = {fq(0), d * d, base + 1, 0.f, sdd, qmat(lo[i].qkv, 3 * d, d, 0), (uint32_t)d};
+        tensors[p + "attention.wk.weight"] = {fq(d * d), d * d, base + 2, 0.f, sdd, qmat(lo[i].qkv, 3 * d, d, d), (uint32_t)d};
+        tensors[p + "attention.wv.weight"] = {fq(2 * d * d), d * d, base + 3, 0.f, sdd, qmat(lo[i].qkv, 3 * d, d, 2 * d), (uint32_t)d};
         tensors[p + "attention.wo.weight"] = {L.wo, d * d, base + 4, 0.f, sdd, L.wo8, (uint32_t)d};
         tensors[p + "ffn_norm.weight"] = {L.ffn_norm, d, base + 5, 1.f, 0.1f, Q8Mat()};
         tensors[p + "feed_forward.w1.weight"] = {L.w1, ff * d, base + 6, 0.f, sdd, L.w18, (uint32_t)d};
@@ -134,7 +136,7 @@ void Model::set_tensor(const std::string &name, int dtype, const void *host, siz
     }
     if (quant) {
         k::quantize_q8(dst, e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
-        if ((e.nelem / e.cols) % 16 == 0) k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+        k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, e.q8.tm_rows, e.q8.tm_row0, (uint32_t)(e.nelem / e.cols), e.cols, 0);
     }
     LB_CUDA(cudaDeviceSynchronize());
     if (tmp16) cudaFree(tmp16);
@@ -172,7 +174,7 @@ void Model::init_random(uint64_t seed) {
         if (e.q8.q) {
             k::init_random(static_cast<float *>(tmp), e.nelem, seed, e.tid, e.mean, sscale, 0);
             k::quantize_q8(static_cast<float *>(tmp), e.q8.q, e.q8.d, (uint32_t)(e.nelem / e.cols), e.cols, 0);
-            if ((e.nelem / e.cols) % 16 == 0) k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, (uint32_t)(e.nelem / e.cols), e.cols, 0);
+            k::q8_to_tile_major(e.q8.q, e.q8.d, e.q8.tm, e.q8.tm_rows, e.q8.tm_row0, (uint32_t)(e.nelem / e.cols), e.cols, 0);
         } else {
             k::init_random(e.ptr, e.nelem, seed, e.tid, e.mean, sscale, 0);
         }
@@ -239,7 +241,7 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
         mega_layers_dev = mem.dmalloc<k::MegaLayerHost>(nl, false);
         LB_CUDA(cudaMemcpy(mega_layers_dev, ml.data(), nl * sizeof(k::MegaLayerHost), cudaMemcpyHostToDevice));
         mega_barrier = mem.dmalloc<unsigned>(4 + 4 * nl);  // grid barrier + per-phase ticket counters
-        if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13 + 5 * 148);
+        if (getenv("LB_MEGA_TRACE")) mega_trace = mem.dmalloc<unsigned long long>(nl * 13 + 13 * 148);   // + 5 arrival stamps, 4 producer stall times, 4 job counts per CTA (layer 5)
         if (use_ring_q8) {
             std::vector<k::RingQ8Layer> pl(nl);
             for (size_t i = 0; i < nl; i++) {

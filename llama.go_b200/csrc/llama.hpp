@@ -23,7 +23,9 @@ struct Q8Mat {  // Q8_0 planes of one matrix: 4-row-interleaved q / d (kernels_q
                 // tile-major decode plane streamed by the ring megakernel (kernels_ring_q8.cu: q8_to_tile_major)
     int8_t *q = nullptr;
     float *d = nullptr;
-    uint8_t *tm = nullptr;
+    uint8_t *tm = nullptr;      // decode plane of the WHOLE matrix this tensor is part of (wq/wk/wv share the [3*dim][dim] plane)
+    uint32_t tm_row0 = 0;       // first row of this tensor inside that matrix
+    uint32_t tm_rows = 0;       // rows of the whole matrix (the plane's row grouping depends on it)
 };
 
 struct Layer {  // llama.go:128-146; wq|wk|wv are stored as one [3*dim][dim] matrix
