@@ -1,24 +1,31 @@
 // kernels_ring.cu — the single-token forward pass (llama.Eval with N = 1, pkg/llama/llama.go:211-426) as ONE
 // persistent cooperative kernel whose weight stream never stops: a dedicated producer warp copies every weight
 // this CTA will need, in schedule order, from HBM into a shared-memory ring with cp.async.bulk (the TMA copy
-// engine, completion on mbarriers), and runs AHEAD of the 16 consumer warps — across row tiles, across phases,
+// engine, completion on mbarriers), and runs AHEAD of the 16 consumer warps — across rows, across phases,
 // across the grid barriers and the attention phase.  Weights do not depend on anything computed in the launch,
 // so the only thing that ever stops the stream is a full ring.
 //
-// Why (profiles/README.md, round 1): the register-fed megakernel (kernels_mega.cu) streams its four MulMat
-// phases at ~7.0 TB/s but leaves HBM idle for ~11 us of grid barriers and ~4 us of attention per 137 us layer
-// (0.914 of the measured-peak roofline); L2 prefetch hints issued around the barriers measured no gain
-// (round 2, profiles/README.md).  A ring of 9 x 16 KB per SM holds ~3.3 us of the CTA's share of the stream.
+// Why (profiles/README.md): the register-fed megakernel (kernels_mega.cu) streams its four MulMat phases at ~7.0 TB/s
+// but leaves HBM idle for ~11 us of grid barriers and ~4 us of attention per 137 us layer (0.905-0.914 of the
+// measured-peak roofline); L2 prefetch hints around the barriers and a shared-memory head start of the next phase
+// measured no gain or a loss (r02a, r02j).
 //
-// Layout of the stream: a MulMat phase gives CTA c a contiguous block of ~M/148 output rows.  One ring slot = one
-// row (K <= 4096) or one K chunk of a longer row, filled by ONE bulk copy of up to 16 KB (1 KB copies were measured
-// copy-engine bound at ~75 clk per copy: 4 TB/s, profiles/README.md).  Consumer warp w owns the rows r0 + w, r0 + w + 16,
-// ... and consumes the slots of its rows by itself: 32 conflict-free LDS.128 of weights against the activation vector
-// kept in shared memory for the phase, one warp-shuffle reduction per ROW, no cross-warp combine and no CTA barrier
-// inside a MulMat phase.  Slot q lives in ring entry q % n; full[] (expect_tx + the copy's complete_tx) / empty[] (the
-// owning warp's arrival); both sides compute q from (phase base, row, chunk), so there is no shared cursor.
-// Numerics are those of kernels_mega.cu (f64 RMSNorm sums, f64 RoPE, f64 exp softmax terms); only the
-// association order of the FP32 dot products differs (lane-sequential over k, then a shuffle tree).
+// Version 3 (r02m).  Versions 1-2 gave every ring slot (one row, 16 KB) to ONE consumer warp and kept the activation
+// vector in shared memory: a slot stayed occupied for the ~0.6 us a single warp needs to walk 16 KB, only 9 slots fit
+// next to the 44 KB vector, and the kernel ended 3 % BEHIND the register-fed one (r02i/r02j: 215.8 vs 221.5 tok/s) — the
+// ring was latency-bound: 9 x 16 KB / (HBM latency + 0.6 us) is no more than an SM's share of the HBM rate.  Now
+//   * every slot is consumed by ALL 16 warps at once: warp w owns the fixed 1/16 slice of the slot's K range and keeps
+//     that slice of the activation vector in REGISTERS for the whole phase (the register-fed kernel's decomposition),
+//     reads its 1 KB of the row with two conflict-free LDS.128, and releases the slot (mbarrier count 16) ~50 ns after
+//     the bytes have landed;
+//   * no activation vector in shared memory: the ring is 12 x 16 KB = 192 KB per SM (4 us of stream);
+//   * per-warp partial sums go through shared memory and are combined in a fixed order once per 32 rows (deterministic).
+// Layout of the stream: a MulMat phase gives CTA c a contiguous block of ~0.8 M/148 output rows plus rows drawn from a
+// ticket pool; one ring slot = one row (K <= 4096) or one K chunk of a longer row, filled by ONE bulk copy of up to
+// 16 KB (1 KB copies were measured copy-engine bound at ~75 clk per copy: 4 TB/s, profiles/README.md r02f).
+// Slot q lives in ring entry q % n; full[] (expect_tx + the copy's complete_tx) / empty[] (the 16 warps' arrivals).
+// Numerics are those of kernels_mega.cu (f64 RMSNorm sums, f64 RoPE, f64 exp softmax terms, K-slice partial sums combined
+// in warp order); only the chunking of K > 4096 rows differs in the association order of the FP32 dot products.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -31,11 +38,12 @@ namespace {
 
 constexpr int RG_CWARPS = 16;                      // consumer warps
 constexpr int RG_CTHREADS = RG_CWARPS * 32;        // 512
-constexpr int RG_THREADS = RG_CTHREADS + 64;       // + the producer warp + the L2 look-ahead warp
+constexpr int RG_THREADS = RG_CTHREADS + 32;       // + the producer warp
 constexpr int RG_HALF = RG_CTHREADS / 2;
 constexpr uint32_t RG_SLOT_FLOATS = 4096;          // one slot = one row (or a K chunk of a longer row): ONE bulk copy of <= 16 KB
 constexpr uint32_t RG_SLOT = RG_SLOT_FLOATS * 4;
-constexpr int RG_MAX_SLOTS = 12;
+constexpr int RG_MAX_SLOTS = 13;
+constexpr int RG_GROUP = 32;                       // rows whose K-slice partials are combined per CTA barrier
 constexpr int RG_MAX_PHASES = 4 * 160 + 1;        // MulMat phases of a launch: 4 per layer + lm_head
 constexpr int RG_MAX_ITEMS = 2 * kNumSMs;
 constexpr int RG_MAX_HEADS = 256;
@@ -44,6 +52,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void ccsync() { asm volatile("bar.sync 1, %0;" ::"n"(RG_CTHREADS) : "memory"); }   // consumers only
 __device__ __forceinline__ void hsync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(2 + half), "n"(RG_HALF) : "memory"); }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -58,18 +71,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
+    while (!mbar_try(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline bug must not hang the box
     }
 }
@@ -91,8 +106,7 @@ struct RingParams {
     float *part_o, *part_ml;
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
-    uint32_t pf_bytes;            // L2 look-ahead of the prefetch warp beyond the ring, bytes per CTA (0: off)
-    unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0
+    unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0 (+ per-CTA statistics of layer 5)
     // fused stage hand-off over NVLink peer memory (see MegaParamsHost)
     uint32_t *p2p_flags;          // local {in_flag, ack, seq}
     uint32_t p2p_wait_in;
@@ -102,10 +116,10 @@ struct RingParams {
 
 struct RingShared {
     unsigned long long full[RG_MAX_SLOTS], empty[RG_MAX_SLOTS];
-    unsigned epoch[RG_MAX_SLOTS];   // q / n_slots of the slot's current occupant (written by the producer before it arms full[])
     unsigned jobrow[RG_MAX_SLOTS];  // the output row the slot's bytes belong to
-    unsigned copied;                // nominal stream position of the producer (bytes of this CTA's share copied so far), read by the look-ahead warp
     unsigned short done_jobs[RG_MAX_PHASES];   // jobs of MulMat phase i of this launch (0xFFFF: the producer has not finished it)
+    float part[2][2][RG_GROUP][RG_CWARPS];     // [buffer][matrix (w1|w3)][row of the group][warp]
+    unsigned grow[2][RG_GROUP];                // output rows of the group
     double red[RG_CWARPS];
     double rope_cs[64][2];
     float fred[2][RG_CWARPS / 2];
@@ -152,34 +166,33 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
     ccsync();
 }
 
+// A row of K floats is streamed as NCH = ceil(K / 4096) chunks of CH floats (a multiple of 64: every warp's 1/16 slice of
+// a chunk is whole float4s); the last chunk may be shorter.  Inside chunk c warp w owns floats [w * len_c / 16, (w + 1) * len_c / 16),
+// lane l the float4s l and l + 32 of that slice (a slice is at most 256 floats).
+__host__ __device__ __forceinline__ uint32_t ring_nch(uint32_t K) { return (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS; }
+__host__ __device__ __forceinline__ uint32_t ring_chunk(uint32_t K, uint32_t nch) { return (((K + nch - 1) / nch) + 63u) / 64u * 64u; }
 
-// The stream is a sequence of slots numbered from the start of the launch: slot q lives in ring entry q % n_slots, its
-// mbarrier phase bit is (q / n_slots) & 1.  Both sides derive q from (phase base, row, chunk, matrix) — no shared cursor.
-__device__ __forceinline__ uint32_t chunk_floats(uint32_t K, uint32_t nch) { return ((K / 4 + nch - 1) / nch) * 4; }
-
-// Work of a MulMat phase = "jobs", one per output row (its nch K-chunks, both matrices of the SwiGLU pair: J slots).
-// 3/4 of the rows are dealt out statically (CTA c: a contiguous block), the rest is a pool handed out one row per ticket
-// (atomic counter per phase) — drawn by the PRODUCER as it runs ahead, so an SM that streams faster takes more rows and
-// all CTAs reach the grid barrier within about one row time (a purely static split left the fast CTAs waiting 5-12 us
-// per barrier for the slow ones: 203 vs 214 tok/s, profiles/README.md r02h).  Job j of the phase (in issue order) is
-// consumed by warp j % 16; its row number travels in sh.jobrow[]; the producer ends the phase by publishing the job count.
-constexpr unsigned RG_STATIC_NUM = 3, RG_STATIC_DEN = 4;
-constexpr unsigned RG_TICKET_ROWS = 4;   // rows per ticket; two tickets are kept in flight (an L2 atomic round trip is ~4 row times)
+// Work of a MulMat phase = "jobs", one per output row (its NCH chunks, both matrices of the SwiGLU pair).
+// 4/5 of the rows are dealt out statically (CTA c: a contiguous block), the rest is a pool handed out a few rows per ticket
+// (atomic counter per phase) — drawn by the PRODUCER as it runs ahead, one ticket at a time (the first one a few rows before
+// the static block ends, the next one when a ticket's rows start), so an SM that streams faster takes more rows and all
+// CTAs reach the grid barrier within about a ticket of each other.  (r02k: drawing two tickets up front handed the whole
+// pool of a short phase to the first 128 CTAs to ask — wo and w2 ran as an UNBALANCED static split.)
+// Every warp consumes every job, in issue order; the job's row number travels in sh.jobrow[]; the producer ends a phase by
+// publishing its job count BEFORE it installs anything of the next phase.
+constexpr unsigned RG_STATIC_NUM = 4, RG_STATIC_DEN = 5;
+__device__ __forceinline__ uint32_t ticket_rows(uint32_t M) { return M / gridDim.x >= 64 ? 4u : 2u; }
 
 // ---------------------------------------------------------------------------------------------------------
 // producer (one thread)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t phase_share_bytes(uint32_t K, uint32_t M, int NM) {   // one CTA's nominal share of a MulMat phase
-    return (uint32_t)(((uint64_t)M * K * 4ull * (uint64_t)NM) / gridDim.x);
-}
 template <int NM>
 __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_t K, uint32_t M, uint32_t &q, uint32_t phidx, unsigned *ticket,
-                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t &stream_pos,
-                                        unsigned long long *pstat = nullptr) {
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, unsigned long long *pstat = nullptr) {
     unsigned long long stall = 0;   // profiling aid (pstat != nullptr): ns this producer spent waiting for a free ring entry
-    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
+    const uint32_t nch = ring_nch(K), CH = ring_chunk(K, nch);
     const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));   // static rows per CTA
-    const uint32_t pool0 = Q * gridDim.x;
+    const uint32_t pool0 = Q * gridDim.x, TR = ticket_rows(M);
     uint32_t njobs = 0;
     auto job = [&](uint32_t row) {
         for (uint32_t c = 0; c < nch; c++) {
@@ -194,11 +207,10 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
                     mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
                     stall += tb - ta;
-                } else
-                mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // the consumer warp of slot q - n_slots released it
+                } else {
+                    mbar_wait(smem_u32(&sh.empty[slot]), ph ^ 1);   // all 16 warps have read slot q - n_slots
+                }
                 *reinterpret_cast<volatile unsigned *>(&sh.jobrow[slot]) = row;
-                __threadfence_block();
-                *reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) = q / n_slots;
                 __threadfence_block();
                 mbar_expect_tx(fb, len * 4);
                 bulk_g2s(ring_base + slot * RG_SLOT, (m == 0 ? W : W3) + (size_t)row * K + k0, len * 4, fb);
@@ -206,171 +218,143 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
             }
         }
         njobs++;
-        *reinterpret_cast<volatile unsigned *>(&sh.copied) = stream_pos + njobs * K * 4u * (uint32_t)NM;
     };
-    unsigned ta = atomicAdd(ticket, 1u), tb = atomicAdd(ticket, 1u);   // two tickets on their way while the static rows stream
-    for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
-    while ((uint64_t)pool0 + (uint64_t)ta * RG_TICKET_ROWS < M) {
-        const uint32_t rb = pool0 + ta * RG_TICKET_ROWS, re = min(M, rb + RG_TICKET_ROWS);
-        ta = tb;
-        tb = atomicAdd(ticket, 1u);                             // next ticket, overlapped with these rows' copies
+    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q, early = Q > 6 ? r1 - 6 : r0;   // draw the first ticket ~6 rows before the static block ends
+    unsigned ta = 0;
+    bool have = false;
+    for (uint32_t row = r0; row < r1; row++) {
+        if (row == early) { ta = atomicAdd(ticket, 1u); have = true; }
+        job(row);
+    }
+    if (!have) ta = atomicAdd(ticket, 1u);
+    while ((uint64_t)pool0 + (uint64_t)ta * TR < M) {
+        const uint32_t rb = pool0 + ta * TR, re = min(M, rb + TR);
+        ta = atomicAdd(ticket, 1u);                             // next ticket, overlapped with these rows' copies
         for (uint32_t row = rb; row < re; row++) job(row);
     }
     // end of phase: the job count for the consumers
     *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]) = (unsigned short)njobs;
     __threadfence_block();
-    stream_pos += phase_share_bytes(K, M, NM);
-    *reinterpret_cast<volatile unsigned *>(&sh.copied) = stream_pos;
     if (pstat) { pstat[blockIdx.x] = stall; pstat[4 * gridDim.x + blockIdx.x] = njobs; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// L2 look-ahead (one thread of a second helper warp): walks the same schedule as the producer and keeps the next
-// pf_bytes of this CTA's share of the stream on their way from HBM into L2 (cp.async.bulk.prefetch.L2), beyond what
-// the ring can hold.  The ring covers ~3 us of stream; a grid barrier + the attention phase + the next barrier stop the
-// consumers for ~10 us, so without this HBM idles while the ring is full.  The prefetch stream of CTA c = its static
-// rows + the c-th share of the phase's ticket pool (whoever draws those rows later finds them in L2).
+// consumer: out[row] = epilogue(W[row] . x) for the rows this CTA's producer fetched; x: this warp's K-slices in registers
+// (xs[c][v] = float4 (v * 32 + lane) of the warp's slice of chunk c).  EPI: 0 none, 1 + res[row];
+// NM == 2: out[row] = silu(W1[row].x) * (W3[row].x)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-template <int NM>
-__device__ __forceinline__ void lookahead(const float *W, const float *W3, uint32_t K, uint32_t M, RingShared &sh, uint32_t ring_bytes,
-                                          uint32_t pf_bytes, uint32_t &stream_pos) {
-    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch);
-    const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));
-    const uint32_t pool0 = Q * gridDim.x, P = M - pool0;
-    const uint32_t ps = pool0 + (uint32_t)(((uint64_t)P * blockIdx.x) / gridDim.x), pe = pool0 + (uint32_t)(((uint64_t)P * (blockIdx.x + 1)) / gridDim.x);
-    const uint32_t jb = K * 4u * (uint32_t)NM;
-    uint32_t pos = stream_pos;
-    auto job = [&](uint32_t row) {
-        pos += jb;
-        const long long t0 = clock64();
-        int32_t ahead;
-        while ((ahead = (int32_t)(pos - *reinterpret_cast<volatile unsigned *>(&sh.copied))) > (int32_t)pf_bytes) {
-            __nanosleep(200);
-            if (clock64() - t0 > 4000000000LL) __trap();
-        }
-        if (ahead <= (int32_t)ring_bytes) return;   // the copy engine is about to fetch (or has fetched) this row itself
-        for (uint32_t c = 0; c < nch; c++) {
-            const uint32_t k0 = c * CH, len = min(CH, K - k0);
-#pragma unroll
-            for (int m = 0; m < NM; m++) l2_prefetch((m == 0 ? W : W3) + (size_t)row * K + k0, len * 4);
-        }
-    };
-    for (uint32_t row = blockIdx.x * Q; row < (blockIdx.x + 1) * Q; row++) job(row);
-    for (uint32_t row = ps; row < pe; row++) job(row);
-    stream_pos += phase_share_bytes(K, M, NM);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// consumer: out[row] = epilogue(W[row] . x) for the rows this CTA's producer fetched; x in shared memory (xs).
-// Warp w consumes jobs w, w + 16, ... (every slot of a job by itself).
-// EPI: 0 none, 1 + res[row];  NM == 2: out[row] = silu(W1[row].x) * (W3[row].x)
-// ---------------------------------------------------------------------------------------------------------
-template <int NM, int EPI>
-__device__ __forceinline__ void consume(uint32_t K, const float *xs, float *out, const float *res, uint32_t &qbase, uint32_t phidx,
-                                        const uint8_t *ring, RingShared &sh, uint32_t n_slots) {
+template <int NM, int EPI, int NCH>
+__device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], float *out, const float *res, uint32_t &q, uint32_t phidx,
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t nch = (K + RG_SLOT_FLOATS - 1) / RG_SLOT_FLOATS, CH = chunk_floats(K, nch), J = nch * NM;
-    uint32_t njobs = 0;
-    for (uint32_t j = warp;; j += RG_CWARPS) {
-        uint32_t q = qbase + j * J;
-        // Wait until the producer has installed job j's first slot in its ring entry — or has ended the phase with fewer
-        // jobs.  (A warp's next slot can be several ring wraps ahead of what the entry holds now, and an mbarrier parity
-        // only tells consecutive phases apart: the epoch check comes first, then the wait for the bytes.)
+    const uint32_t CH = ring_chunk(K, NCH);
+    int buf = 0;
+    uint32_t ingroup = 0, j = 0;
+    auto combine = [&](uint32_t n) {
+        ccsync();
+        if (threadIdx.x < n) {
+            float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < RG_CWARPS; wv++) {
+                s1 += sh.part[buf][0][threadIdx.x][wv];
+                if (NM == 2) s3 += sh.part[buf][NM - 1][threadIdx.x][wv];
+            }
+            const uint32_t row = sh.grow[buf][threadIdx.x];
+            float v;
+            if (NM == 2) v = __fmul_rn(silu_ref(s1), s3);
+            else if (EPI == 1) v = __fadd_rn(s1, __ldcg(res + row));
+            else v = s1;
+            out[row] = v;
+        }
+        buf ^= 1;   // the other buffer is written next; this one is reused only after the next ccsync
+    };
+    while (true) {
+        // job j's first slot — or the end of the phase (the producer publishes the job count before it installs anything
+        // of the next phase: a slot seen complete together with a published count <= j belongs to the NEXT phase)
         {
-            const uint32_t slot = q % n_slots;
+            const uint32_t slot = q % n_slots, par = (q / n_slots) & 1, fb = smem_u32(&sh.full[slot]);
             const long long t0 = clock64();
-            bool have = false;
+            bool over = false;
             while (true) {
-                const bool inst = *reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) == q / n_slots;
-                // (read AFTER the epoch: the producer publishes a phase's job count before it installs anything of the next
-                //  phase, so an installed slot number q that belongs to the NEXT phase is always seen together with the count)
+                const bool got = mbar_try(fb, par);
                 const unsigned dj = *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]);
-                if (dj != 0xFFFFu) {
-                    njobs = dj;
-                    if (j >= njobs) break;
-                }
-                if (inst) { have = true; break; }
+                if (dj != 0xFFFFu && j >= dj) { over = true; break; }
+                if (got) break;
                 if (clock64() - t0 > 4000000000LL) __trap();
             }
-            if (!have) break;
+            if (over) break;
         }
         const uint32_t row = *reinterpret_cast<volatile unsigned *>(&sh.jobrow[q % n_slots]);
-        float acc[NM][2];
+        float acc[NM];
 #pragma unroll
-        for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
-        for (uint32_t c = 0; c < nch; c++) {
-            const uint32_t k0 = c * CH, len4 = min(CH, K - k0) / 4;
-            const float4 *x4 = reinterpret_cast<const float4 *>(xs + k0);
+        for (int m = 0; m < NM; m++) acc[m] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint32_t len = min(CH, K - (uint32_t)c * CH), sl16 = len / 16;   // floats of this warp's slice
+            const bool v0 = (uint32_t)lane * 4 < sl16, v1 = (uint32_t)(lane + 32) * 4 < sl16;
 #pragma unroll
             for (int m = 0; m < NM; m++, q++) {
-                const uint32_t slot = q % n_slots, ph = (q / n_slots) & 1;
-                if (c | m) {   // later slots of the job: same epoch rule
-                    const long long t0 = clock64();
-                    while (*reinterpret_cast<volatile unsigned *>(&sh.epoch[slot]) != q / n_slots) {
-                        if (clock64() - t0 > 4000000000LL) __trap();
-                    }
-                }
-                mbar_wait(smem_u32(&sh.full[slot]), ph);
-                const float4 *w4 = reinterpret_cast<const float4 *>(ring + (size_t)slot * RG_SLOT);
-                float s0 = acc[m][0], s1 = acc[m][1];
-                uint32_t f = lane;
-                for (; f + 32 < len4; f += 64) {
-                    const float4 wa = w4[f], wb = w4[f + 32], xa = x4[f], xb = x4[f + 32];
-                    s0 = fmaf(wa.x, xa.x, s0); s0 = fmaf(wa.y, xa.y, s0); s0 = fmaf(wa.z, xa.z, s0); s0 = fmaf(wa.w, xa.w, s0);
-                    s1 = fmaf(wb.x, xb.x, s1); s1 = fmaf(wb.y, xb.y, s1); s1 = fmaf(wb.z, xb.z, s1); s1 = fmaf(wb.w, xb.w, s1);
-                }
-                if (f < len4) {
-                    const float4 wa = w4[f], xa = x4[f];
-                    s0 = fmaf(wa.x, xa.x, s0); s0 = fmaf(wa.y, xa.y, s0); s0 = fmaf(wa.z, xa.z, s0); s0 = fmaf(wa.w, xa.w, s0);
-                }
-                acc[m][0] = s0; acc[m][1] = s1;
-                __syncwarp();
+                const uint32_t slot = q % n_slots, par = (q / n_slots) & 1;
+                if (c | m) mbar_wait(smem_u32(&sh.full[slot]), par);
+                const uint32_t base = ring_base + slot * RG_SLOT + ((uint32_t)warp * sl16 + (uint32_t)lane * 4) * 4u;
+                const float4 wa = v0 ? lds4(base) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 wb = v1 ? lds4(base + 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float s = acc[m];
+                s = fmaf(wa.x, xs[c][0].x, s); s = fmaf(wa.y, xs[c][0].y, s); s = fmaf(wa.z, xs[c][0].z, s); s = fmaf(wa.w, xs[c][0].w, s);
+                s = fmaf(wb.x, xs[c][1].x, s); s = fmaf(wb.y, xs[c][1].y, s); s = fmaf(wb.z, xs[c][1].z, s); s = fmaf(wb.w, xs[c][1].w, s);
+                acc[m] = s;
+                __syncwarp();   // the FMAs above consumed every lane's loads: the slot may be refilled
                 if (lane == 0) mbar_arrive(smem_u32(&sh.empty[slot]));
             }
         }
-        float a1 = warp_sum(__fadd_rn(acc[0][0], acc[0][1]));
-        float a3 = 0.f;
-        if (NM == 2) a3 = warp_sum(__fadd_rn(acc[NM - 1][0], acc[NM - 1][1]));
-        if (lane == 0) {
-            float v;
-            if (NM == 2) v = __fmul_rn(silu_ref(a1), a3);
-            else if (EPI == 1) v = __fadd_rn(a1, __ldcg(res + row));
-            else v = a1;
-            out[row] = v;
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const float a = warp_sum(acc[m]);
+            if (lane == 0) sh.part[buf][m][ingroup][warp] = a;
         }
+        if (threadIdx.x == 0) sh.grow[buf][ingroup] = row;
+        j++;
+        if (++ingroup == RG_GROUP) { combine(ingroup); ingroup = 0; }
     }
-    qbase += njobs * J;   // (every warp left the loop through the producer's end-of-phase word, so njobs is final)
+    if (ingroup) combine(ingroup);
 }
 
-// ---- activation vector of a phase -> shared memory -----------------------------------------------------------
-// y = w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
-__device__ __forceinline__ void fill_norm(float *xs, const float *x, const float *w, uint32_t K, RingShared &sh) {
+// ---- this warp's K-slices of a phase's activation vector -> registers ------------------------------------------------
+// element index of float4 (c, v) of this thread: c * CH + warp * len_c / 16 + (v * 32 + lane) * 4 (0xFFFFFFFF: past the slice)
+template <int NCH>
+__device__ __forceinline__ uint32_t slice_index(uint32_t K, uint32_t CH, int c, int v) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    constexpr int R = 4;   // float4 kept in registers per thread (covers K <= 8192); longer vectors take the shared-memory path for the rest
-    float4 v[R], ww[R];
+    if ((uint32_t)c * CH >= K) return 0xFFFFFFFFu;
+    const uint32_t len = min(CH, K - (uint32_t)c * CH), sl16 = len / 16, o = (uint32_t)(v * 32 + lane) * 4;
+    return o < sl16 ? (uint32_t)c * CH + (uint32_t)warp * sl16 + o : 0xFFFFFFFFu;
+}
+// y = w * (x * f32(1/sqrt(mean_f64(x^2) + 1e-5)))   (ComputeForwardRMSNormFP32 + Mul, ml.go:1753-1812; llama.go:255-259)
+// The 16 warps' slices tile x exactly once, so the slice a thread keeps is also its share of the sum of squares: one L2 round trip.
+template <int NCH>
+__device__ __forceinline__ void fill_norm(float4 (&xs)[NCH][2], const float *x, const float *w, uint32_t K, RingShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t CH = ring_chunk(K, NCH);
+    float4 ww[NCH][2];
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const uint32_t f = threadIdx.x + i * RG_CTHREADS;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ww[i] = v[i];
-        if (f < K / 4) {
-            v[i] = ldcg4(x + (size_t)f * 4);
-            ww[i] = __ldg(reinterpret_cast<const float4 *>(w) + f);
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const uint32_t e = slice_index<NCH>(K, CH, c, v);
+            xs[c][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ww[c][v] = xs[c][v];
+            if (e != 0xFFFFFFFFu) {
+                xs[c][v] = ldcg4(x + e);
+                ww[c][v] = __ldg(reinterpret_cast<const float4 *>(w + e));
+            }
         }
-        acc += (double)__fmul_rn(v[i].x, v[i].x); acc += (double)__fmul_rn(v[i].y, v[i].y);
-        acc += (double)__fmul_rn(v[i].z, v[i].z); acc += (double)__fmul_rn(v[i].w, v[i].w);
-    }
-    for (uint32_t f = threadIdx.x + R * RG_CTHREADS; f < K / 4; f += RG_CTHREADS) {
-        const float4 u = ldcg4(x + (size_t)f * 4);
-        x4[f] = u;
-        acc += (double)__fmul_rn(u.x, u.x); acc += (double)__fmul_rn(u.y, u.y);
-        acc += (double)__fmul_rn(u.z, u.z); acc += (double)__fmul_rn(u.w, u.w);
-    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            acc += (double)__fmul_rn(xs[c][v].x, xs[c][v].x); acc += (double)__fmul_rn(xs[c][v].y, xs[c][v].y);
+            acc += (double)__fmul_rn(xs[c][v].z, xs[c][v].z); acc += (double)__fmul_rn(xs[c][v].w, xs[c][v].w);
+        }
     acc = warp_sum(acc);
     if (lane == 0) sh.red[warp] = acc;
     ccsync();
@@ -379,29 +363,28 @@ __device__ __forceinline__ void fill_norm(float *xs, const float *x, const float
     for (int i = 0; i < RG_CWARPS; i++) t += sh.red[i];
     const float sc = (float)(1.0 / sqrt(t / (double)K + 1e-5));
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const uint32_t f = threadIdx.x + i * RG_CTHREADS;
-        if (f < K / 4)
-            x4[f] = make_float4(__fmul_rn(ww[i].x, __fmul_rn(v[i].x, sc)), __fmul_rn(ww[i].y, __fmul_rn(v[i].y, sc)),
-                                __fmul_rn(ww[i].z, __fmul_rn(v[i].z, sc)), __fmul_rn(ww[i].w, __fmul_rn(v[i].w, sc)));
-    }
-    for (uint32_t f = threadIdx.x + R * RG_CTHREADS; f < K / 4; f += RG_CTHREADS) {
-        const float4 u = x4[f];
-        const float4 wq = __ldg(reinterpret_cast<const float4 *>(w) + f);
-        x4[f] = make_float4(__fmul_rn(wq.x, __fmul_rn(u.x, sc)), __fmul_rn(wq.y, __fmul_rn(u.y, sc)),
-                            __fmul_rn(wq.z, __fmul_rn(u.z, sc)), __fmul_rn(wq.w, __fmul_rn(u.w, sc)));
-    }
-    ccsync();   // also orders sh.red against its next use
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int v = 0; v < 2; v++)
+            xs[c][v] = make_float4(__fmul_rn(ww[c][v].x, __fmul_rn(xs[c][v].x, sc)), __fmul_rn(ww[c][v].y, __fmul_rn(xs[c][v].y, sc)),
+                                   __fmul_rn(ww[c][v].z, __fmul_rn(xs[c][v].z, sc)), __fmul_rn(ww[c][v].w, __fmul_rn(xs[c][v].w, sc)));
+    ccsync();   // sh.red may be rewritten
 }
-__device__ __forceinline__ void fill_plain(float *xs, const float *x, uint32_t K) {
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    for (uint32_t f = threadIdx.x; f < K / 4; f += RG_CTHREADS) x4[f] = ldcg4(x + (size_t)f * 4);
-    ccsync();
+template <int NCH>
+__device__ __forceinline__ void fill_plain(float4 (&xs)[NCH][2], const float *x, uint32_t K) {
+    const uint32_t CH = ring_chunk(K, NCH);
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const uint32_t e = slice_index<NCH>(K, CH, c, v);
+            xs[c][v] = e != 0xFFFFFFFFu ? ldcg4(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 }
 // merge of the attention splits (see kernels_mega.cu::merged_attention_slice): out = (sum_s O_s w_s) * f32(1 / sum_s l_s w_s)
-template <int HD>
-__device__ __forceinline__ void fill_merge(float *xs, const RingParams &p, RingShared &sh) {
-    const uint32_t S = p.splits, items = p.heads * S;
+template <int HD, int NCH>
+__device__ __forceinline__ void fill_merge(float4 (&xs)[NCH][2], const RingParams &p, RingShared &sh) {
+    const uint32_t S = p.splits, items = p.heads * S, K = p.dim, CH = ring_chunk(K, NCH);
     for (uint32_t i = threadIdx.x; i < items; i += RG_CTHREADS) {
         const float2 ml = __ldcg(reinterpret_cast<const float2 *>(p.part_ml) + i);
         sh.mrg_m[i] = ml.x;
@@ -424,29 +407,34 @@ __device__ __forceinline__ void fill_merge(float *xs, const RingParams &p, RingS
         sh.mrg_inv[h] = __fdiv_rn(1.0f, Lsum);
     }
     ccsync();
-    float4 *x4 = reinterpret_cast<float4 *>(xs);
-    constexpr int MB = 12;
-    for (uint32_t f = threadIdx.x; f < p.dim / 4; f += RG_CTHREADS) {
-        const uint32_t e = f * 4, h = e / HD, d = e % HD;
-        const float *po = p.part_o + (size_t)h * S * HD + d;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t s0 = 0; s0 < S; s0 += MB) {
-            float4 pv[MB];
+    constexpr int MB = 12;   // splits per batch of loads (a per-split loop of L2 reads costs one round trip per split)
 #pragma unroll
-            for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < NCH; c++)
 #pragma unroll
-            for (int u = 0; u < MB; u++) {
-                if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
-                    const float wgt = sh.mrg_w[h * S + s0 + u];
-                    o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
-                    o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+        for (int v = 0; v < 2; v++) {
+            const uint32_t e = slice_index<NCH>(K, CH, c, v);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e != 0xFFFFFFFFu) {
+                const uint32_t h = e / HD, d = e % HD;
+                const float *po = p.part_o + (size_t)h * S * HD + d;
+                for (uint32_t s0 = 0; s0 < S; s0 += MB) {
+                    float4 pv[MB];
+#pragma unroll
+                    for (int u = 0; u < MB; u++) pv[u] = s0 + u < S ? ldcg4(po + (size_t)(s0 + u) * HD) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < MB; u++) {
+                        if (s0 + u < S && sh.mrg_l[h * S + s0 + u] > 0.f) {
+                            const float wgt = sh.mrg_w[h * S + s0 + u];
+                            o.x = fmaf(pv[u].x, wgt, o.x); o.y = fmaf(pv[u].y, wgt, o.y);
+                            o.z = fmaf(pv[u].z, wgt, o.z); o.w = fmaf(pv[u].w, wgt, o.w);
+                        }
+                    }
                 }
+                const float inv = sh.mrg_inv[h];
+                o = make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv));
             }
+            xs[c][v] = o;
         }
-        const float inv = sh.mrg_inv[h];
-        x4[f] = make_float4(__fmul_rn(o.x, inv), __fmul_rn(o.y, inv), __fmul_rn(o.z, inv), __fmul_rn(o.w, inv));
-    }
-    ccsync();
 }
 
 // ---- attention phase: identical to kernels_mega.cu::attention_phase (items (head, split), two per CTA at a time)
@@ -573,24 +561,21 @@ __device__ __forceinline__ void attention_phase(const RingParams &p, const MegaL
     }
 }
 
-// dynamic shared memory: [ring: n_slots x RG_SLOT][xs: max(dim, ff) floats][scores: 2 x chunk_cap floats][RingShared]
-template <int HD>
+// dynamic shared memory: [ring: n_slots x RG_SLOT][scores: 2 x chunk_cap floats][RingShared]
+template <int HD, int ND, int NF>
 __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t dim = p.dim, ff = p.ff, n_slots = p.n_slots;
     uint8_t *ring = smem_raw;
-    float *xs = reinterpret_cast<float *>(smem_raw + (size_t)n_slots * RG_SLOT);
-    float *scores = xs + (dim > ff ? dim : ff);
+    float *scores = reinterpret_cast<float *>(smem_raw + (size_t)n_slots * RG_SLOT);
     RingShared &sh = *reinterpret_cast<RingShared *>(scores + 2 * (size_t)((p.chunk_cap + 3) & ~3u));
     const bool producer = threadIdx.x >= RG_CTHREADS;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < n_slots; s++) {
             mbar_init(smem_u32(&sh.full[s]), 1);
-            mbar_init(smem_u32(&sh.empty[s]), 1);
-            sh.epoch[s] = 0xFFFFFFFFu;
+            mbar_init(smem_u32(&sh.empty[s]), RG_CWARPS);
         }
-        sh.copied = 0;
         for (int i = 0; i < RG_MAX_PHASES; i++) sh.done_jobs[i] = 0xFFFFu;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -603,38 +588,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     }
     __syncthreads();   // the only CTA-wide barrier: after it the producer warp and the consumers never meet again
 
-    uint32_t pos = 0;   // slot counter (producer: next slot to fill; consumers: first slot of the current phase)
+    uint32_t pos = 0;   // slot counter: the producer's next slot to fill / the consumers' next slot to read
+    const uint32_t ring_base = smem_u32(ring);
     if (producer) {
-        if (threadIdx.x == RG_CTHREADS + 32 && p.pf_bytes) {
-            // ================= look-ahead warp =================
-            const uint32_t ring_bytes = 2 * RG_SLOT;   // closer than this to the copy cursor: not worth a prefetch
-            uint32_t sp = 0;
-            for (uint32_t li = 0; li < p.n_layers; li++) {
-                const MegaLayerHost L = p.layers[li];
-                lookahead<1>(L.wqkv, nullptr, dim, 3 * dim, sh, ring_bytes, p.pf_bytes, sp);
-                lookahead<1>(L.wo, nullptr, dim, dim, sh, ring_bytes, p.pf_bytes, sp);
-                lookahead<2>(L.w1, L.w3, dim, ff, sh, ring_bytes, p.pf_bytes, sp);
-                lookahead<1>(L.w2, nullptr, ff, dim, sh, ring_bytes, p.pf_bytes, sp);
-            }
-            if (p.final_norm) lookahead<1>(p.output, nullptr, dim, p.vocab, sh, ring_bytes, p.pf_bytes, sp);
-            return;
-        }
         if (threadIdx.x != RG_CTHREADS) return;   // one thread drives the copy engine
-        uint32_t stream_pos = 0;
         // ================= producer warp: the whole token's weights of this CTA, in schedule order =================
-        const uint32_t ring_base = smem_u32(ring);
         unsigned *tk = p.barrier + 2;   // one ticket counter per MulMat phase of the launch (zeroed with the barrier)
         uint32_t phidx = 0;
         for (uint32_t li = 0; li < p.n_layers; li++) {
             const MegaLayerHost L = p.layers[li];
-            // profiling aid: layer 5's producer stall time and job count per CTA and phase (after the 13 stamps per layer and the 5 x grid arrival stamps)
+            // profiling aid: layer 5's producer wait time and job count per CTA and phase (after the 13 stamps per layer and the 5 x grid arrival stamps)
             unsigned long long *ps = (p.trace && li == 5 && p.n_layers > 6) ? p.trace + (size_t)p.n_layers * 13 + 5 * (size_t)gridDim.x : nullptr;
-            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps); phidx++;
-            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + gridDim.x : nullptr); phidx++;
-            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + 2 * gridDim.x : nullptr); phidx++;
-            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos, ps ? ps + 3 * gridDim.x : nullptr); phidx++;
+            produce<1>(L.wqkv, nullptr, dim, 3 * dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, ps); phidx++;
+            produce<1>(L.wo, nullptr, dim, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, ps ? ps + gridDim.x : nullptr); phidx++;
+            produce<2>(L.w1, L.w3, dim, ff, pos, phidx, tk + phidx, ring_base, sh, n_slots, ps ? ps + 2 * gridDim.x : nullptr); phidx++;
+            produce<1>(L.w2, nullptr, ff, dim, pos, phidx, tk + phidx, ring_base, sh, n_slots, ps ? ps + 3 * gridDim.x : nullptr); phidx++;
         }
-        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots, stream_pos);
+        if (p.final_norm) produce<1>(p.output, nullptr, dim, p.vocab, pos, phidx, tk + phidx, ring_base, sh, n_slots);
         return;
     }
     // ================= consumers =================
@@ -669,10 +639,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     for (uint32_t li = 0; li < p.n_layers; li++) {
         const MegaLayerHost L = p.layers[li];
         stamp(li, 0);
-        // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
-        fill_norm(xs, xin, L.attention_norm, dim, sh);
-        stamp(li, 1);
-        consume<1, 0>(dim, xs, p.qkv, nullptr, pos, phidx++, ring, sh, n_slots);
+        {   // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
+            float4 xs[ND][2];
+            fill_norm<ND>(xs, xin, L.attention_norm, dim, sh);
+            stamp(li, 1);
+            consume<1, 0, ND>(dim, xs, p.qkv, nullptr, pos, phidx++, ring_base, sh, n_slots);
+        }
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 0));
         stamp(li, 3);
@@ -681,30 +653,37 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         stamp(li, 4);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 1));
         stamp(li, 5);
-        // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
-        fill_merge<HD>(xs, p, sh);
-        consume<1, 1>(dim, xs, p.y, xin, pos, phidx++, ring, sh, n_slots);
+        {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
+            float4 xs[ND][2];
+            fill_merge<HD, ND>(xs, p, sh);
+            consume<1, 1, ND>(dim, xs, p.y, xin, pos, phidx++, ring_base, sh, n_slots);
+        }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 2));
         stamp(li, 7);
-        // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
-        fill_norm(xs, p.y, L.ffn_norm, dim, sh);
-        stamp(li, 8);
-        consume<2, 0>(dim, xs, p.act, nullptr, pos, phidx++, ring, sh, n_slots);
+        {   // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
+            float4 xs[ND][2];
+            fill_norm<ND>(xs, p.y, L.ffn_norm, dim, sh);
+            stamp(li, 8);
+            consume<2, 0, ND>(dim, xs, p.act, nullptr, pos, phidx++, ring_base, sh, n_slots);
+        }
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 3));
         stamp(li, 10);
-        // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
-        fill_plain(xs, p.act, ff);
-        consume<1, 1>(ff, xs, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring, sh, n_slots);
+        {   // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
+            float4 xf[NF][2];
+            fill_plain<NF>(xf, p.act, ff);
+            consume<1, 1, NF>(ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring_base, sh, n_slots);
+        }
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers, arr(li, 4));
         stamp(li, 12);
         xin = p.x;
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
-        fill_norm(xs, xin, p.final_norm, dim, sh);
-        consume<1, 0>(dim, xs, p.logits, nullptr, pos, phidx++, ring, sh, n_slots);
+        float4 xs[ND][2];
+        fill_norm<ND>(xs, xin, p.final_norm, dim, sh);
+        consume<1, 0, ND>(dim, xs, p.logits, nullptr, pos, phidx++, ring_base, sh, n_slots);
     }
     if (p.p2p_flags && blockIdx.x == 0 && threadIdx.x == 0) {
         // every CTA passed the last grid barrier (system-scope fences below) after storing its rows of the residual
@@ -714,14 +693,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     }
 }
 
-template <int HD>
+template <int HD, int ND, int NF>
 static cudaError_t launch(const RingParams &p, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};  // function attributes are per device
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || attr[dev] < smem) {
-        e = cudaFuncSetAttribute(decode_ring_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(decode_ring_kernel<HD, ND, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr[dev] = 227 * 1024;
     }
@@ -731,7 +710,18 @@ static cudaError_t launch(const RingParams &p, size_t smem, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_ring_kernel<HD>, p);
+    return cudaLaunchKernelEx(&cfg, decode_ring_kernel<HD, ND, NF>, p);
+}
+// instantiated (chunks of dim, chunks of ff): (1,1) (1,2) test models — every head dim; (1,3) 7B, (2,4) 13B, (2,5) 30B, (2,6) 65B — head dim 128
+static bool ring_variant(uint32_t dim, uint32_t ff, uint32_t hd) {
+    const uint32_t nd = ring_nch(dim), nf = ring_nch(ff);
+    if (nd == 1 && (nf == 1 || nf == 2)) return true;
+    if (hd != 128) return false;
+    return (nd == 1 && nf == 3) || (nd == 2 && (nf == 4 || nf == 5 || nf == 6));
+}
+template <int HD>
+static cudaError_t launch_small(const RingParams &p, uint32_t nf, size_t smem, cudaStream_t st) {
+    return nf == 1 ? launch<HD, 1, 1>(p, smem, st) : launch<HD, 1, 2>(p, smem, st);
 }
 
 static uint32_t ring_splits(uint32_t heads) {
@@ -739,9 +729,9 @@ static uint32_t ring_splits(uint32_t heads) {
     return s < 1 ? 1 : (s > 32 ? 32 : s);
 }
 // shared-memory plan: returns the number of ring slots (0 = does not fit)
-static uint32_t ring_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx, size_t *smem_out) {
+static uint32_t ring_plan(uint32_t heads, uint32_t ctx, size_t *smem_out) {
     const uint32_t S = ring_splits(heads), chunk_cap = (ctx + S - 1) / S;
-    const size_t fixed = (size_t)(dim > ff ? dim : ff) * 4 + 2 * (size_t)((chunk_cap + 3) & ~3u) * 4 + sizeof(RingShared) + 128;
+    const size_t fixed = 2 * (size_t)((chunk_cap + 3) & ~3u) * 4 + sizeof(RingShared) + 128;
     const size_t cap = 227 * 1024;
     if (fixed + 4 * (size_t)RG_SLOT > cap) return 0;
     uint32_t n = (uint32_t)((cap - fixed) / RG_SLOT);
@@ -757,9 +747,9 @@ bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t v
     if (((uint64_t)(ff > vocab ? ff : vocab) > 3ull * dim ? (ff > vocab ? ff : vocab) : 3ull * dim) >= 65535ull * kNumSMs / 2) return false;   // job counts are 16-bit
     const uint32_t hd = dim / heads;
     if (hd != 128 && hd != 64 && hd != 32) return false;
-    if (dim % 4 || ff % 4) return false;               // 16-byte bulk copies
-    (void)vocab;
-    return ring_plan(dim, ff, heads, ctx, nullptr) >= 4;
+    if (dim % 64 || ff % 64) return false;             // every warp's 1/16 slice of a chunk is whole float4s; 16-byte bulk copies
+    if (!ring_variant(dim, ff, hd)) return false;
+    return ring_plan(heads, ctx, nullptr) >= 4;
 }
 
 void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
@@ -775,19 +765,22 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
     p.splits = ring_splits(h.heads);
     p.chunk_cap = (h.ctx + p.splits - 1) / p.splits;
     size_t smem = 0;
-    p.n_slots = ring_plan(h.dim, h.ff, h.heads, h.ctx, &smem);
+    p.n_slots = ring_plan(h.heads, h.ctx, &smem);
     if (const char *e = getenv("LB_RING_SLOTS")) {   // profiling aid: a shallower ring
         const uint32_t n = (uint32_t)atoi(e);
         if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
     }
-    static const uint32_t pf_kb = getenv("LB_RING_PF_KB") ? (uint32_t)atoi(getenv("LB_RING_PF_KB")) : 0u;   // L2 look-ahead per SM
-    p.pf_bytes = pf_kb * 1024u;
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
     p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
     p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (3 + 4 * (size_t)h.n_layers), st));   // grid barrier + per-phase row tickets
-    const uint32_t hd = h.dim / h.heads;
-    cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);
+    const uint32_t hd = h.dim / h.heads, nd = ring_nch(h.dim), nf = ring_nch(h.ff);
+    cudaError_t e;
+    if (nd == 1 && nf <= 2) e = hd == 128 ? launch_small<128>(p, nf, smem, st) : hd == 64 ? launch_small<64>(p, nf, smem, st) : launch_small<32>(p, nf, smem, st);
+    else if (nd == 1) e = launch<128, 1, 3>(p, smem, st);
+    else if (nf == 4) e = launch<128, 2, 4>(p, smem, st);
+    else if (nf == 5) e = launch<128, 2, 5>(p, smem, st);
+    else e = launch<128, 2, 6>(p, smem, st);
     LB_CUDA(e);
     count_launch();
 }
