@@ -118,8 +118,25 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return r;
 }
 
+// ---- fused pipeline-stage hand-off (multi-GPU layer sharding; same protocol as kernels_ring.cu) ----
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin (one thread) until *flag >= want; traps after ~10 s instead of hanging the GPU if the peer stage died
+__device__ __forceinline__ void p2p_wait(const unsigned *flag, unsigned want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u32(flag) < want) {
+        if (clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+
 // ---- grid barrier: monotonically increasing counter, reset to 0 by a memset node before each launch
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr) {
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas, unsigned long long *arrive = nullptr, bool sys = false) {
     target += nctas;
     csync();
     if (threadIdx.x == 0) {
@@ -128,7 +145,8 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             arrive[blockIdx.x] = t;
         }
-        __threadfence();
+        if (sys) __threadfence_system();   // this CTA's stores to the peer GPU are ordered before the hand-off flag
+        else __threadfence();
         atomicAdd(bar, 1u);
     }
     if (threadIdx.x == 0) {
@@ -318,7 +336,12 @@ struct MegaParams {
     unsigned *tickets, *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap;
     unsigned long long *trace;  // optional: 13 globaltimer stamps per layer written by CTA 0 (profiling aid)
-    uint32_t pre_bytes;         // shared-memory head start of the next MulMat phase: buffer size (0: off, LB_MEGA_NO_PRE)
+    uint32_t pre_bytes;         // shared-memory head start of the next MulMat phase: buffer size (0: off; LB_MEGA_PRE_KB)
+    // fused stage hand-off over NVLink peer memory (see MegaParamsHost)
+    uint32_t *p2p_flags;        // local {in_flag, ack, seq}
+    uint32_t p2p_wait_in;
+    float *p2p_x_out;
+    uint32_t *p2p_flag_out, *p2p_ack_out;
 };
 
 // ---- attention phase: items (head, split); each CTA runs up to two items CONCURRENTLY, one per half
@@ -557,6 +580,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     csync();
+    // Pipeline stage hand-off fused into this kernel: the upstream stage's kernel stored the residual stream straight into this
+    // context's x over NVLink and then raised in_flag.  Before this launch may overwrite the downstream context's x (in its
+    // last phase) the downstream stage must have consumed the previous step: ack >= seq.
+    unsigned p2p_seq = 0;
+    if (p.p2p_flags) {
+        p2p_seq = p.p2p_flags[2];
+        if (threadIdx.x == 0) {
+            if (p.p2p_wait_in) p2p_wait(p.p2p_flags + 0, p2p_seq + 1);
+            if (p.p2p_x_out) p2p_wait(p.p2p_flags + 1, p2p_seq);
+        }
+        csync();
+    }
     // thread 32 (warp 1; thread 0 fences and polls in the grid barriers) starts the head-start copies
     const bool pre_thread = threadIdx.x == 32;
     if (pre_thread && p.n_layers) mg_pre_issue(pre, p.layers[0].wqkv, nullptr, 3 * dim, dim);
@@ -601,14 +636,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         {   // ---- P5: w2 + residual (llama.go:363-366)
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
-            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, p.x, p.y, sh, sched + li * 4 + 3, pre, pre_parity);
+            // (the stage's last layer writes the residual into the next stage's x)
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, sh, sched + li * 4 + 3,
+                                  pre, pre_parity);
         }
         if (pre_thread) {
             if (li + 1 < p.n_layers) mg_pre_issue(pre, p.layers[li + 1].wqkv, nullptr, 3 * dim, dim);
             else if (p.final_norm) mg_pre_issue(pre, p.output, nullptr, p.vocab, dim);
         }
         stamp(li, 11);
-        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4));
+        grid_barrier(p.barrier, target, gridDim.x, arr(li, 4), p.p2p_x_out != nullptr && li + 1 == p.n_layers);
         stamp(li, 12);
         xin = p.x;
     }
@@ -616,6 +653,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         float4 xs[VD];
         rms_slice<VD>(xin, p.final_norm, dim, xs, sh);
         gemv_phase<VD, false>(p.output, nullptr, p.vocab, dim, xs, p.logits, nullptr, sh, sched + p.n_layers * 4, pre, pre_parity);
+    }
+    if (p.p2p_flags && blockIdx.x == 0 && threadIdx.x == 0) {
+        // every CTA passed the last grid barrier (system-scope fences) after storing its rows of the residual
+        __threadfence_system();
+        if (p.p2p_flag_out) st_release_sys_u32(p.p2p_flag_out + 0, p2p_seq + 1);   // downstream: your input for step seq+1 is there
+        if (p.p2p_ack_out) st_release_sys_u32(p.p2p_ack_out + 1, p2p_seq + 1);     // upstream: I am done with what you sent for step seq+1
     }
 }
 
@@ -971,6 +1014,8 @@ void decode_mega(const MegaParamsHost &h, cudaStream_t st) {
     LB_CHECK(pick_variant(h.dim, h.ff, hd, vd, vf) && decode_mega_supported(h.dim, h.ff, h.heads), "decode_mega: unsupported shape");
     size_t smem = 2 * (size_t)p.chunk_cap * sizeof(float);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    p.p2p_flags = h.q8 ? nullptr : h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
+    p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
     // head-start buffer (opt-in, LB_MEGA_PRE_KB=<KB>): measured SLOWER than no buffer (profiles/README.md r02j: 180 tok/s with
     // 196 KB, 217 with 96 KB, 221.5 without) — every MulMat phase streams slower once the shared-memory carve-out
     // shrinks the L1 that the 128 KB of LDGs in flight per SM pass through, and the barriers grow with the copy traffic.

@@ -66,8 +66,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (try_wait suspends the thread in hardware for a bounded time; the spin counter only exists so that a pipeline bug traps
+//  instead of hanging the box — no clock read per iteration: ncu r02n counted 3.5-6.5 % CS2R instructions in the ring kernels)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (true) {
         uint32_t done;
         asm volatile(
@@ -78,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline bug must not hang the box
+        if (++spins > (1u << 24)) __trap();
     }
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)

@@ -225,7 +225,9 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     const bool mega_ok = k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
     const bool ring_ok = getenv("LB_NO_RING") == nullptr && k::decode_ring_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
     use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && (mega_ok || ring_ok);
-    use_ring = use_mega && ring_ok;   // TMA-ring megakernel (kernels_ring.cu); LB_NO_RING=1 keeps the register-fed one
+    // TMA-ring megakernel (kernels_ring.cu): measured 4 % behind the register-fed one (r02m: 210 vs 219 tok/s) — opt-in with LB_RING=1;
+    // it is the only variant for shapes kernels_mega.cu has no K-slice instantiation for
+    use_ring = use_mega && ring_ok && (getenv("LB_RING") != nullptr || !mega_ok);
     // Q8_0 weights: TMA ring + int8 tensor cores (kernels_ring_q8.cu); LB_NO_RING_Q8=1 keeps the per-op kernels
     use_ring_q8 = m->q8() && getenv("LB_NO_MEGA") == nullptr && getenv("LB_NO_RING_Q8") == nullptr &&
                   k::decode_ring_q8_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
@@ -314,7 +316,7 @@ void Context::forward(uint32_t n, bool tokens_indirect, bool all_rows, const flo
         mp.tickets = reinterpret_cast<unsigned *>(mp.part_ml + (size_t)H * 32 * 2);
         mp.barrier = mega_barrier;
         mp.trace = mega_trace;
-        if (p2p_on && use_ring) {
+        if (p2p_on && !use_ring_q8) {
             mp.p2p_flags = p2p_flags;
             mp.p2p_wait_in = !model->has_embedding();
             mp.p2p_x_out = p2p_x_out; mp.p2p_flag_out = p2p_flag_out; mp.p2p_ack_out = p2p_ack_out;

@@ -125,7 +125,7 @@ void p2p_import(llama::Context **ctxs, uint32_t n_seq, const void *down, const v
     for (uint32_t s = 0; s < n_seq; s++) {
         llama::Context *c = ctxs[s];
         LB_CHECK(c->p2p_flags != nullptr, "p2p_import: call p2p_export first");
-        LB_CHECK(c->use_ring, "p2p_import: the fused hand-off needs the TMA-ring megakernel (unsupported shape or LB_NO_RING)");
+        LB_CHECK(c->use_mega && !c->use_ring_q8, "p2p_import: the fused hand-off needs the FP32 decode megakernel (unsupported shape, Q8 weights or LB_NO_MEGA)");
         LB_CHECK(!c->stage_graph, "p2p_import: the stage graph is already captured");
         LB_CUDA(cudaSetDevice(c->model->device));
         cudaIpcMemHandle_t h;

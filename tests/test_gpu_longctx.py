@@ -63,16 +63,19 @@ def small_ref(synth, oracle):
     return hp, tensors, ids, gen, ref
 
 
-@pytest.mark.parametrize("path", ["mega", "perop"])
+@pytest.mark.parametrize("path", ["mega", "ring", "perop"])
 def test_small_model_at_T3000_against_oracle(L, small_ref, path, monkeypatch):
     """prefill of 3000 tokens in ONE Eval (prefill attention kernel at N = 3000, tcgen05 GEMMs), then 4 decode
-    steps at past 3000..3003: `mega` = persistent megakernel (chunk 94 > 64: second score trip + V reload),
-    `perop` = LB_NO_MEGA=1 -> attention_decode_kernel past T = 1024."""
+    steps at past 3000..3003: `mega` = persistent register-fed megakernel (chunk 94 > 64: second score trip + V
+    reload), `ring` = LB_RING=1 -> the TMA-ring megakernel (kernels_ring.cu), `perop` = LB_NO_MEGA=1 ->
+    attention_decode_kernel past T = 1024."""
     hp, tensors, ids, gen, ref = small_ref
+    monkeypatch.delenv("LB_NO_MEGA", raising=False)
+    monkeypatch.delenv("LB_RING", raising=False)
     if path == "perop":
         monkeypatch.setenv("LB_NO_MEGA", "1")
-    else:
-        monkeypatch.delenv("LB_NO_MEGA", raising=False)
+    elif path == "ring":
+        monkeypatch.setenv("LB_RING", "1")
     model = L.Model(hp).load(tensors)
     lctx = L.NewContext(model, SMALL_CTX)
     errs = [assert_logits_close(L.Eval(lctx, ids, 0).copy(), ref["prefill"], what=f"{path} prefill T={SMALL_T}")]
@@ -128,26 +131,39 @@ SHAPED = [
 ]
 
 
+_SHAPED_REF = {}
+
+
+@pytest.mark.parametrize("path", ["mega", "ring"])
 @pytest.mark.parametrize("name,dims,ctx,T", SHAPED, ids=[s[0] for s in SHAPED])
-def test_shaped_layers_at_operating_T_against_oracle(L, synth, oracle, name, dims, ctx, T):
+def test_shaped_layers_at_operating_T_against_oracle(L, synth, oracle, name, dims, ctx, T, path, monkeypatch):
+    if path == "ring":
+        monkeypatch.setenv("LB_RING", "1")    # the TMA-ring megakernel (opt-in): K chunking of the 13B / 65B shapes
+    else:
+        monkeypatch.delenv("LB_RING", raising=False)
     hp = synth.HParams(*dims)           # vocab cut to 2048: the lm_head shape is covered by test_gpu_eval.py
     model = L.Model(hp).init_random(0)
     rs = np.random.RandomState(7)
     ids = rs.randint(3, hp.vocab, size=T).astype(np.uint32)
     gen = rs.randint(3, hp.vocab, size=4).astype(np.uint32)
-    oracle.set_dot_mode(True)
-    try:
-        om = oracle.OracleModel(hp).load(synth.synth_model_fast(0, hp))
-        oc = oracle.OracleContext(om, ctx)
-        lctx = L.NewContext(model, ctx)
-        e0 = assert_logits_close(L.Eval(lctx, ids, 0).copy(), oracle_prefill(oc, ids), what=f"{name}-shape prefill T={T}")
-        for i, t in enumerate(gen):
-            got = L.Eval(lctx, [int(t)], T + i).copy()
-            e1 = assert_logits_close(got, oc.eval([int(t)], T + i), what=f"{name}-shape decode past {T + i}")
-        k, v = lctx.kv(hp.layers - 1, T - 8, 12)
-        ko, vo = oc.kv()
-        np.testing.assert_allclose(k, ko[hp.layers - 1, T - 8:T + 4], rtol=0, atol=1e-4 * np.abs(ko[hp.layers - 1, :T + 4]).max())
-        np.testing.assert_allclose(v, vo[hp.layers - 1, T - 8:T + 4], rtol=0, atol=1e-4 * np.abs(vo[hp.layers - 1, :T + 4]).max())
-    finally:
-        oracle.set_dot_mode(False)
-    print(f"[{name}-shaped, ctx {ctx}] prefill rel err {e0:.3e}, decode at T={T + 3} rel err {e1:.3e}")
+    if name not in _SHAPED_REF:         # the oracle's side once per shape (both decode paths are checked against it)
+        oracle.set_dot_mode(True)
+        try:
+            om = oracle.OracleModel(hp).load(synth.synth_model_fast(0, hp))
+            oc = oracle.OracleContext(om, ctx)
+            ref_prefill = oracle_prefill(oc, ids)
+            ref_steps = [oc.eval([int(t)], T + i) for i, t in enumerate(gen)]
+            ko, vo = oc.kv()
+            _SHAPED_REF[name] = (ref_prefill, ref_steps, ko[hp.layers - 1, :T + 4].copy(), vo[hp.layers - 1, :T + 4].copy())
+        finally:
+            oracle.set_dot_mode(False)
+    ref_prefill, ref_steps, ko, vo = _SHAPED_REF[name]
+    lctx = L.NewContext(model, ctx)
+    e0 = assert_logits_close(L.Eval(lctx, ids, 0).copy(), ref_prefill, what=f"{name}-shape prefill T={T}")
+    for i, t in enumerate(gen):
+        got = L.Eval(lctx, [int(t)], T + i).copy()
+        e1 = assert_logits_close(got, ref_steps[i], what=f"{name}-shape {path} decode past {T + i}")
+    k, v = lctx.kv(hp.layers - 1, T - 8, 12)
+    np.testing.assert_allclose(k, ko[T - 8:T + 4], rtol=0, atol=1e-4 * np.abs(ko).max())
+    np.testing.assert_allclose(v, vo[T - 8:T + 4], rtol=0, atol=1e-4 * np.abs(vo).max())
+    print(f"[{name}-shaped {path}, ctx {ctx}] prefill rel err {e0:.3e}, decode at T={T + 3} rel err {e1:.3e}")
