@@ -84,10 +84,11 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // (try_wait suspends the thread in hardware for a bounded time; the spin counter only exists so that a pipeline bug traps
 //  after a few seconds instead of hanging the box — no clock read per iteration: ncu r02n counted 6.5 % CS2R instructions)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
     if (mbar_try(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
+        if (backoff_ns) __nanosleep(backoff_ns);   // (consumers) polling burns issue slots and power: the decode step runs into the 1 kW cap
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -115,6 +116,7 @@ struct RingParams {
     float *part_o, *part_ml;
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots;
+    uint32_t spin_ns;             // consumers' back-off between polls of a slot's mbarrier (LB_RING_SPIN_NS)
     unsigned long long *trace;    // optional: 13 globaltimer stamps per layer written by consumer thread 0 of CTA 0 (+ per-CTA statistics of layer 5)
     // fused stage hand-off over NVLink peer memory (see MegaParamsHost)
     uint32_t *p2p_flags;          // local {in_flag, ack, seq}
@@ -183,10 +185,11 @@ __host__ __device__ __forceinline__ uint32_t ring_chunk(uint32_t K, uint32_t nch
 
 // Work of a MulMat phase = "jobs", one per output row (its NCH chunks, both matrices of the SwiGLU pair).
 // 4/5 of the rows are dealt out statically (CTA c: a contiguous block), the rest is a pool handed out a few rows per ticket
-// (atomic counter per phase) — drawn by the PRODUCER as it runs ahead, one ticket at a time (the first one a few rows before
-// the static block ends, the next one when a ticket's rows start), so an SM that streams faster takes more rows and all
-// CTAs reach the grid barrier within about a ticket of each other.  (r02k: drawing two tickets up front handed the whole
-// pool of a short phase to the first 128 CTAs to ask — wo and w2 ran as an UNBALANCED static split.)
+// (atomic counter per phase) — drawn by the PRODUCER as it runs ahead, two tickets in flight, the first two a few rows before
+// the static block ends, so an SM that streams faster takes more rows and all CTAs reach the grid barrier within about a
+// ticket of each other.  (r02k: drawing two tickets at the START of a phase handed the whole pool of a short phase to the
+// first 128 CTAs to ask — wo and w2 ran as an UNBALANCED static split; r02o: one ticket at a time exposed the atomic's
+// round trip, wo 13.6 us for 9.6 us of stream.)
 // Every warp consumes every job, in issue order; the job's row number travels in sh.jobrow[]; the producer ends a phase by
 // publishing its job count BEFORE it installs anything of the next phase.
 constexpr unsigned RG_STATIC_NUM = 4, RG_STATIC_DEN = 5;
@@ -228,17 +231,21 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
         }
         njobs++;
     };
-    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q, early = Q > 6 ? r1 - 6 : r0;   // draw the first ticket ~6 rows before the static block ends
-    unsigned ta = 0;
-    bool have = false;
+    // two tickets in flight (an L2 atomic round trip under load is ~1 us = 2-3 rows of stream), the first drawn ~8 rows and the
+    // second ~4 rows before the static block ends — late enough that a CTA only takes tickets when it is about to need them
+    const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
+    const uint32_t e1 = Q > 8 ? r1 - 8 : r0, e2 = Q > 4 ? r1 - 4 : r0;
+    unsigned ta = 0, tb = 0;
+    if (Q == 0) { ta = atomicAdd(ticket, 1u); tb = atomicAdd(ticket, 1u); }
     for (uint32_t row = r0; row < r1; row++) {
-        if (row == early) { ta = atomicAdd(ticket, 1u); have = true; }
+        if (row == e1) ta = atomicAdd(ticket, 1u);
+        if (row == e2) tb = atomicAdd(ticket, 1u);
         job(row);
     }
-    if (!have) ta = atomicAdd(ticket, 1u);
     while ((uint64_t)pool0 + (uint64_t)ta * TR < M) {
         const uint32_t rb = pool0 + ta * TR, re = min(M, rb + TR);
-        ta = atomicAdd(ticket, 1u);                             // next ticket, overlapped with these rows' copies
+        ta = tb;
+        tb = atomicAdd(ticket, 1u);                             // next ticket, overlapped with these rows' copies
         for (uint32_t row = rb; row < re; row++) job(row);
     }
     // end of phase: the job count for the consumers
@@ -254,7 +261,7 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI, int NCH>
 __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], float *out, const float *res, RingPos &q, uint32_t phidx,
-                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots) {
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t spin_ns) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t CH = ring_chunk(K, NCH);
     int buf = 0;
@@ -289,6 +296,7 @@ __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], 
                 const unsigned dj = *reinterpret_cast<volatile unsigned short *>(&sh.done_jobs[phidx]);
                 if (dj != 0xFFFFu && j >= dj) { over = true; break; }
                 if (got) break;
+                if (spin_ns) __nanosleep(spin_ns);
                 if (++spins > (1u << 24)) __trap();
             }
             if (over) break;
@@ -304,7 +312,7 @@ __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], 
 #pragma unroll
             for (int m = 0; m < NM; m++) {
                 const uint32_t slot = q.slot;
-                if (c | m) mbar_wait(smem_u32(&sh.full[slot]), q.par);
+                if (c | m) mbar_wait(smem_u32(&sh.full[slot]), q.par, spin_ns);
                 const uint32_t base = ring_base + slot * RG_SLOT + ((uint32_t)warp * sl16 + (uint32_t)lane * 4) * 4u;
                 const float4 wa = v0 ? lds4(base) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 wb = v1 ? lds4(base + 512) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
             float4 xs[ND][2];
             fill_norm<ND>(xs, xin, L.attention_norm, dim, sh);
             stamp(li, 1);
-            consume<1, 0, ND>(dim, xs, p.qkv, nullptr, pos, phidx++, ring_base, sh, n_slots);
+            consume<1, 0, ND>(dim, xs, p.qkv, nullptr, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
         }
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 0));
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         {   // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
             float4 xs[ND][2];
             fill_merge<HD, ND>(xs, p, sh);
-            consume<1, 1, ND>(dim, xs, p.y, xin, pos, phidx++, ring_base, sh, n_slots);
+            consume<1, 1, ND>(dim, xs, p.y, xin, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
         }
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 2));
@@ -676,7 +684,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
             float4 xs[ND][2];
             fill_norm<ND>(xs, p.y, L.ffn_norm, dim, sh);
             stamp(li, 8);
-            consume<2, 0, ND>(dim, xs, p.act, nullptr, pos, phidx++, ring_base, sh, n_slots);
+            consume<2, 0, ND>(dim, xs, p.act, nullptr, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
         }
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x, false, arr(li, 3));
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         {   // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
             float4 xf[NF][2];
             fill_plain<NF>(xf, p.act, ff);
-            consume<1, 1, NF>(ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring_base, sh, n_slots);
+            consume<1, 1, NF>(ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
         }
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers, arr(li, 4));
@@ -694,7 +702,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         float4 xs[ND][2];
         fill_norm<ND>(xs, xin, p.final_norm, dim, sh);
-        consume<1, 0, ND>(dim, xs, p.logits, nullptr, pos, phidx++, ring_base, sh, n_slots);
+        consume<1, 0, ND>(dim, xs, p.logits, nullptr, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
     }
     if (p.p2p_flags && blockIdx.x == 0 && threadIdx.x == 0) {
         // every CTA passed the last grid barrier (system-scope fences below) after storing its rows of the residual
@@ -782,6 +790,8 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
         if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
     }
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    static const uint32_t spin_ns = getenv("LB_RING_SPIN_NS") ? (uint32_t)atoi(getenv("LB_RING_SPIN_NS")) : 0u;
+    p.spin_ns = spin_ns;
     p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
     p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * (3 + 4 * (size_t)h.n_layers), st));   // grid barrier + per-phase row tickets

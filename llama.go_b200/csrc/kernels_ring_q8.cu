@@ -65,7 +65,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // (try_wait suspends the thread in hardware for a bounded time; the spin counter only exists so that a pipeline bug traps
 //  instead of hanging the box — no clock read per iteration: ncu r02n counted 3.5-6.5 % CS2R instructions in the ring kernels)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
     uint32_t spins = 0;
     while (true) {
         uint32_t done;
@@ -77,6 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
+        if (backoff_ns) __nanosleep(backoff_ns);   // 16 warps polling one mbarrier compete with the producer's and the copy engine's updates of it
         if (++spins > (1u << 24)) __trap();
     }
 }
@@ -108,6 +109,7 @@ struct RQParams {
     float *part_o, *part_ml;
     unsigned *barrier;
     uint32_t dim, ff, heads, vocab, ctx, splits, chunk_cap, n_slots, kpad;   // kpad = max(dim, ff) rounded up to 1024
+    uint32_t spin_ns;   // consumers' back-off between polls of a slot's mbarrier (LB_Q8_SPIN_NS)
     unsigned long long *trace;
 };
 
@@ -368,7 +370,7 @@ __device__ __forceinline__ void merge_digits(const RQParams &p, uint32_t kp, int
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI>
 __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *dig, const float *xsc, float *out, const float *res,
-                                        uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots) {
+                                        uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots, uint32_t spin_ns) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     uint32_t r0, r1;
     cta_rows(M, ph++, r0, r1);
@@ -395,7 +397,7 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
             }
 #pragma unroll
             for (int m = 0; m < NM; m++) {
-                mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase);
+                mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase, spin_ns);
                 const uint8_t *sl = ring + (size_t)pos.slot * RQ_SLOT;
                 const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));   // blocks in this record (the last segment may be short)
                 uint2 qa[2], qb[2];
@@ -418,8 +420,6 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
                     // intermediate is exact, the final FMA rounds c1 * w1 + c0 * w0 once — bit-identical to the I2F form)
                     float va = fmaf(__int_as_float(c[1] + 0x4B400000), w1, fmaf(__int_as_float(c[0] + 0x4B400000), w0, koff));   // row g: this lane's two digit columns
                     float vb = fmaf(__int_as_float(c[3] + 0x4B400000), w1, fmaf(__int_as_float(c[2] + 0x4B400000), w0, koff));   // row g + 8
-                    va += __shfl_xor_sync(0xffffffffu, va, 1);                       // digits 0,1 (t = 0) + digits 2,3 (t = 1)
-                    vb += __shfl_xor_sync(0xffffffffu, vb, 1);
                     acc[m][0] = fmaf(va, __fmul_rn(da[j], sx[j]), acc[m][0]);
                     acc[m][1] = fmaf(vb, __fmul_rn(db[j], sx[j]), acc[m][1]);
                 }
@@ -427,6 +427,13 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
                 if (lane == 0) mbar_arrive(smem_u32(&sh.empty[pos.slot]));
                 pos.next(n_slots);
             }
+        }
+        // digits 0,1 (lanes t = 0) + digits 2,3 (t = 1): the block scale d_w * s is common to both, so the two lanes' sums
+        // are added once per tile instead of once per block
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            acc[m][0] += __shfl_xor_sync(0xffffffffu, acc[m][0], 1);
+            acc[m][1] += __shfl_xor_sync(0xffffffffu, acc[m][1], 1);
         }
         // ---- combine the 16 warps' K-slices of this tile (lanes t == 0 hold rows g and g + 8)
         if (t == 0) {
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         norm_digits(xin, L.attention_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 1);
-        consume<1, 0>(dim, 3 * dim, dig, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots);
+        consume<1, 0>(dim, 3 * dim, dig, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
@@ -654,20 +661,20 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         stamp(li, 5);
         // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
         merge_digits<HD>(p, kp_dim, dig, xsc, sh);
-        consume<1, 1>(dim, dim, dig, xsc, p.y, xin, ph, pos, ring, sh, n_slots);
+        consume<1, 1>(dim, dim, dig, xsc, p.y, xin, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         norm_digits(p.y, L.ffn_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 8);
-        consume<2, 0>(dim, ff, dig, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots);
+        consume<2, 0>(dim, ff, dig, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366)
         plain_digits(p.act, ff, kp_ff, dig, xsc);
-        consume<1, 1>(ff, dim, dig, xsc, p.x, p.y, ph, pos, ring, sh, n_slots);
+        consume<1, 1>(ff, dim, dig, xsc, p.x, p.y, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 12);
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         norm_digits(xin, p.final_norm, dim, kp_dim, dig, xsc, sh);
-        consume<1, 0>(dim, p.vocab, dig, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots);
+        consume<1, 0>(dim, p.vocab, dig, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
     }
 }
 
@@ -795,6 +802,8 @@ void decode_ring_q8(const MegaParamsHost &h, const RingQ8Layer *planes_dev, cons
     size_t smem = 0;
     p.n_slots = q8_plan(h.dim, h.ff, h.heads, h.ctx, &p.kpad, &smem);
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
+    static const uint32_t spin_ns = getenv("LB_Q8_SPIN_NS") ? (uint32_t)atoi(getenv("LB_Q8_SPIN_NS")) : 0u;
+    p.spin_ns = spin_ns;
     LB_CUDA(cudaMemsetAsync(h.barrier, 0, sizeof(unsigned) * 2, st));
     const uint32_t hd = h.dim / h.heads;
     cudaError_t e = hd == 128 ? launch<128>(p, smem, st) : hd == 64 ? launch<64>(p, smem, st) : launch<32>(p, smem, st);

@@ -225,9 +225,9 @@ Context::Context(Model *m, uint32_t cs) : model(m), ctx_size(cs) {
     const bool mega_ok = k::decode_mega_supported(hp.dim, hp.ff(), hp.heads);
     const bool ring_ok = getenv("LB_NO_RING") == nullptr && k::decode_ring_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);
     use_mega = getenv("LB_NO_MEGA") == nullptr && !m->q8() && (mega_ok || ring_ok);
-    // TMA-ring megakernel (kernels_ring.cu): measured 4 % behind the register-fed one (r02m: 210 vs 219 tok/s) — opt-in with LB_RING=1;
-    // it is the only variant for shapes kernels_mega.cu has no K-slice instantiation for
-    use_ring = use_mega && ring_ok && (getenv("LB_RING") != nullptr || !mega_ok);
+    // TMA-ring megakernel (kernels_ring.cu, version 3): 234 vs 221 tok/s on an un-capped box, 224 vs 216 under the power cap
+    // (profiles/README.md r02o/r02p) — the default; LB_NO_RING=1 keeps the register-fed megakernel (kernels_mega.cu)
+    use_ring = use_mega && ring_ok;
     // Q8_0 weights: TMA ring + int8 tensor cores (kernels_ring_q8.cu); LB_NO_RING_Q8=1 keeps the per-op kernels
     use_ring_q8 = m->q8() && getenv("LB_NO_MEGA") == nullptr && getenv("LB_NO_RING_Q8") == nullptr &&
                   k::decode_ring_q8_supported(hp.dim, hp.ff(), hp.heads, hp.vocab, cs);

@@ -66,16 +66,16 @@ def small_ref(synth, oracle):
 @pytest.mark.parametrize("path", ["mega", "ring", "perop"])
 def test_small_model_at_T3000_against_oracle(L, small_ref, path, monkeypatch):
     """prefill of 3000 tokens in ONE Eval (prefill attention kernel at N = 3000, tcgen05 GEMMs), then 4 decode
-    steps at past 3000..3003: `mega` = persistent register-fed megakernel (chunk 94 > 64: second score trip + V
-    reload), `ring` = LB_RING=1 -> the TMA-ring megakernel (kernels_ring.cu), `perop` = LB_NO_MEGA=1 ->
-    attention_decode_kernel past T = 1024."""
+    steps at past 3000..3003: `ring` = the default TMA-ring megakernel (kernels_ring.cu; chunk 94 > 64: second score
+    trip + V reload), `mega` = LB_NO_RING=1 -> the register-fed megakernel (kernels_mega.cu), `perop` = LB_NO_MEGA=1
+    -> attention_decode_kernel past T = 1024."""
     hp, tensors, ids, gen, ref = small_ref
     monkeypatch.delenv("LB_NO_MEGA", raising=False)
-    monkeypatch.delenv("LB_RING", raising=False)
+    monkeypatch.delenv("LB_NO_RING", raising=False)
     if path == "perop":
         monkeypatch.setenv("LB_NO_MEGA", "1")
-    elif path == "ring":
-        monkeypatch.setenv("LB_RING", "1")
+    elif path == "mega":
+        monkeypatch.setenv("LB_NO_RING", "1")
     model = L.Model(hp).load(tensors)
     lctx = L.NewContext(model, SMALL_CTX)
     errs = [assert_logits_close(L.Eval(lctx, ids, 0).copy(), ref["prefill"], what=f"{path} prefill T={SMALL_T}")]
@@ -137,10 +137,10 @@ _SHAPED_REF = {}
 @pytest.mark.parametrize("path", ["mega", "ring"])
 @pytest.mark.parametrize("name,dims,ctx,T", SHAPED, ids=[s[0] for s in SHAPED])
 def test_shaped_layers_at_operating_T_against_oracle(L, synth, oracle, name, dims, ctx, T, path, monkeypatch):
-    if path == "ring":
-        monkeypatch.setenv("LB_RING", "1")    # the TMA-ring megakernel (opt-in): K chunking of the 13B / 65B shapes
+    if path == "mega":
+        monkeypatch.setenv("LB_NO_RING", "1")    # the register-fed megakernel; default = the TMA-ring one (K chunking of the 13B / 65B shapes)
     else:
-        monkeypatch.delenv("LB_RING", raising=False)
+        monkeypatch.delenv("LB_NO_RING", raising=False)
     hp = synth.HParams(*dims)           # vocab cut to 2048: the lm_head shape is covered by test_gpu_eval.py
     model = L.Model(hp).init_random(0)
     rs = np.random.RandomState(7)
