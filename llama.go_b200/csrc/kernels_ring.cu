@@ -193,7 +193,13 @@ __host__ __device__ __forceinline__ uint32_t ring_chunk(uint32_t K, uint32_t nch
 // Every warp consumes every job, in issue order; the job's row number travels in sh.jobrow[]; the producer ends a phase by
 // publishing its job count BEFORE it installs anything of the next phase.
 constexpr unsigned RG_STATIC_NUM = 4, RG_STATIC_DEN = 5;
-__device__ __forceinline__ uint32_t ticket_rows(uint32_t M) { return M / gridDim.x >= 64 ? 4u : 2u; }
+// rows per ticket: ~64 KB of stream (1.4 us of an SM's share; r02q: 4-row tickets of the w1|w3 pair = 128 KB left the CTAs up to
+// 4.6 us apart at the barrier), at most 2 rows when a CTA has fewer than 48 rows in the phase
+__device__ __forceinline__ uint32_t ticket_rows(uint32_t M, uint32_t K, uint32_t NM) {
+    uint32_t t = 65536u / (K * 4u * NM);
+    t = t < 1u ? 1u : (t > 4u ? 4u : t);
+    return (M / gridDim.x < 48u && t > 2u) ? 2u : t;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // producer (one thread)
@@ -204,7 +210,7 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
     unsigned long long stall = 0;   // profiling aid (pstat != nullptr): ns this producer spent waiting for a free ring entry
     const uint32_t nch = ring_nch(K), CH = ring_chunk(K, nch);
     const uint32_t Q = (uint32_t)(((uint64_t)M * RG_STATIC_NUM) / (RG_STATIC_DEN * gridDim.x));   // static rows per CTA
-    const uint32_t pool0 = Q * gridDim.x, TR = ticket_rows(M);
+    const uint32_t pool0 = Q * gridDim.x, TR = ticket_rows(M, K, NM);
     uint32_t njobs = 0;
     auto job = [&](uint32_t row) {
         for (uint32_t c = 0; c < nch; c++) {
