@@ -262,6 +262,13 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- our arm
+DECODE_PATHS = {"ring": "persistent cooperative megakernel fed by a TMA ring (kernels_ring.cu)",
+                "mega": "persistent cooperative megakernel, register-fed (kernels_mega.cu)",
+                "ring_q8": "persistent cooperative Q8_0 megakernel on a TMA ring, int8 tensor cores (kernels_ring_q8.cu)",
+                "perop": "per-op kernels + PDL"}
+MEGA_KERNELS = {"ring": "decode_ring_kernel", "mega": "decode_mega_kernel", "ring_q8": "decode_ring_q8_kernel"}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -365,6 +372,7 @@ def measure_decode(llama, lib, hp, q8, ctx_size, K, W, sampler=None):
     T_mid = PROMPT_LEN + W + K / 2.0
     bytes_per_token = model.weight_bytes_per_token + 2 * hp.layers * T_mid * hp.dim * 4 + 2 * hp.layers * hp.dim * 4 + 4 * hp.vocab
     return {"model": model, "lctx": lctx, "value": value, "ms": ms, "e2e": e2e, "launches": int(launches), "clocks": clocks,
+            "decode_path": DECODE_PATHS.get(lib.lb_context_decode_path(lctx._h).decode(), "?"),
             "repeats": R, "repeat_ms": [round(r, 3) for r in reps], "setup_s": t_setup, "bytes_per_token": int(bytes_per_token),
             "prefill": {"tokens": PROMPT_LEN, "ms": round(prefill_s * 1e3, 2), "tok_s": round(PROMPT_LEN / prefill_s, 1),
                         "what": "lb_eval of the %d-token prompt (host buffers, synchronous; tcgen05 3xTF32 GEMMs + prefill attention)" % PROMPT_LEN}}
@@ -372,7 +380,7 @@ def measure_decode(llama, lib, hp, q8, ctx_size, K, W, sampler=None):
 
 def sub_record(r, peak, what, K, W, extra=None):
     gbs = r["bytes_per_token"] * r["value"] / 1e9
-    rec = {"workload": what, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K, "steps": K, "warmup": W, "repeats": r["repeats"],
+    rec = {"workload": what, "decode_path": r.get("decode_path"), "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K, "steps": K, "warmup": W, "repeats": r["repeats"],
            "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "prefill": r["prefill"],
            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
                         "bytes_per_step": r["bytes_per_token"], "roofline_tok_s": round(peak * 1e9 / r["bytes_per_token"], 1)}}
@@ -477,7 +485,8 @@ def run_single_gpu(args):
     bytes_per_token = r["bytes_per_token"]
     step_gbs = bytes_per_token * value / 1e9
 
-    mega = (not q8) and os.environ.get("LB_NO_MEGA") is None
+    path = lib.lb_context_decode_path(lctx._h).decode()
+    mega = path in MEGA_KERNELS      # one persistent launch per token: the whole step is the dominant kernel
     ref_stream = compare_with_reference_stream(llama, synth, model) if (args.model == "7b" and not q8) else None
 
     # ---- the other single-GPU BASELINE configurations, same process, weights freed in between
@@ -529,16 +538,16 @@ def run_single_gpu(args):
                                % (args.model.upper(), "Q8_0" if q8 else "FP32", ctx_size, PROMPT_LEN, PROMPT_LEN + W, PROMPT_LEN + W + K),
                    "weights": "random-init (device RNG, seed 0) %.1f GB" % (wbytes / 1e9), "kv_cache": "fp32 in HBM",
                    "sequences_in_flight": 1, "parallelism": "single GPU", "l2": "inputs>L2 (%.1f GB weights per step)" % (wbytes / 1e9),
-                   "decode_path": "persistent cooperative megakernel, CUDA-graph replay" if mega else "per-op kernels + PDL, CUDA-graph replay",
+                   "decode_path": DECODE_PATHS.get(path, path) + ", CUDA-graph replay",
                    "timed_regions": "%d regions of exactly %d steps each (CUDA events), mean reported" % (repeats, K),
                    "setup_s": round(t_setup, 1)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 4 + 8, "d2h_bytes_per_step": 4 * hp.vocab,
                 "api": "lb_eval (C-ABI, host buffers, synchronous)"},
         "gpu_launches": int(launches),
-        "roofline": ({"bound": "hbm", "kernel": "decode_mega_kernel (whole token: 32 layers + lm_head in one persistent launch)",
+        "roofline": ({"bound": "hbm", "kernel": "%s (whole token: 32 layers + lm_head in one persistent launch)" % MEGA_KERNELS.get(path, path),
                       "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(step_gbs / peak, 4),
-                      "traffic": kernel_traffic("decode_mega_kernel"), "peak_source": peak_src,
+                      "traffic": kernel_traffic(MEGA_KERNELS.get(path, path)), "peak_source": peak_src,
                       "bytes_per_launch": int(bytes_per_token), "us_per_launch": round(ms / K * 1e3, 1),
                       "note": "algorithmic bytes of one token (SURVEY 8d: weights + KV read/write + logits) / CUDA-event time per graph replay "
                               "(memset + megakernel + 1-thread state advance)"}

@@ -139,6 +139,9 @@ LB_API int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint
                          const float *hidden_in_dev, float *hidden_out_dev, float *logits_out);
 LB_API float *lb_context_hidden_buffer(lb_context *c);   /* device [max_batch][dim] scratch for hand-offs */
 LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
+/* which kernels a single-token Eval of this context runs: "ring" (TMA-ring megakernel), "mega" (register-fed megakernel),
+   "ring_q8" (Q8_0 ring megakernel) or "perop" (one kernel per op) — measurement aid, no reference counterpart */
+LB_API const char *lb_context_decode_path(lb_context *c);
 
 /* ---- tokenizer: ml.Tokenize (pkg/ml/ml.go:2761-2848) on the host; works without a GPU ---- */
 typedef struct lb_vocab lb_vocab;                                  /* = ml.Vocab (ml.go:2653-2657) */

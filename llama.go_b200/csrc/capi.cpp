@@ -198,6 +198,12 @@ int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t pa
 }
 float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
 void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }
+const char *lb_context_decode_path(lb_context *c) {
+    if (!c) return "";
+    if (c->c->use_ring_q8) return "ring_q8";
+    if (!c->c->use_mega) return "perop";
+    return c->c->use_ring ? "ring" : "mega";
+}
 
 // ---- pod batching ----
 lb_batch *lb_batch_create(lb_context **ctxs, uint32_t n) {

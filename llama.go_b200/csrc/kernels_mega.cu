@@ -228,7 +228,7 @@ __host__ __device__ constexpr int mg_rb(int V, int NM) { return (V * NM >= 10) ?
 template <int V, bool SWIGLU>
 __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const float *__restrict__ W3, uint32_t M, uint32_t K,
                                            const float4 (&xs)[V], float *out, const float *res, MegaShared &sh, unsigned *ctr,
-                                           const MegaPre &pre, uint32_t &pre_parity) {
+                                           const MegaPre &pre, uint32_t &pre_parity, bool peer_out = false) {
     constexpr int NM = SWIGLU ? 2 : 1;
     constexpr int RB = mg_rb(V, NM);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -291,6 +291,9 @@ __device__ __forceinline__ void gemv_phase(const float *__restrict__ W, const fl
             if (SWIGLU) v = __fmul_rn(silu_ref(s1), s3);
             else v = res ? __fadd_rn(s1, __ldcg(res + row)) : s1;
             out[row] = v;
+            // out is the NEXT pipeline stage's buffer on another GPU: the WRITING thread orders its own store at system scope
+            // (a fence by thread 0 after the CTA barrier does not cover other threads' stores still in flight over NVLink)
+            if (peer_out) __threadfence_system();
         }
         buf ^= 1;  // the other partial buffer is used next; this one is reused only after the next csync
     };
@@ -637,8 +640,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             float4 xf[VF];
             load_slice<VF>(p.act, ff, xf);
             // (the stage's last layer writes the residual into the next stage's x)
-            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, sh, sched + li * 4 + 3,
-                                  pre, pre_parity);
+            const bool to_peer = p.p2p_x_out != nullptr && li + 1 == p.n_layers;
+            gemv_phase<VF, false>(L.w2, nullptr, dim, ff, xf, to_peer ? p.p2p_x_out : p.x, p.y, sh, sched + li * 4 + 3, pre, pre_parity, to_peer);
         }
         if (pre_thread) {
             if (li + 1 < p.n_layers) mg_pre_issue(pre, p.layers[li + 1].wqkv, nullptr, 3 * dim, dim);

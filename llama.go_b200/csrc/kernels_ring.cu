@@ -267,7 +267,7 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
 // ---------------------------------------------------------------------------------------------------------
 template <int NM, int EPI, int NCH>
 __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], float *out, const float *res, RingPos &q, uint32_t phidx,
-                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t spin_ns) {
+                                        uint32_t ring_base, RingShared &sh, uint32_t n_slots, uint32_t spin_ns, bool peer_out = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t CH = ring_chunk(K, NCH);
     int buf = 0;
@@ -287,6 +287,10 @@ __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], 
             else if (EPI == 1) v = __fadd_rn(s1, __ldcg(res + row));
             else v = s1;
             out[row] = v;
+            // out is the NEXT pipeline stage's buffer on another GPU: the WRITING thread orders its own store at system scope
+            // (a fence by thread 0 after the CTA barrier does not cover other threads' stores still in flight over NVLink:
+            //  r02r, logits 6e-3 off with the fence in the grid barrier only)
+            if (peer_out) __threadfence_system();
         }
         buf ^= 1;   // the other buffer is written next; this one is reused only after the next ccsync
     };
@@ -698,7 +702,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) decode_ring_kernel(const RingPa
         {   // ---- P5: w2 + residual (llama.go:363-366); the stage's last layer writes the residual into the next stage's x
             float4 xf[NF][2];
             fill_plain<NF>(xf, p.act, ff);
-            consume<1, 1, NF>(ff, xf, (p.p2p_x_out && li + 1 == p.n_layers) ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring_base, sh, n_slots, p.spin_ns);
+            const bool to_peer = p.p2p_x_out != nullptr && li + 1 == p.n_layers;
+            consume<1, 1, NF>(ff, xf, to_peer ? p.p2p_x_out : p.x, p.y, pos, phidx++, ring_base, sh, n_slots, p.spin_ns, to_peer);
         }
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x, p.p2p_x_out != nullptr && li + 1 == p.n_layers, arr(li, 4));
