@@ -176,7 +176,10 @@ LB_API int  lb_nccl_version(void);
  * (CUDA IPC mapping) and raises a flag there, which the next stage's kernel waits for while it already streams its weights.
  * export: handles_out receives n x 128 bytes for this stage's n contexts; every rank exchanges them (any transport);
  * import: the bytes of the downstream stage (NULL on the last stage) and of the upstream stage (NULL on the first), before
- * the first lb_pipeline_decode.  Without import, lb_pipeline_decode uses NCCL send/recv as before; prefill always does. */
+ * the first lb_pipeline_decode.  Without import, lb_pipeline_decode uses NCCL send/recv as before; prefill always does.
+ * import also captures the stage's CUDA graph (its warm-up launch must not run once a peer is decoding).  Caller's contract:
+ * a barrier over all stages after import and after every lb_pipeline_prefill, before any stage calls lb_pipeline_decode —
+ * prefill is outside the hand-off's flag protocol (llama.go_b200/pipeline.py does both barriers). */
 LB_API int lb_pipeline_p2p_export(lb_context **ctxs, uint32_t n, void *handles_out);
 LB_API int lb_pipeline_p2p_import(lb_context **ctxs, uint32_t n, const void *downstream_handles, const void *upstream_handles);
 LB_API int lb_pipeline_p2p_disable(lb_context **ctxs, uint32_t n);   /* back to NCCL (e.g. another rank's import failed) */

@@ -144,13 +144,29 @@ void p2p_import(llama::Context **ctxs, uint32_t n_seq, const void *down, const v
             c->p2p_ack_out = static_cast<uint32_t *>(ptr);
         }
         c->p2p_ready = true;
+        // Capture the stage graph NOW, while no peer can be decoding yet (the caller's enable_p2p is collective and ends with
+        // a barrier).  ensure_stage_graph starts with an eager warm-up launch that runs outside the flag protocol and, on every
+        // stage but the first, overwrites this context's x with its own layer outputs: left to the first lb_pipeline_decode, it
+        // clobbered the step-0 residual an already-running upstream stage had deposited there (2-GPU run r02s: 9e-3 logits
+        // error on the 1 + 2 layer split, where stage 0 is the faster one).  The warm-up runs at the LAST cache position: the
+        // K/V row it writes is rewritten by the real step that reaches it before anything reads it.
+        c->state_host[0] = c->ctx_size - 1; c->state_host[1] = 0;
+        LB_CUDA(cudaMemcpyAsync(c->state_dev, c->state_host, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        c->ensure_stage_graph(c->stream);
+        LB_CUDA(cudaStreamSynchronize(c->stream));
     }
 }
 
 void p2p_disable(llama::Context **ctxs, uint32_t n_seq) {
     for (uint32_t s = 0; s < n_seq; s++) {
-        LB_CHECK(!ctxs[s]->stage_graph || !ctxs[s]->p2p_ready, "p2p_disable: the stage graph is already captured with the hand-off");
-        ctxs[s]->p2p_ready = false;
+        llama::Context *c = ctxs[s];
+        if (c->stage_graph && c->p2p_ready) {   // captured with the hand-off (p2p_import): drop it, the next decode captures the NCCL variant
+            LB_CUDA(cudaSetDevice(c->model->device));
+            LB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaGraphExecDestroy(c->stage_graph);
+            c->stage_graph = nullptr;
+        }
+        c->p2p_ready = false;
     }
 }
 

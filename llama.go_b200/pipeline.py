@@ -58,6 +58,7 @@ class Stage:
         self.ctxs = [llama.NewContext(self.model, ctx_size) for _ in range(n_seq)]
         self._arr = (C.c_void_p * n_seq)(*[c._h for c in self.ctxs])
         self.p2p = False
+        self._dist = None
 
     @property
     def is_first(self):
@@ -71,6 +72,11 @@ class Stage:
         """tokens [n_seq][n] (read on rank 0 only; other ranks may pass shape-compatible zeros)."""
         t = np.ascontiguousarray(tokens, dtype=np.uint32)
         check(lib().lb_pipeline_prefill(self._arr, len(self.ctxs), t.ctypes.data_as(_u32p), t.shape[1], past))
+        if self.p2p and self._dist is not None:
+            # the prefill is outside the decode hand-off's flag protocol: an upstream stage that is already decoding would store
+            # step 0's residual into an x buffer this stage's prefill kernels are still reading.  lb_pipeline_prefill returns
+            # with this rank's work complete; nobody decodes before every rank is here.
+            self._dist.barrier()
 
     def decode(self, tokens, past: int) -> float:
         """tokens [n_seq][steps]; returns CUDA-event ms on this rank."""
@@ -109,6 +115,7 @@ class Stage:
         t = torch.tensor([ok])
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         self.p2p = bool(t.item() == 1.0)
+        self._dist = dist if self.p2p else None
         if not self.p2p:
             try:
                 lib().lb_pipeline_p2p_disable(self._arr, n)
