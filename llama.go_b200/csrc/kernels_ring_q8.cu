@@ -96,6 +96,19 @@ __device__ __forceinline__ void mma_s8(int (&d)[4], uint32_t a0, uint32_t a1, ui
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
 }
 
+// explicit shared-space loads from 32-bit shared addresses: a generic pointer into the ring costs an S2R of the cluster CTA id
+// and an address-space conversion per load (SASS of the first version of this loop)
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+
 struct RQParams {
     const MegaLayerHost *layers;      // norm vectors and the KV slabs
     const RingQ8Layer *planes;        // [n_layers] tile-major decode planes of the layer's matrices
@@ -119,7 +132,7 @@ struct RQShared {
     double rope_cs[64][2];
     float fred[2][RQ_CWARPS / 2];
     float hbcast[2];
-    float part[2][RQ_CWARPS][16];     // [matrix][warp][row of the tile]
+    float part[2][2][RQ_CWARPS][16];  // [buffer][matrix][warp][row of the tile]
     float4 pv[RQ_CTHREADS];
     float mrg_m[RQ_MAX_ITEMS], mrg_l[RQ_MAX_ITEMS], mrg_w[RQ_MAX_ITEMS], mrg_inv[RQ_MAX_HEADS];
 };
@@ -368,62 +381,109 @@ __device__ __forceinline__ void merge_digits(const RQParams &p, uint32_t kp, int
 // Warp w takes blocks 2w and 2w + 1 of every slot (64 of its 1024 k) for all 16 rows; K-slices are combined
 // across the 16 warps per tile in a fixed order.
 // ---------------------------------------------------------------------------------------------------------
-template <int NM, int EPI>
+// KREG: number of 1024-column segments whose B fragments (activation digits + block scales) stay in registers for the whole
+// phase (K <= KREG * 1024; 0: reloaded from shared memory for every segment — what the kernel uses: with 17 warps per CTA the
+// register file allows 96 registers per thread, and 24 more live registers spill inside the slot loop).  Instruction diet of round 2 (ncu r02n: an HBM-bound
+// kernel with 49 % of its issue slots busy): full 16-row tiles and full 32-block records take a path without predicates whose
+// eight loads are immediates off two per-warp base registers; K-slice partials are double-buffered (one CTA barrier per tile).
+template <int NM, int EPI, int KREG>
 __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *dig, const float *xsc, float *out, const float *res,
                                         uint32_t &ph, RingPos &pos, const uint8_t *ring, RQShared &sh, uint32_t n_slots, uint32_t spin_ns) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t ring_s = smem_u32(ring), dig_s = smem_u32(dig), xsc_s = smem_u32(xsc);
     uint32_t r0, r1;
     cta_rows(M, ph++, r0, r1);
     const uint32_t nblk = K / 32, nseg = (K + RQ_SEGK - 1) / RQ_SEGK;
     // digit weights of this lane's two D columns (2t, 2t + 1): digits 0..3 live in columns 0..3, columns 4..7 are zero planes
     const float w0 = t == 0 ? 0.015625f : (t == 1 ? 9.5367431640625e-07f : 0.f);            // 2^-6, 2^-20
     const float w1 = t == 0 ? 1.220703125e-04f : (t == 1 ? 7.450580596923828e-09f : 0.f);   // 2^-13, 2^-27
+    auto bfrag = [&](uint32_t b, uint2 &bd, float &sx) {   // B fragment (digits) of block b: plane g (g < 4), 8 bytes at 8t
+        const bool ok = b < nblk;
+        bd = (g < 4 && ok) ? lds_u2(dig_s + (b * 4 + g) * 32 + t * 8) : make_uint2(0u, 0u);
+        sx = ok ? lds_f(xsc_s + b * 4) : 0.f;
+    };
+    constexpr int NR = KREG ? KREG : 1;
+    uint2 bdr[NR][2];
+    float sxr[NR][2];
+    if (KREG) {
+#pragma unroll
+        for (int sg = 0; sg < NR; sg++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) bfrag((uint32_t)sg * (RQ_SEGK / 32) + warp * 2 + j, bdr[sg][j], sxr[sg][j]);
+    }
+    // offsets inside a FULL record (16 rows, 32 blocks): int8 rows g / g + 8 of blocks 2w, 2w + 1; their scales
+    const uint32_t cA = ((uint32_t)warp * 2 * RQ_ROWS + g) * 32 + t * 8;
+    const uint32_t cD = (RQ_SEGK / 32) * RQ_BLKQ + ((uint32_t)warp * 2 * RQ_ROWS + g) * 4;
+    int buf = 0;
     for (uint32_t tile = r0; tile < r1; tile += RQ_ROWS) {
         const uint32_t rt = min((uint32_t)RQ_ROWS, r1 - tile);   // rows of this tile (the chunk's last tile may be short)
+        const bool full_tile = rt == RQ_ROWS;
         const bool lo_row = (uint32_t)g < rt, hi_row = (uint32_t)g + 8 < rt;
         float acc[NM][2];
 #pragma unroll
         for (int m = 0; m < NM; m++) acc[m][0] = acc[m][1] = 0.f;
-        for (uint32_t seg = 0; seg < nseg; seg++) {
-            // B fragments (digits) of this warp's two blocks: plane g (g < 4), 8 bytes at 8t
-            uint2 bd[2];
-            float sx[2];
+        auto slot_math = [&](int m, const uint2 (&qa)[2], const uint2 (&qb)[2], const float (&da)[2], const float (&db)[2],
+                             const uint2 (&bd)[2], const float (&sx)[2]) {
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const uint32_t b = seg * (RQ_SEGK / 32) + warp * 2 + j;
-                bd[j] = g < 4 ? *reinterpret_cast<const uint2 *>(dig + (b * 4 + g) * 32 + t * 8) : make_uint2(0u, 0u);
-                sx[j] = xsc[b];
+                int c[4];
+                mma_s8(c, qa[j].x, qb[j].x, qa[j].y, qb[j].y, bd[j].x, bd[j].y);
+                // (the s32 -> f32 conversions stay on the I2F pipe, which is otherwise idle: the bit-pattern trick — 2 IADD + the
+                //  offset folded into the FMA — moved them onto the ALU pipe, the busiest one: 437 vs 451 tok/s, r02o/r02q)
+                const float va = fmaf((float)c[1], w1, __fmul_rn((float)c[0], w0));   // row g:     this lane's two digit columns
+                const float vb = fmaf((float)c[3], w1, __fmul_rn((float)c[2], w0));   // row g + 8
+                acc[m][0] = fmaf(va, __fmul_rn(da[j], sx[j]), acc[m][0]);
+                acc[m][1] = fmaf(vb, __fmul_rn(db[j], sx[j]), acc[m][1]);
             }
+        };
+        auto do_seg = [&](uint32_t seg, const uint2 (&bd)[2], const float (&sx)[2]) {
+            const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));   // blocks in this record (the last segment may be short)
+            const bool fast = full_tile && nb == RQ_SEGK / 32;
 #pragma unroll
             for (int m = 0; m < NM; m++) {
                 mbar_wait(smem_u32(&sh.full[pos.slot]), pos.phase, spin_ns);
-                const uint8_t *sl = ring + (size_t)pos.slot * RQ_SLOT;
-                const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));   // blocks in this record (the last segment may be short)
+                const uint32_t sl = ring_s + pos.slot * RQ_SLOT;
                 uint2 qa[2], qb[2];
                 float da[2], db[2];
+                if (fast) {
+                    const uint32_t pa = sl + cA, pd = sl + cD;
+                    qa[0] = lds_u2(pa);                        // block 2w,     row g
+                    qb[0] = lds_u2(pa + 8 * 32);               //               row g + 8
+                    qa[1] = lds_u2(pa + RQ_BLKQ);              // block 2w + 1
+                    qb[1] = lds_u2(pa + RQ_BLKQ + 8 * 32);
+                    da[0] = lds_f(pd);
+                    db[0] = lds_f(pd + 8 * 4);
+                    da[1] = lds_f(pd + RQ_ROWS * 4);
+                    db[1] = lds_f(pd + RQ_ROWS * 4 + 8 * 4);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const uint32_t bl = warp * 2 + j;   // block inside the record: [bl][row < rt][32 int8], scales [bl][row] after the nb int8 blocks
-                    const bool live = bl < nb;
-                    qa[j] = live && lo_row ? *reinterpret_cast<const uint2 *>(sl + (bl * rt + g) * 32 + t * 8) : make_uint2(0u, 0u);        // row g, 8 int8
-                    qb[j] = live && hi_row ? *reinterpret_cast<const uint2 *>(sl + (bl * rt + g + 8) * 32 + t * 8) : make_uint2(0u, 0u);    // row g + 8
-                    da[j] = live && lo_row ? *reinterpret_cast<const float *>(sl + nb * rt * 32 + (bl * rt + g) * 4) : 0.f;
-                    db[j] = live && hi_row ? *reinterpret_cast<const float *>(sl + nb * rt * 32 + (bl * rt + g + 8) * 4) : 0.f;
+                    for (int j = 0; j < 2; j++) {
+                        const uint32_t bl = warp * 2 + j;   // block inside the record: [bl][row < rt][32 int8], scales [bl][row] after the nb int8 blocks
+                        const bool live = bl < nb;
+                        qa[j] = live && lo_row ? lds_u2(sl + (bl * rt + g) * 32 + t * 8) : make_uint2(0u, 0u);        // row g, 8 int8
+                        qb[j] = live && hi_row ? lds_u2(sl + (bl * rt + g + 8) * 32 + t * 8) : make_uint2(0u, 0u);    // row g + 8
+                        da[j] = live && lo_row ? lds_f(sl + nb * rt * 32 + (bl * rt + g) * 4) : 0.f;
+                        db[j] = live && hi_row ? lds_f(sl + nb * rt * 32 + (bl * rt + g + 8) * 4) : 0.f;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    int c[4];
-                    mma_s8(c, qa[j].x, qb[j].x, qa[j].y, qb[j].y, bd[j].x, bd[j].y);
-                    // (the s32 -> f32 conversions stay on the I2F pipe, which is otherwise idle: the bit-pattern trick — 2 IADD + the
-                    //  offset folded into the FMA — moved them onto the ALU pipe, the busiest one: 437 vs 451 tok/s, r02o/r02q)
-                    float va = fmaf((float)c[1], w1, __fmul_rn((float)c[0], w0));   // row g:     this lane's two digit columns
-                    float vb = fmaf((float)c[3], w1, __fmul_rn((float)c[2], w0));   // row g + 8
-                    acc[m][0] = fmaf(va, __fmul_rn(da[j], sx[j]), acc[m][0]);
-                    acc[m][1] = fmaf(vb, __fmul_rn(db[j], sx[j]), acc[m][1]);
-                }
+                slot_math(m, qa, qb, da, db, bd, sx);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sh.empty[pos.slot]));
                 pos.next(n_slots);
+            }
+        };
+        if (KREG) {
+#pragma unroll
+            for (int sg = 0; sg < NR; sg++)
+                if ((uint32_t)sg < nseg) do_seg((uint32_t)sg, bdr[sg], sxr[sg]);
+        } else {
+#pragma unroll 1
+            for (uint32_t seg = 0; seg < nseg; seg++) {
+                uint2 bd[2];
+                float sx[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) bfrag(seg * (RQ_SEGK / 32) + warp * 2 + j, bd[j], sx[j]);
+                do_seg(seg, bd, sx);
             }
         }
         // digits 0,1 (lanes t = 0) + digits 2,3 (t = 1): the block scale d_w * s is common to both, so the two lanes' sums
@@ -433,12 +493,13 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
             acc[m][0] += __shfl_xor_sync(0xffffffffu, acc[m][0], 1);
             acc[m][1] += __shfl_xor_sync(0xffffffffu, acc[m][1], 1);
         }
-        // ---- combine the 16 warps' K-slices of this tile (lanes t == 0 hold rows g and g + 8)
+        // ---- combine the 16 warps' K-slices of this tile (lanes t == 0 hold rows g and g + 8); double-buffered partials:
+        //      a buffer is rewritten two tiles later, after the next tile's barrier
         if (t == 0) {
 #pragma unroll
             for (int m = 0; m < NM; m++) {
-                sh.part[m][warp][g] = acc[m][0];
-                sh.part[m][warp][g + 8] = acc[m][1];
+                sh.part[buf][m][warp][g] = acc[m][0];
+                sh.part[buf][m][warp][g + 8] = acc[m][1];
             }
         }
         ccsync();
@@ -447,8 +508,8 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
             float s1 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int wv = 0; wv < RQ_CWARPS; wv++) {
-                s1 += sh.part[0][wv][threadIdx.x];
-                if (NM == 2) s3 += sh.part[NM - 1][wv][threadIdx.x];
+                s1 += sh.part[buf][0][wv][threadIdx.x];
+                if (NM == 2) s3 += sh.part[buf][NM - 1][wv][threadIdx.x];
             }
             if (row < r1) {
                 float v;
@@ -458,8 +519,9 @@ __device__ __forceinline__ void consume(uint32_t K, uint32_t M, const int8_t *di
                 out[row] = v;
             }
         }
-        ccsync();   // part[] is reused by the next tile
+        buf ^= 1;
     }
+    ccsync();   // the last tile's partials are read before the next phase's prologue reuses shared memory
 }
 
 // ---- attention phase: identical to kernels_mega.cu::attention_phase (items (head, split), two per CTA at a time)
@@ -648,7 +710,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         // ---- P1: rmsnorm * attention_norm, [wq;wk;wv] (llama.go:255-265)
         norm_digits(xin, L.attention_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 1);
-        consume<1, 0>(dim, 3 * dim, dig, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
+        consume<1, 0, 0>(dim, 3 * dim, dig, xsc, p.qkv, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 2);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 3);
@@ -659,20 +721,20 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
         stamp(li, 5);
         // ---- P3: merge the attention splits, wo + residual (llama.go:336-340)
         merge_digits<HD>(p, kp_dim, dig, xsc, sh);
-        consume<1, 1>(dim, dim, dig, xsc, p.y, xin, ph, pos, ring, sh, n_slots, p.spin_ns);
+        consume<1, 1, 0>(dim, dim, dig, xsc, p.y, xin, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 6);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 7);
         // ---- P4: rmsnorm * ffn_norm, silu(w1.)*(w3.) (llama.go:346-361)
         norm_digits(p.y, L.ffn_norm, dim, kp_dim, dig, xsc, sh);
         stamp(li, 8);
-        consume<2, 0>(dim, ff, dig, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
+        consume<2, 0, 0>(dim, ff, dig, xsc, p.act, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 9);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 10);
         // ---- P5: w2 + residual (llama.go:363-366)
         plain_digits(p.act, ff, kp_ff, dig, xsc);
-        consume<1, 1>(ff, dim, dig, xsc, p.x, p.y, ph, pos, ring, sh, n_slots, p.spin_ns);
+        consume<1, 1, 0>(ff, dim, dig, xsc, p.x, p.y, ph, pos, ring, sh, n_slots, p.spin_ns);
         stamp(li, 11);
         grid_barrier(p.barrier, target, gridDim.x);
         stamp(li, 12);
@@ -680,7 +742,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) decode_ring_q8_kernel(const RQP
     }
     if (p.final_norm) {  // final norm + lm_head (llama.go:374-384)
         norm_digits(xin, p.final_norm, dim, kp_dim, dig, xsc, sh);
-        consume<1, 0>(dim, p.vocab, dig, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
+        consume<1, 0, 0>(dim, p.vocab, dig, xsc, p.logits, nullptr, ph, pos, ring, sh, n_slots, p.spin_ns);
     }
 }
 
