@@ -254,17 +254,11 @@ __device__ __forceinline__ void fill_pass(float4 *xs, const float *src, uint32_t
     const int lane = threadIdx.x & 31, pod = lane >> 2, t = lane & 3;
     const uint32_t nf4 = nchunks * 32, B = p.B;
     const float sc = MODE == 1 ? sh.scale[pod] : 1.f;
-    for (uint32_t f = threadIdx.x; f < nf4; f += RP_CTHREADS) {
-        const uint32_t kk = k0 + (f >> 5) * 16 + t * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pod < (int)B) {
-            if (MODE == 0) v = ldcg4(src + (size_t)pod * ld + kk);
-            else if (MODE == 1) {
-                const float4 xv = ldcg4(sh.xrow[pod] + kk);
-                const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + kk));
-                v = make_float4(__fmul_rn(ww.x, __fmul_rn(xv.x, sc)), __fmul_rn(ww.y, __fmul_rn(xv.y, sc)),
-                                __fmul_rn(ww.z, __fmul_rn(xv.z, sc)), __fmul_rn(ww.w, __fmul_rn(xv.w, sc)));
-            } else {
+    if (MODE == 2) {
+        for (uint32_t f = threadIdx.x; f < nf4; f += RP_CTHREADS) {
+            const uint32_t kk = k0 + (f >> 5) * 16 + t * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pod < (int)B) {
                 const uint32_t S = p.splits, h = kk / HD, d = kk % HD, bh = pod * p.heads + h;
                 const float *po = p.part_o + (size_t)bh * S * HD + d;
                 for (uint32_t s = 0; s < S; s++) {
@@ -278,8 +272,39 @@ __device__ __forceinline__ void fill_pass(float4 *xs, const float *src, uint32_t
                 const float inv = sh.mrg_inv[bh];
                 v = make_float4(__fmul_rn(v.x, inv), __fmul_rn(v.y, inv), __fmul_rn(v.z, inv), __fmul_rn(v.w, inv));
             }
+            xs[f] = v;
         }
-        xs[f] = v;
+    } else {
+        // a pass is 8 float4 per thread: all of a batch's L2 loads are issued before the first use (a load -> store loop pays one
+        // L2 round trip per iteration: ncu r02n, 24 % of the kernel's warp samples on long_scoreboard)
+        constexpr int U = 8;
+        for (uint32_t f0 = threadIdx.x; f0 < nf4; f0 += U * RP_CTHREADS) {
+            float4 xv[U], ww[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t f = f0 + u * RP_CTHREADS, kk = k0 + (f >> 5) * 16 + t * 4;
+                xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ww[u] = xv[u];
+                if (f < nf4 && pod < (int)B) {
+                    if (MODE == 0) xv[u] = ldcg4(src + (size_t)pod * ld + kk);
+                    else {
+                        xv[u] = ldcg4(sh.xrow[pod] + kk);
+                        ww[u] = __ldg(reinterpret_cast<const float4 *>(w + kk));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t f = f0 + u * RP_CTHREADS;
+                if (f < nf4) {
+                    float4 v = xv[u];
+                    if (MODE == 1)
+                        v = make_float4(__fmul_rn(ww[u].x, __fmul_rn(v.x, sc)), __fmul_rn(ww[u].y, __fmul_rn(v.y, sc)),
+                                        __fmul_rn(ww[u].z, __fmul_rn(v.z, sc)), __fmul_rn(ww[u].w, __fmul_rn(v.w, sc)));
+                    xs[f] = v;
+                }
+            }
+        }
     }
     ccsync();
 }
@@ -290,10 +315,19 @@ __device__ __forceinline__ void rms_scales(uint32_t K, uint32_t B, RPShared &sh)
     const float *xr = pod < (int)B ? sh.xrow[pod] : nullptr;
     double acc = 0.0;
     if (xr) {
-        for (uint32_t f = threadIdx.x >> 5; f < K / 16; f += RP_CWARPS) {   // warp-strided chunks; lane (pod, t) takes 4 floats
-            const float4 v = ldcg4(xr + (size_t)f * 16 + t * 4);
-            acc += (double)__fmul_rn(v.x, v.x); acc += (double)__fmul_rn(v.y, v.y);
-            acc += (double)__fmul_rn(v.z, v.z); acc += (double)__fmul_rn(v.w, v.w);
+        constexpr int U = 8;   // loads per batch: one L2 round trip per 128 chunks instead of one per chunk
+        for (uint32_t f0 = threadIdx.x >> 5; f0 < K / 16; f0 += U * RP_CWARPS) {   // warp-strided chunks; lane (pod, t) takes 4 floats
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t f = f0 + u * RP_CWARPS;
+                v[u] = f < K / 16 ? ldcg4(xr + (size_t)f * 16 + t * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                acc += (double)__fmul_rn(v[u].x, v[u].x); acc += (double)__fmul_rn(v[u].y, v[u].y);
+                acc += (double)__fmul_rn(v[u].z, v[u].z); acc += (double)__fmul_rn(v[u].w, v[u].w);
+            }
         }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
