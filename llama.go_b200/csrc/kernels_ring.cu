@@ -237,6 +237,9 @@ __device__ __forceinline__ void produce(const float *W, const float *W3, uint32_
         }
         njobs++;
     };
+    // (Measured and rejected, r02y: bringing the REST of the short wo phase — 16 of a CTA's 28 rows do not fit in the ring — into L2
+    //  with cp.async.bulk.prefetch.L2 while the consumers are in the attention phase: 220.5 vs 223.1 tok/s, the wo phase no
+    //  shorter (13.7 us), barrier 1 longer.  Third L2-prefetch experiment without a gain on this part: r02a, r02j, r02y.)
     // two tickets in flight (an L2 atomic round trip under load is ~1 us = 2-3 rows of stream), the first drawn ~8 rows and the
     // second ~4 rows before the static block ends — late enough that a CTA only takes tickets when it is about to need them
     const uint32_t r0 = blockIdx.x * Q, r1 = r0 + Q;
