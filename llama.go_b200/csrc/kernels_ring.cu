@@ -804,7 +804,7 @@ void decode_ring(const MegaParamsHost &h, cudaStream_t st) {
         if (n >= 2 && n < p.n_slots) { smem -= (size_t)(p.n_slots - n) * RG_SLOT; p.n_slots = n; }
     }
     p.trace = reinterpret_cast<unsigned long long *>(h.trace);
-    static const uint32_t spin_ns = getenv("LB_RING_SPIN_NS") ? (uint32_t)atoi(getenv("LB_RING_SPIN_NS")) : 0u;
+    static const uint32_t spin_ns = getenv("LB_RING_SPIN_NS") ? (uint32_t)atoi(getenv("LB_RING_SPIN_NS")) : 50u;   // no effect on an un-capped box (r02q); fewer polls = less power under the 1 kW cap
     p.spin_ns = spin_ns;
     p.p2p_flags = h.p2p_flags; p.p2p_wait_in = h.p2p_wait_in ? 1u : 0u;
     p.p2p_x_out = h.p2p_x_out; p.p2p_flag_out = h.p2p_flag_out; p.p2p_ack_out = h.p2p_ack_out;
