@@ -142,6 +142,12 @@ LB_API void  *lb_context_stream(lb_context *c);          /* cudaStream_t */
 /* which kernels a single-token Eval of this context runs: "ring" (TMA-ring megakernel), "mega" (register-fed megakernel),
    "ring_q8" (Q8_0 ring megakernel) or "perop" (one kernel per op) — measurement aid, no reference counterpart */
 LB_API const char *lb_context_decode_path(lb_context *c);
+/* work split / data layout of the ring megakernels, evaluated on the HOST by the same functions the kernels use (test aid, no
+   GPU needed, no reference counterpart).  kind 0: FP32 ring, K = a -> out {chunks per row, floats per chunk};
+   kind 1: Q8 ring, matrix [a x b], rows of work slot c -> out {r0, r1};  kind 2: Q8 decode plane, matrix [a x b], tile of row c ->
+   out {first row, height, byte offset of the tile's first record (low, high)};  kind 3: pods ring, a rows, work slot c ->
+   out {r0, r1, chunk index or 0xFFFFFFFF}.  Returns 0, or -1 for shapes the kernel does not take. */
+LB_API int lb_layout_query(uint32_t kind, uint32_t a, uint32_t b, uint32_t c, uint32_t out[4]);
 
 /* ---- tokenizer: ml.Tokenize (pkg/ml/ml.go:2761-2848) on the host; works without a GPU ---- */
 typedef struct lb_vocab lb_vocab;                                  /* = ml.Vocab (ml.go:2653-2657) */

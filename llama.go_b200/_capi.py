@@ -59,6 +59,7 @@ _SIGS = {
     "lb_context_hidden_buffer": (_vp, [_vp]),
     "lb_context_stream": (_vp, [_vp]),
     "lb_context_decode_path": (C.c_char_p, [_vp]),
+    "lb_layout_query": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
     "lb_vocab_create": (_vp, [C.c_uint32]),
     "lb_vocab_free": (None, [_vp]),
     "lb_vocab_set": (C.c_int, [_vp, C.c_uint32, C.c_char_p, C.c_uint32, C.c_float]),

@@ -198,6 +198,17 @@ int lb_eval_stage(lb_context *c, const uint32_t *tokens, uint32_t n, uint32_t pa
 }
 float *lb_context_hidden_buffer(lb_context *c) { return c ? c->c->x : nullptr; }
 void *lb_context_stream(lb_context *c) { return c ? (void *)c->c->stream : nullptr; }
+int lb_layout_query(uint32_t kind, uint32_t a, uint32_t b, uint32_t c, uint32_t out[4]) {
+    if (!out) return -1;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    switch (kind) {
+        case 0: lb::k::ring_layout_query(a, out); return 0;
+        case 1: return lb::k::ring_q8_layout_query(0, a, b, c, out) ? 0 : -1;
+        case 2: return lb::k::ring_q8_layout_query(1, a, b, c, out) ? 0 : -1;
+        case 3: lb::k::ring_pods_layout_query(a, c, out); return 0;
+        default: return -1;
+    }
+}
 const char *lb_context_decode_path(lb_context *c) {
     if (!c) return "";
     if (c->c->use_ring_q8) return "ring_q8";

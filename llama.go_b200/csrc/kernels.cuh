@@ -145,6 +145,9 @@ void decode_mega(const MegaParamsHost &p, cudaStream_t st);
 // ---- the same token as one persistent kernel fed by a producer warp through a shared-memory ring of TMA bulk copies
 //      (kernels_ring.cu): the weight stream runs ahead across phases and grid barriers
 bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx);
+void ring_layout_query(uint32_t K, uint32_t *out);                                             // CPU layout tests
+bool ring_q8_layout_query(uint32_t what, uint32_t M, uint32_t K, uint32_t idx, uint32_t *out);
+void ring_pods_layout_query(uint32_t M, uint32_t idx, uint32_t *out);
 void decode_ring(const MegaParamsHost &p, cudaStream_t st);
 
 // ---- Q8_0 single-token decode on the TMA ring with the MulMat on the INT8 tensor cores (kernels_ring_q8.cu)

@@ -775,6 +775,12 @@ static uint32_t ring_plan(uint32_t heads, uint32_t ctx, size_t *smem_out) {
 
 }  // namespace
 
+// layout query for the CPU tests: K -> out {chunks per row, floats per chunk}
+void ring_layout_query(uint32_t K, uint32_t *out) {
+    out[0] = ring_nch(K);
+    out[1] = ring_chunk(K, out[0]);
+}
+
 bool decode_ring_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
     if (heads == 0 || dim % heads || heads > (uint32_t)RG_MAX_HEADS) return false;
     if (((uint64_t)(ff > vocab ? ff : vocab) > 3ull * dim ? (ff > vocab ? ff : vocab) : 3ull * dim) >= 65535ull * kNumSMs / 2) return false;   // job counts are 16-bit

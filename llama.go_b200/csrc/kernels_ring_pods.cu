@@ -141,21 +141,24 @@ struct RowPlan {
     uint32_t r0, r1;      // rows [r0, r1)
     uint32_t chunk;       // >= 0: index into the chunked map; 0xFFFFFFFF: use the matrix-bounded map with absolute rows
 };
-__device__ __forceinline__ RowPlan cta_rows_plan(uint32_t M, uint32_t ph) {
+__host__ __device__ __forceinline__ RowPlan rp_rows_plan(uint32_t M, uint32_t c, uint32_t grid) {   // work slot c of `grid` (host: CPU layout test)
     RowPlan rp;
-    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x;
-    if (M >= RP_ROWS * gridDim.x) {
-        const uint32_t R = (M + gridDim.x - 1) / gridDim.x, nfull = M / R;
-        rp.r0 = min(M, c * R);
-        rp.r1 = min(M, rp.r0 + R);
+    if (M >= RP_ROWS * grid) {
+        const uint32_t R = (M + grid - 1) / grid, nfull = M / R;
+        rp.r0 = M < c * R ? M : c * R;
+        rp.r1 = M < rp.r0 + R ? M : rp.r0 + R;
         rp.chunk = c < nfull ? c : 0xFFFFFFFFu;
     } else {
         const uint32_t ntiles = (M + RP_ROWS - 1) / RP_ROWS;
-        rp.r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RP_ROWS);
-        rp.r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RP_ROWS);
+        const uint32_t a = (uint32_t)(((uint64_t)ntiles * c) / grid) * RP_ROWS, b = (uint32_t)(((uint64_t)ntiles * (c + 1)) / grid) * RP_ROWS;
+        rp.r0 = M < a ? M : a;
+        rp.r1 = M < b ? M : b;
         rp.chunk = 0xFFFFFFFFu;
     }
     return rp;
+}
+__device__ __forceinline__ RowPlan cta_rows_plan(uint32_t M, uint32_t ph) {
+    return rp_rows_plan(M, (blockIdx.x + ph * 37u) % gridDim.x, gridDim.x);
 }
 
 struct RPParams {
@@ -728,6 +731,12 @@ static cudaError_t launch(const RPParams &p, const RPMaps &maps, size_t smem, cu
 }
 
 }  // namespace
+
+// layout query for the CPU tests: rows and chunk index of work slot `idx` -> out {r0, r1, chunk}
+void ring_pods_layout_query(uint32_t M, uint32_t idx, uint32_t *out) {
+    const RowPlan rp = rp_rows_plan(M, idx, kNumSMs);
+    out[0] = rp.r0; out[1] = rp.r1; out[2] = rp.chunk;
+}
 
 bool decode_ring_pods_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
     if (heads == 0 || dim % heads) return false;

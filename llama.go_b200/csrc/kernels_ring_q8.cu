@@ -168,16 +168,33 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, un
 __host__ __device__ __forceinline__ uint32_t rq_chunk_rows(uint32_t M, uint32_t grid) {   // 0: plain 16-row tiles
     return M >= RQ_ROWS * grid ? (M + grid - 1) / grid : 0u;
 }
-__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
-    const uint32_t c = (blockIdx.x + ph * 37u) % gridDim.x, R = rq_chunk_rows(M, gridDim.x);
+// rows [r0, r1) of work slot c of `grid` (host + device: the same function drives the producer, the consumers and the CPU layout test)
+__host__ __device__ __forceinline__ void rq_rows_of(uint32_t M, uint32_t c, uint32_t grid, uint32_t &r0, uint32_t &r1) {
+    const uint32_t R = rq_chunk_rows(M, grid);
     if (R) {
-        r0 = min(M, c * R);
-        r1 = min(M, r0 + R);
+        r0 = M < c * R ? M : c * R;
+        r1 = M < r0 + R ? M : r0 + R;
     } else {
         const uint32_t ntiles = (M + RQ_ROWS - 1) / RQ_ROWS;
-        r0 = min(M, (uint32_t)(((uint64_t)ntiles * c) / gridDim.x) * RQ_ROWS);
-        r1 = min(M, (uint32_t)(((uint64_t)ntiles * (c + 1)) / gridDim.x) * RQ_ROWS);
+        const uint32_t a = (uint32_t)(((uint64_t)ntiles * c) / grid) * RQ_ROWS, b = (uint32_t)(((uint64_t)ntiles * (c + 1)) / grid) * RQ_ROWS;
+        r0 = M < a ? M : a;
+        r1 = M < b ? M : b;
     }
+}
+// the tile of the decode plane that holds `row`: first row g0, height rt (<= 16)
+__host__ __device__ __forceinline__ void rq_group_of(uint32_t M, uint32_t row, uint32_t grid, uint32_t &g0, uint32_t &rt) {
+    const uint32_t R = rq_chunk_rows(M, grid);
+    if (R) {
+        const uint32_t c = row / R, cend = M < (c + 1) * R ? M : (c + 1) * R;
+        g0 = c * R + ((row - c * R) / RQ_ROWS) * RQ_ROWS;
+        rt = cend - g0 < RQ_ROWS ? cend - g0 : RQ_ROWS;
+    } else {
+        g0 = (row / RQ_ROWS) * RQ_ROWS;
+        rt = M - g0 < RQ_ROWS ? M - g0 : RQ_ROWS;
+    }
+}
+__device__ __forceinline__ void cta_rows(uint32_t M, uint32_t ph, uint32_t &r0, uint32_t &r1) {
+    rq_rows_of(M, (blockIdx.x + ph * 37u) % gridDim.x, gridDim.x, r0, r1);
 }
 
 struct RingPos {
@@ -788,7 +805,7 @@ static uint32_t q8_plan(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t ctx,
 // scales [blocks of the segment][16 rows] f32 FOLLOW the segment's int8 blocks:  record(tile, seg) at
 // (tile * K/32 + seg * 32) * 576 bytes = [nb][16][32] int8 | [nb][16] f32.  Rows >= `rows` of the last tile are zero.
 __global__ void q8_to_tile_major_kernel(const int8_t *__restrict__ q, const float *__restrict__ d, uint8_t *__restrict__ plane,
-                                        uint32_t M, uint32_t row0, uint32_t nrows, uint32_t K, uint32_t R) {
+                                        uint32_t M, uint32_t row0, uint32_t nrows, uint32_t K, uint32_t grid) {
     const uint32_t nblk = K / 32;
     const size_t n = (size_t)nrows * nblk * 8, stride = (size_t)gridDim.x * blockDim.x;   // one thread per (row, block, 4-byte group)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -796,16 +813,9 @@ __global__ void q8_to_tile_major_kernel(const int8_t *__restrict__ q, const floa
         const size_t rb = i >> 3;
         const uint32_t b = (uint32_t)(rb % nblk), lr = (uint32_t)(rb / nblk);   // lr: row inside q/d (the tensor's own planes)
         const uint32_t row = row0 + lr;                                           // row inside the whole matrix
-        // the tile this row belongs to (rq_chunk_rows / cta_rows): first row g0, height rt
+        // the tile this row belongs to: first row g0, height rt
         uint32_t g0, rt;
-        if (R) {
-            const uint32_t c = row / R, cend = min(M, (c + 1) * R);
-            g0 = c * R + ((row - c * R) / RQ_ROWS) * RQ_ROWS;
-            rt = min((uint32_t)RQ_ROWS, cend - g0);
-        } else {
-            g0 = (row / RQ_ROWS) * RQ_ROWS;
-            rt = min((uint32_t)RQ_ROWS, M - g0);
-        }
+        rq_group_of(M, row, grid, g0, rt);
         const uint32_t r = row - g0, seg = b / (RQ_SEGK / 32), bl = b % (RQ_SEGK / 32);
         const uint32_t nb = min(RQ_SEGK / 32, nblk - seg * (RQ_SEGK / 32));
         uint8_t *rec = plane + ((size_t)g0 * nblk + (size_t)seg * (RQ_SEGK / 32) * rt) * 36u;
@@ -831,8 +841,22 @@ void q8_to_tile_major(const int8_t *q, const float *d, uint8_t *plane, uint32_t 
     if (!rq_layout_ok(M, K)) return;   // shapes the ring megakernel does not take (decode_ring_q8_supported): no decode plane
     LB_CHECK(row0 % 4 == 0 && nrows % 4 == 0 && row0 + nrows <= M, "q8_to_tile_major: bad row range");
     if (!nrows) return;
-    q8_to_tile_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, plane, M, row0, nrows, K, rq_chunk_rows(M, kNumSMs));
+    q8_to_tile_major_kernel<<<148 * 8, 256, 0, st>>>(q, d, plane, M, row0, nrows, K, (uint32_t)kNumSMs);
     LB_LAUNCH_CHECK();
+}
+
+// layout queries for the CPU tests (tests/test_layouts.py): what=0 rows of work slot `idx` -> out {r0, r1};
+// what=1 tile of row `idx` -> out {g0, rt, byte offset of the tile's segment-0 record (low, high 32 bits)}
+bool ring_q8_layout_query(uint32_t what, uint32_t M, uint32_t K, uint32_t idx, uint32_t *out) {
+    if (!rq_layout_ok(M, K)) return false;
+    if (what == 0) {
+        rq_rows_of(M, idx, kNumSMs, out[0], out[1]);
+    } else {
+        rq_group_of(M, idx, kNumSMs, out[0], out[1]);
+        const uint64_t off = (uint64_t)out[0] * (K / 32) * 36u;
+        out[2] = (uint32_t)off; out[3] = (uint32_t)(off >> 32);
+    }
+    return true;
 }
 
 bool decode_ring_q8_supported(uint32_t dim, uint32_t ff, uint32_t heads, uint32_t vocab, uint32_t ctx) {
