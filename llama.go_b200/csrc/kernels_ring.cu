@@ -89,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
         if (backoff_ns) __nanosleep(backoff_ns);   // (consumers) polling burns issue slots and power: the decode step runs into the 1 kW cap
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (1u << 27)) __trap();   // ~8 s at ~60 ns per failed poll: longer than any legitimate wait for a peer stage (p2p_wait traps after ~10 s)
     }
 }
 struct RingPos {   // ring entry and mbarrier phase parity of the next slot (no division on the hot path: ncu r02n)
@@ -310,7 +310,7 @@ __device__ __forceinline__ void consume(uint32_t K, const float4 (&xs)[NCH][2], 
                 if (dj != 0xFFFFu && j >= dj) { over = true; break; }
                 if (got) break;
                 if (spin_ns) __nanosleep(spin_ns);
-                if (++spins > (1u << 24)) __trap();
+                if (++spins > (1u << 27)) __trap();   // ~8 s at ~60 ns per failed poll: longer than any legitimate wait for a peer stage (p2p_wait traps after ~10 s)
             }
             if (over) break;
         }
